@@ -1,0 +1,418 @@
+// C ABI of libadrt_b200.so (declared in include/adrt_b200.h): argument
+// validation, dtype dispatch, the per-stage fallback drivers, the cached
+// interp_to_cart tables and the host-pointer (NumPy) pipeline.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+namespace adrt_b200 {
+
+std::atomic<int64_t> g_launch_count{0};
+std::atomic<int> g_mode{0};
+
+static thread_local char t_error[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int check_image(const void *in, const void *out, int64_t B, int64_t n, int dtype)
+{
+    ADRT_REQUIRE(in && out, "null pointer argument");
+    ADRT_REQUIRE(dtype_ok(dtype), "unsupported dtype %d", dtype);
+    ADRT_REQUIRE(B > 0, "batch must be positive, got %lld", (long long)B);
+    ADRT_REQUIRE(is_pow2(n) && n <= kMaxN, "n must be a power of two <= %lld, got %lld", (long long)kMaxN, (long long)n);
+    return ADRT_B200_OK;
+}
+
+// ---- per-stage drivers (also the oracle-like definition of the full ops) -----
+template <typename T>
+int adrt_by_steps(const T *in, T *out, int64_t B, int64_t n, T *ws, cudaStream_t s)
+{
+    const int K = num_iters(n);
+    T *a = (K % 2 == 0) ? out : ws, *b = (K % 2 == 0) ? ws : out;
+    int rc = launch_adrt_init<T>(in, a, B, n, s);
+    for (int i = 0; i < K && rc == ADRT_B200_OK; ++i) {
+        rc = launch_adrt_step<T>(a, b, B, n, i, s);
+        T *t = a; a = b; b = t;
+    }
+    return rc;
+}
+
+template <typename T>
+int bdrt_by_steps(const T *in, T *out, int64_t B, int64_t n, T *ws, cudaStream_t s)
+{
+    const int K = num_iters(n);
+    if (K == 0) {
+        ADRT_CUDA_CHECK(cudaMemcpyAsync(out, in, sizeof(T) * sino_elems(B, n), cudaMemcpyDeviceToDevice, s));
+        return ADRT_B200_OK;
+    }
+    const T *src = in;
+    T *a = (K % 2 == 1) ? out : ws, *b = (K % 2 == 1) ? ws : out;
+    int rc = ADRT_B200_OK;
+    for (int i = 0; i < K && rc == ADRT_B200_OK; ++i) {
+        rc = launch_bdrt_step<T>(src, a, B, n, i, /*core_semantics=*/true, s);
+        src = a;
+        T *t = a; a = b; b = t;
+    }
+    return rc;
+}
+
+template <typename T>
+int iadrt_by_stages(const T *in, T *out, int64_t B, int64_t n, T *ws, cudaStream_t s)
+{
+    const int K = num_iters(n);
+    if (K == 0) {
+        ADRT_CUDA_CHECK(cudaMemcpyAsync(out, in, sizeof(T) * sino_elems(B, n), cudaMemcpyDeviceToDevice, s));
+        return ADRT_B200_OK;
+    }
+    const T *src = in;
+    T *a = (K % 2 == 1) ? out : ws, *b = (K % 2 == 1) ? ws : out;
+    int rc = ADRT_B200_OK;
+    for (int i = 0; i < K && rc == ADRT_B200_OK; ++i) {
+        rc = launch_iadrt_stage<T>(src, a, B, n, i, s);
+        src = a;
+        T *t = a; a = b; b = t;
+    }
+    return rc;
+}
+
+template <typename T>
+size_t adrt_ws_elems(int64_t B, int64_t n)
+{
+    if (g_mode.load() == 0) {
+        size_t f = fused_adrt_workspace_elems<T>(B, n);
+        if (f != (size_t)-1) return f;
+    }
+    return num_iters(n) == 0 ? 0 : (size_t)sino_elems(B, n);
+}
+
+template <typename T>
+size_t bdrt_ws_elems(int64_t B, int64_t n)
+{
+    if (g_mode.load() == 0) {
+        size_t f = fused_bdrt_workspace_elems<T>(B, n);
+        if (f != (size_t)-1) return f;
+    }
+    return num_iters(n) <= 1 ? 0 : (size_t)sino_elems(B, n);
+}
+
+template <typename T>
+int adrt_impl(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_bytes, cudaStream_t s)
+{
+    const size_t need = adrt_ws_elems<T>(B, n) * sizeof(T);
+    if (need > 0 && (!ws || ws_bytes < need)) {
+        set_error("adrt workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return ADRT_B200_EWORKSPACE;
+    }
+    if (g_mode.load() == 0) {
+        bool handled = false;
+        int rc = fused_adrt<T>(in, out, B, n, ws, ws_bytes / sizeof(T), s, &handled);
+        if (rc != ADRT_B200_OK || handled) return rc;
+    }
+    return adrt_by_steps<T>(in, out, B, n, ws, s);
+}
+
+template <typename T>
+int bdrt_impl(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_bytes, cudaStream_t s)
+{
+    const size_t need = bdrt_ws_elems<T>(B, n) * sizeof(T);
+    if (need > 0 && (!ws || ws_bytes < need)) {
+        set_error("bdrt workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return ADRT_B200_EWORKSPACE;
+    }
+    if (g_mode.load() == 0) {
+        bool handled = false;
+        int rc = fused_bdrt<T>(in, out, B, n, ws, ws_bytes / sizeof(T), s, &handled);
+        if (rc != ADRT_B200_OK || handled) return rc;
+    }
+    return bdrt_by_steps<T>(in, out, B, n, ws, s);
+}
+
+// ---- interp_to_cart tables ------------------------------------------------------
+// Host half of adrt_cdefs_interp_adrtcart.hpp:61-114 with float_index = float
+// (adrt_cdefs_py.cpp:638): everything that involves libm transcendentals
+// (tanf, cosf) depends on the output column only, so it is evaluated here on
+// the host with the very expressions the reference uses and shipped as O(n)
+// tables; the device finishes with correctly-rounded IEEE div/mul/add and
+// exact roundf, which are bit-identical to the host's.
+struct InterpTable {
+    float *t = nullptr;         // [n]   t_left * lerp(-1,1,offset/(n-1))
+    int32_t *base = nullptr;    // [4n]  q*D*n + si
+    float *h_base = nullptr;    // [4n]  0.5f + tan/2
+    float *cosv = nullptr;      // [4n]  cosf(th0)
+    int32_t *sgn = nullptr;     // [4n]  1 if even quadrant else 0
+    void *factor = nullptr;     // [4n]  T
+};
+
+std::mutex g_interp_mu;
+std::map<std::tuple<int, int64_t, int>, InterpTable> g_interp_cache;
+
+int get_interp_table(int device, int64_t n, int dtype, cudaStream_t s, InterpTable *out)
+{
+    std::lock_guard<std::mutex> lock(g_interp_mu);
+    auto key = std::make_tuple(device, n, dtype);
+    auto it = g_interp_cache.find(key);
+    if (it != g_interp_cache.end()) { *out = it->second; return ADRT_B200_OK; }
+
+    const int64_t D = 2 * n - 1, W = 4 * n;
+    std::vector<float> t(n), hb(W), cv(W);
+    std::vector<int32_t> base(W), sg(W);
+    std::vector<float> f32(W);
+    std::vector<double> f64(W);
+    const float sqrt2_2 = (float)1.41421356237309504880168872420969808L / 2.0f;
+    const float pi = (float)3.14159265358979323846264338327950288L;
+    const float pi_2 = pi / 2.0f, pi_4 = pi / 4.0f, pi_8 = pi / 8.0f;
+    const float t_left = sqrt2_2 - (sqrt2_2 / (float)n);
+    const float th_left = pi_2 - (pi_8 / (float)n);
+    for (int64_t off = 0; off < n; ++off) {
+        const volatile float of = (float)off / (float)(n - 1);
+        const volatile float p1 = of * 1.0f;
+        const volatile float p2 = (1.0f - of) * -1.0f;
+        const volatile float l = p1 + p2;   // std::lerp(-1, 1, of), opposite-sign branch
+        t[off] = t_left * l;
+    }
+    for (int64_t ang = 0; ang < W; ++ang) {
+        const volatile float af = (float)ang / (float)(W - 1);
+        const volatile float p1 = af * -1.0f;
+        const volatile float p2 = (1.0f - af) * 1.0f;
+        const volatile float l = p1 + p2;   // std::lerp(1, -1, af)
+        const float th = th_left * l;
+        float qf = -th / pi_4;
+        qf = qf < -2.0f ? -2.0f : (qf > 1.0f ? 1.0f : qf);
+        const int q = (int)(std::floor(qf) + 2);
+        const float th0 = pi_4 - std::fabs(std::fabs(th) - pi_4);
+        float tant = std::tan(th0);
+        tant = tant < 0.0f ? 0.0f : (tant > 1.0f ? 1.0f : tant);
+        const float si = std::round(tant * (float)(n - 1));
+        {
+            const volatile float sa = si / (float)(n - 1);
+            const volatile float sq = sa * sa;
+            f32[ang] = std::sqrt(sq + 1.0f);
+            const volatile double sad = (double)si / (double)(n - 1);
+            const volatile double sqd = sad * sad;
+            f64[ang] = std::sqrt(sqd + 1.0);
+        }
+        const volatile float half_tan = tant / 2.0f;
+        hb[ang] = 0.5f + half_tan;
+        cv[ang] = std::cos(th0);
+        sg[ang] = (q % 2 == 0) ? 1 : 0;
+        base[ang] = (int32_t)((int64_t)q * D * n + (int64_t)si);
+    }
+    InterpTable tab;
+    const size_t fsz = dtype == ADRT_B200_F64 ? sizeof(double) : sizeof(float);
+    ADRT_CUDA_CHECK(cudaMalloc(&tab.t, n * sizeof(float)));
+    ADRT_CUDA_CHECK(cudaMalloc(&tab.base, W * sizeof(int32_t)));
+    ADRT_CUDA_CHECK(cudaMalloc(&tab.h_base, W * sizeof(float)));
+    ADRT_CUDA_CHECK(cudaMalloc(&tab.cosv, W * sizeof(float)));
+    ADRT_CUDA_CHECK(cudaMalloc(&tab.sgn, W * sizeof(int32_t)));
+    ADRT_CUDA_CHECK(cudaMalloc(&tab.factor, W * fsz));
+    // synchronous copies from pageable memory: the vectors die at scope exit
+    ADRT_CUDA_CHECK(cudaMemcpy(tab.t, t.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    ADRT_CUDA_CHECK(cudaMemcpy(tab.base, base.data(), W * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ADRT_CUDA_CHECK(cudaMemcpy(tab.h_base, hb.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+    ADRT_CUDA_CHECK(cudaMemcpy(tab.cosv, cv.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+    ADRT_CUDA_CHECK(cudaMemcpy(tab.sgn, sg.data(), W * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ADRT_CUDA_CHECK(cudaMemcpy(tab.factor, dtype == ADRT_B200_F64 ? (void *)f64.data() : (void *)f32.data(),
+                               W * fsz, cudaMemcpyHostToDevice));
+    (void)s;
+    g_interp_cache[key] = tab;
+    *out = tab;
+    return ADRT_B200_OK;
+}
+
+}  // namespace
+
+}  // namespace adrt_b200
+
+using namespace adrt_b200;
+
+#define DISPATCH(dtype, CALL_F32, CALL_F64) ((dtype) == ADRT_B200_F64 ? (CALL_F64) : (CALL_F32))
+
+extern "C" {
+
+int adrt_b200_version(void) { return 100; }
+const char *adrt_b200_last_error(void) { return t_error; }
+int adrt_b200_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return c;
+}
+void adrt_b200_set_mode(int mode) { g_mode.store(mode); }
+int adrt_b200_get_mode(void) { return g_mode.load(); }
+int64_t adrt_b200_launch_count(void) { return g_launch_count.load(); }
+int adrt_b200_num_iters(int64_t n) { return num_iters(n); }
+
+size_t adrt_b200_adrt_workspace_bytes(int64_t B, int64_t n, int dtype)
+{
+    if (B <= 0 || !is_pow2(n) || !dtype_ok(dtype)) return 0;
+    return DISPATCH(dtype, adrt_ws_elems<float>(B, n) * 4, adrt_ws_elems<double>(B, n) * 8);
+}
+
+int adrt_b200_adrt(const void *in, void *out, int64_t B, int64_t n, int dtype, void *ws, size_t ws_bytes, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    return DISPATCH(dtype,
+                    adrt_impl<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes, as_stream(stream)),
+                    adrt_impl<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes, as_stream(stream)));
+}
+
+size_t adrt_b200_bdrt_workspace_bytes(int64_t B, int64_t n, int dtype)
+{
+    if (B <= 0 || !is_pow2(n) || !dtype_ok(dtype)) return 0;
+    return DISPATCH(dtype, bdrt_ws_elems<float>(B, n) * 4, bdrt_ws_elems<double>(B, n) * 8);
+}
+
+int adrt_b200_bdrt(const void *in, void *out, int64_t B, int64_t n, int dtype, void *ws, size_t ws_bytes, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    return DISPATCH(dtype,
+                    bdrt_impl<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes, as_stream(stream)),
+                    bdrt_impl<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes, as_stream(stream)));
+}
+
+int adrt_b200_adrt_step(const void *in, void *out, int64_t B, int64_t n, int step, int dtype, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    ADRT_REQUIRE(step >= 0 && step < num_iters(n), "step %d is out of range for n=%lld", step, (long long)n);
+    ADRT_REQUIRE(in != out, "adrt_step cannot run in place");
+    return DISPATCH(dtype,
+                    launch_adrt_step<float>((const float *)in, (float *)out, B, n, step, as_stream(stream)),
+                    launch_adrt_step<double>((const double *)in, (double *)out, B, n, step, as_stream(stream)));
+}
+
+int adrt_b200_bdrt_step(const void *in, void *out, int64_t B, int64_t n, int step, int dtype, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    ADRT_REQUIRE(step >= 0 && step < num_iters(n), "step %d is out of range for n=%lld", step, (long long)n);
+    ADRT_REQUIRE(in != out, "bdrt_step cannot run in place");
+    return DISPATCH(dtype,
+                    launch_bdrt_step<float>((const float *)in, (float *)out, B, n, step, false, as_stream(stream)),
+                    launch_bdrt_step<double>((const double *)in, (double *)out, B, n, step, false, as_stream(stream)));
+}
+
+int adrt_b200_adrt_init(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    return DISPATCH(dtype,
+                    launch_adrt_init<float>((const float *)in, (float *)out, B, n, as_stream(stream)),
+                    launch_adrt_init<double>((const double *)in, (double *)out, B, n, as_stream(stream)));
+}
+
+size_t adrt_b200_iadrt_workspace_bytes(int64_t B, int64_t n, int dtype)
+{
+    if (B <= 0 || !is_pow2(n) || !dtype_ok(dtype)) return 0;
+    return num_iters(n) <= 1 ? 0 : (size_t)sino_elems(B, n) * dtype_size(dtype);
+}
+
+int adrt_b200_iadrt(const void *in, void *out, int64_t B, int64_t n, int dtype, void *ws, size_t ws_bytes, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    const size_t need = adrt_b200_iadrt_workspace_bytes(B, n, dtype);
+    if (need > 0 && (!ws || ws_bytes < need)) {
+        set_error("iadrt workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return ADRT_B200_EWORKSPACE;
+    }
+    return DISPATCH(dtype,
+                    iadrt_by_stages<float>((const float *)in, (float *)out, B, n, (float *)ws, as_stream(stream)),
+                    iadrt_by_stages<double>((const double *)in, (double *)out, B, n, (double *)ws, as_stream(stream)));
+}
+
+int adrt_b200_fmg_restriction(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream)
+{
+    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0, "bad argument");
+    ADRT_REQUIRE(n >= 2 && n % 2 == 0 && n <= kMaxN, "restriction needs even n >= 2, got %lld", (long long)n);
+    return DISPATCH(dtype,
+                    launch_fmg_restriction<float>((const float *)in, (float *)out, B, n, as_stream(stream)),
+                    launch_fmg_restriction<double>((const double *)in, (double *)out, B, n, as_stream(stream)));
+}
+
+int adrt_b200_fmg_prolongation(const void *in, void *out, int64_t B, int64_t h, int64_t w, int dtype, void *stream)
+{
+    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0 && h > 0 && w > 0, "bad argument");
+    return DISPATCH(dtype,
+                    launch_fmg_prolongation<float>((const float *)in, (float *)out, B, h, w, as_stream(stream)),
+                    launch_fmg_prolongation<double>((const double *)in, (double *)out, B, h, w, as_stream(stream)));
+}
+
+int adrt_b200_fmg_highpass(const void *in, void *out, int64_t B, int64_t h, int64_t w, int dtype, void *stream)
+{
+    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0, "bad argument");
+    ADRT_REQUIRE(h >= 2 && w >= 2, "array is too small to high-pass filter");
+    return DISPATCH(dtype,
+                    launch_fmg_highpass<float>((const float *)in, (float *)out, B, h, w, as_stream(stream)),
+                    launch_fmg_highpass<double>((const double *)in, (double *)out, B, h, w, as_stream(stream)));
+}
+
+int adrt_b200_interp_to_cart(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    ADRT_REQUIRE(n >= 2, "interp_to_cart needs n >= 2");
+    int device = 0;
+    ADRT_CUDA_CHECK(cudaGetDevice(&device));
+    InterpTable tab;
+    rc = get_interp_table(device, n, dtype, as_stream(stream), &tab);
+    if (rc) return rc;
+    return DISPATCH(dtype,
+                    launch_interp_to_cart<float>((const float *)in, (float *)out, tab.t, tab.base, tab.h_base, tab.cosv,
+                                                 tab.sgn, (const float *)tab.factor, B, n, as_stream(stream)),
+                    launch_interp_to_cart<double>((const double *)in, (double *)out, tab.t, tab.base, tab.h_base, tab.cosv,
+                                                  tab.sgn, (const double *)tab.factor, B, n, as_stream(stream)));
+}
+
+int adrt_b200_truncate(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream)
+{
+    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
+    return DISPATCH(dtype,
+                    launch_truncate<float>((const float *)in, (float *)out, B, n, as_stream(stream)),
+                    launch_truncate<double>((const double *)in, (double *)out, B, n, as_stream(stream)));
+}
+
+int adrt_b200_truncate_mean(const void *in, void *out, int64_t B, int64_t n, double divisor, int dtype, void *stream)
+{
+    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
+    return DISPATCH(dtype,
+                    launch_truncate_mean<float>((const float *)in, (float *)out, B, n, (float)divisor, as_stream(stream)),
+                    launch_truncate_mean<double>((const double *)in, (double *)out, B, n, divisor, as_stream(stream)));
+}
+
+int adrt_b200_sub(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream)
+{
+    ADRT_REQUIRE(a && b && out && dtype_ok(dtype) && count > 0, "bad argument");
+    return DISPATCH(dtype,
+                    launch_binary<float>((const float *)a, (const float *)b, (float *)out, count, 0, as_stream(stream)),
+                    launch_binary<double>((const double *)a, (const double *)b, (double *)out, count, 0, as_stream(stream)));
+}
+
+int adrt_b200_add(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream)
+{
+    ADRT_REQUIRE(a && b && out && dtype_ok(dtype) && count > 0, "bad argument");
+    return DISPATCH(dtype,
+                    launch_binary<float>((const float *)a, (const float *)b, (float *)out, count, 1, as_stream(stream)),
+                    launch_binary<double>((const double *)a, (const double *)b, (double *)out, count, 1, as_stream(stream)));
+}
+
+}  // extern "C"

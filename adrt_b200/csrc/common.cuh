@@ -1,0 +1,79 @@
+// Shared host/device helpers for the adrt_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/adrt_b200.h"
+
+namespace adrt_b200 {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launch_count;
+extern std::atomic<int> g_mode;
+
+#define ADRT_CUDA_CHECK(expr)                                                          \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            ::adrt_b200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                   __FILE__, __LINE__);                                \
+            return ADRT_B200_ECUDA;                                                    \
+        }                                                                              \
+    } while (0)
+
+#define ADRT_LAUNCH_CHECK()                                                            \
+    do {                                                                               \
+        ::adrt_b200::g_launch_count.fetch_add(1, std::memory_order_relaxed);           \
+        ADRT_CUDA_CHECK(cudaGetLastError());                                           \
+    } while (0)
+
+#define ADRT_REQUIRE(cond, ...)                                                        \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            ::adrt_b200::set_error(__VA_ARGS__);                                       \
+            return ADRT_B200_EINVAL;                                                   \
+        }                                                                              \
+    } while (0)
+
+// ---- shape helpers (adrt_cdefs_common.cpp:140-142, 176-192) -------------------
+inline bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+inline int num_iters(int64_t n)
+{
+    if (n <= 0) return 0;
+    int bw = 0;
+    for (uint64_t v = (uint64_t)n; v; v >>= 1) ++bw;
+    return bw - (is_pow2(n) ? 1 : 0);
+}
+inline size_t dtype_size(int dtype) { return dtype == ADRT_B200_F64 ? 8 : 4; }
+inline bool dtype_ok(int dtype) { return dtype == ADRT_B200_F32 || dtype == ADRT_B200_F64; }
+// Largest image side the kernels index with 32-bit in-plane offsets: D*n < 2^31.
+constexpr int64_t kMaxN = 16384;
+
+inline int64_t sino_elems(int64_t B, int64_t n) { return B * 4 * (2 * n - 1) * n; }
+
+// ---- per-dtype launchers implemented in the .cu files --------------------------
+template <typename T> int launch_adrt_init(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s);
+template <typename T> int launch_adrt_step(const T *in, T *out, int64_t B, int64_t n, int step, cudaStream_t s);
+template <typename T> int launch_bdrt_step(const T *in, T *out, int64_t B, int64_t n, int step, bool core_semantics, cudaStream_t s);
+template <typename T> int launch_iadrt_stage(const T *in, T *out, int64_t B, int64_t n, int stage, cudaStream_t s);
+template <typename T> int launch_fmg_restriction(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s);
+template <typename T> int launch_fmg_prolongation(const T *in, T *out, int64_t B, int64_t h, int64_t w, cudaStream_t s);
+template <typename T> int launch_fmg_highpass(const T *in, T *out, int64_t B, int64_t h, int64_t w, cudaStream_t s);
+template <typename T> int launch_interp_to_cart(const T *in, T *out, const float *t, const int32_t *base, const float *h_base, const float *cosv, const int32_t *sgn, const T *factor, int64_t B, int64_t n, cudaStream_t s);
+template <typename T> int launch_truncate(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s);
+template <typename T> int launch_truncate_mean(const T *in, T *out, int64_t B, int64_t n, T divisor, cudaStream_t s);
+template <typename T> int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStream_t s);
+
+// Fused multi-stage paths (fused_adrt.cu).  Return ADRT_B200_OK or an error;
+// `handled` is false when the shape is left to the per-stage path.
+template <typename T> size_t fused_adrt_workspace_elems(int64_t B, int64_t n);
+template <typename T> size_t fused_bdrt_workspace_elems(int64_t B, int64_t n);
+template <typename T> int fused_adrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
+template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
+
+}  // namespace adrt_b200

@@ -1,0 +1,418 @@
+// One-kernel-per-stage operators in the public Q-layout (B,4,D,n), D = 2n-1.
+//
+// These implement the reference's single-step API (adrt_step / bdrt_step),
+// adrt_init, the exact inverse iadrt, the Press FMG operators, the
+// interp_to_cart gather and the elementwise glue of the multigrid driver.
+// They are simple streaming kernels (every element read/written once per
+// stage, c is the contiguous, coalesced axis).  The fast full transforms
+// live in fused_adrt.cu.
+//
+// Bit-exactness rules (SURVEY.md section 8a "exactness"): exactly one IEEE add
+// of the two named operands per output, a copy where the reference copies.
+// A copy is expressed as `x + (-0.0)`, which is the identity for every x
+// including -0.0 (x + (+0.0) would turn -0.0 into +0.0).  nvcc never contracts
+// a lone add, and -fmad=false is set for the whole library anyway.
+#include "common.cuh"
+
+namespace adrt_b200 {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__host__ __device__ inline int ilog2(int64_t n)
+{
+    int k = 0;
+    while ((int64_t(1) << k) < n) ++k;
+    return k;
+}
+
+// grid: x over in-plane chunks, y over planes (looped when > 65535)
+inline dim3 plane_grid(int64_t plane_elems, int64_t planes)
+{
+    int64_t gx = (plane_elems + kThreads - 1) / kThreads;
+    int64_t gy = planes < 65535 ? planes : 65535;
+    return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+// ---- adrt_init: core.py:169-176 / adrt_cdefs_adrt.hpp:124-186 -----------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+adrt_init_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int logn)
+{
+    const int64_t D = 2 * (int64_t)n - 1;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= D * n) return;
+    const int d = (int)(idx >> logn), c = (int)(idx & (n - 1));
+    for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
+        const int q = (int)(p & 3);
+        const T *img = in + (p >> 2) * (int64_t)n * n;
+        T v = T(0);
+        if (d < n) {
+            int r, k;
+            switch (q) {
+            case 0: r = c; k = n - 1 - d; break;
+            case 1: r = n - 1 - d; k = c; break;
+            case 2: r = d; k = c; break;
+            default: r = n - 1 - c; k = n - 1 - d; break;
+            }
+            v = img[(int64_t)r * n + k];
+        }
+        out[p * D * n + idx] = v;
+    }
+}
+
+// ---- adrt_step: adrt_cdefs_adrt.hpp:215-258 -----------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+adrt_step_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int logn, int iter)
+{
+    const int64_t D = 2 * (int64_t)n - 1;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= D * n) return;
+    const int d = (int)(idx >> logn), c = (int)(idx & (n - 1));
+    const int e = 1 << iter;
+    const int a = c & (2 * e - 1);
+    const int base = c - a;  // k * 2e
+    const int cA = base + (a >> 1);
+    const int cB = cA + e;
+    const int sh = (a + 1) >> 1;
+    for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
+        const T *I = in + p * D * n;
+        const T av = I[(int64_t)d * n + cA];
+        const T bv = (d >= sh) ? I[(int64_t)(d - sh) * n + cB] : T(-0.0);
+        out[p * D * n + idx] = av + bv;
+    }
+}
+
+// ---- bdrt_step: adrt_cdefs_bdrt.hpp:190-244 (step semantics) and --------------
+// ---- bdrt_core: adrt_cdefs_bdrt.hpp:55-116 (core semantics) -------------------
+// step semantics: missing operands are +0 and are still added (aval=0; bval=0).
+// core semantics: last valid row is a copy of la_val, rows past it are +0.
+template <typename T, bool kCore>
+__global__ void __launch_bounds__(kThreads)
+bdrt_step_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int logn, int adrt_iter)
+{
+    const int64_t D = 2 * (int64_t)n - 1;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= D * n) return;
+    const int d = (int)(idx >> logn), c = (int)(idx & (n - 1));
+    const int e = 1 << adrt_iter;
+    const int cb = c >> adrt_iter, ci = c & (e - 1);
+    const int beta = 2 * (ci + e * (cb >> 1));
+    const bool odd = cb & 1;
+    const int64_t r = odd ? (int64_t)d + ci : d;
+    for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
+        const T *I = in + p * D * n;
+        T av, bv;
+        if (!odd) {
+            av = I[r * n + beta];
+            bv = I[r * n + beta + 1];
+        } else {
+            av = (r < D) ? I[r * n + beta] : T(0.0);
+            bv = (r + 1 < D) ? I[(r + 1) * n + beta + 1] : (kCore ? T(-0.0) : T(0.0));
+        }
+        out[p * D * n + idx] = av + bv;
+    }
+}
+
+// ---- iadrt stage: adrt_cdefs_iadrt.hpp:52-105 in the Q-layout -----------------
+// One thread per (plane, output column); the offset axis is walked serially
+// from D-1 down (the reference's "must be serial" loop, iadrt.hpp:73-98) with
+// the running value kept in a register.  Adjacent threads own adjacent
+// columns, so every load and store is coalesced.
+template <typename T>
+__global__ void __launch_bounds__(128)
+iadrt_stage_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int stage)
+{
+    const int64_t D = 2 * (int64_t)n - 1;
+    const int co = blockIdx.x * 128 + threadIdx.x;
+    if (co >= n) return;
+    const int Cin = n >> stage, C = Cin >> 1;
+    const int l = co / C, col = co - l * C;
+    const int A = (l >> 1) * Cin + 2 * col;
+    const bool even = (l & 1) == 0;
+    for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
+        const T *I = in + p * D * n;
+        T *O = out + p * D * n;
+        T prev = T(0);
+        for (int64_t d = D - 1; d >= 0; --d) {
+            T val = T(0);
+            if (even) {
+                val += I[d * n + A];
+                if (d + 1 < D) val -= I[(d + 1) * n + A + 1];
+            } else if (d + 1 + col < D) {
+                val += I[(d + 1 + col) * n + A + 1];
+                val -= I[(d + 1 + col) * n + A];
+            }
+            if (d + 1 < D) val += prev;
+            O[d * n + co] = val;
+            prev = val;
+        }
+    }
+}
+
+// ---- Press FMG operators: adrt_cdefs_fmg.hpp ----------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+fmg_restriction_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n)
+{
+    const int64_t D = 2 * (int64_t)n - 1, R = n - 1, C = n / 2;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= R * C) return;
+    const int64_t r = idx / C, c = idx - r * C;
+    for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
+        const T *I = in + p * D * n;
+        const T va = I[(2 * r) * n + 2 * c];
+        const T vb = I[(2 * r + 1) * n + 2 * c];
+        out[p * R * C + idx] = (va + vb) / T(4);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+fmg_prolongation_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int64_t h, int64_t w)
+{
+    const int64_t W2 = 2 * w, H2 = 2 * h;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= H2 * W2) return;
+    const int64_t r = idx / W2, c = idx - r * W2;
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y)
+        out[b * H2 * W2 + idx] = in[b * h * w + (r >> 1) * w + (c >> 1)];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+fmg_highpass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int64_t h, int64_t w)
+{
+    const T ca = T(-0.0625), cb = T(-0.125), cc = T(0.75);
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= h * w) return;
+    const int64_t r = idx / w, c = idx - r * w;
+    const int64_t pr = (r == 0 ? 1 : r - 1), nr = (r == h - 1 ? r - 1 : r + 1);
+    const int64_t pc = (c == 0 ? 1 : c - 1), nc = (c == w - 1 ? c - 1 : c + 1);
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        const T *I = in + b * h * w;
+        // every product is rounded on its own (no FMA), then summed column by
+        // column exactly like fmg.hpp:129,150,167
+        const T v11 = ca * I[pr * w + pc], v12 = cb * I[pr * w + c], v13 = ca * I[pr * w + nc];
+        const T v21 = cb * I[r * w + pc], v22 = cc * I[r * w + c], v23 = cb * I[r * w + nc];
+        const T v31 = ca * I[nr * w + pc], v32 = cb * I[nr * w + c], v33 = ca * I[nr * w + nc];
+        out[b * h * w + idx] = ((v11 + v21) + v31) + ((v12 + v22) + v32) + ((v13 + v23) + v33);
+    }
+}
+
+// ---- interp_to_cart: adrt_cdefs_interp_adrtcart.hpp:61-114 --------------------
+// The per-column transcendental pieces come from the host tables built in
+// api.cu (get_interp_table); this kernel finishes the index computation with
+// IEEE-exact float ops in the reference's order (interp.hpp:97-100):
+//   h0 = (0.5 + tan/2) + ((sgn >= 0 ? t : -t) / cos(th0))
+//   hi = (round(h0 * 2n) - 1) / 2
+// and gathers factor * in[q, floor(hi), si] (0 when hi is out of range).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+interp_kernel(const T *__restrict__ in, T *__restrict__ out, const float *__restrict__ tt,
+              const int32_t *__restrict__ base, const float *__restrict__ h_base,
+              const float *__restrict__ cosv, const int32_t *__restrict__ sgn,
+              const T *__restrict__ factor, int64_t B, int n, int logn)
+{
+    const int64_t D = 2 * (int64_t)n - 1, N = (int64_t)n * 4 * n;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= N) return;
+    const int off = (int)(idx >> (logn + 2)), ang = (int)(idx & (4 * n - 1));
+    const float t = tt[off];
+    const float ts = sgn[ang] ? t : -t;
+    const float h0 = __fadd_rn(h_base[ang], __fdiv_rn(ts, cosv[ang]));
+    const float hi = __fdiv_rn(__fadd_rn(roundf(__fmul_rn(h0, (float)(2 * n))), -1.0f), 2.0f);
+    const bool ok = hi >= 0.0f && hi < (float)D;
+    const int64_t src = ok ? (int64_t)base[ang] + (int64_t)hi * n : 0;
+    const T f = factor[ang];
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        T v = T(0);
+        if (ok) v = f * in[b * 4 * D * n + src];
+        out[b * N + idx] = v;
+    }
+}
+
+// ---- truncate (utils.py:231-242) and truncate+divide+mean (core.py:329) -------
+template <typename T>
+__device__ inline T truncate_load(const T *plane0, int q, int r, int c, int n, int64_t D)
+{
+    // T0 = flip_rows(a0[:n,:n])^T  -> T0[r,c] = a0[n-1-c, r]
+    // T1 = flip_rows(a1[:n,:n])    -> T1[r,c] = a1[n-1-r, c]
+    // T2 = a2[:n,:n]
+    // T3 = flip_both(a3[:n,:n])^T  -> T3[r,c] = a3[n-1-c, n-1-r]
+    int d, k;
+    switch (q) {
+    case 0: d = n - 1 - c; k = r; break;
+    case 1: d = n - 1 - r; k = c; break;
+    case 2: d = r; k = c; break;
+    default: d = n - 1 - c; k = n - 1 - r; break;
+    }
+    return plane0[((int64_t)q * D + d) * n + k];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+truncate_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int logn)
+{
+    const int64_t D = 2 * (int64_t)n - 1;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (int64_t)n * n) return;
+    const int r = (int)(idx >> logn), c = (int)(idx & (n - 1));
+    for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
+        const int q = (int)(p & 3);
+        out[p * n * n + idx] = truncate_load(in + (p >> 2) * 4 * D * n, q, r, c, n, D);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+truncate_mean_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int n, int logn, T divisor)
+{
+    const int64_t D = 2 * (int64_t)n - 1;
+    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (int64_t)n * n) return;
+    const int r = (int)(idx >> logn), c = (int)(idx & (n - 1));
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        const T *I = in + b * 4 * D * n;
+        const T t0 = truncate_load(I, 0, r, c, n, D) / divisor;
+        const T t1 = truncate_load(I, 1, r, c, n, D) / divisor;
+        const T t2 = truncate_load(I, 2, r, c, n, D) / divisor;
+        const T t3 = truncate_load(I, 3, r, c, n, D) / divisor;
+        out[b * n * n + idx] = (((t0 + t1) + t2) + t3) / T(4);
+    }
+}
+
+template <typename T, int kOp>
+__global__ void __launch_bounds__(kThreads)
+binary_kernel(const T *a, const T *b, T *out, int64_t count)  // out may alias a or b
+{
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads)
+        out[i] = kOp == 0 ? a[i] - b[i] : a[i] + b[i];
+}
+
+}  // namespace
+
+// ---- launchers ------------------------------------------------------------------
+template <typename T>
+int launch_adrt_init(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s)
+{
+    const int64_t D = 2 * n - 1;
+    adrt_init_kernel<T><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n));
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_adrt_step(const T *in, T *out, int64_t B, int64_t n, int step, cudaStream_t s)
+{
+    const int64_t D = 2 * n - 1;
+    adrt_step_kernel<T><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), step);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_bdrt_step(const T *in, T *out, int64_t B, int64_t n, int step, bool core_semantics, cudaStream_t s)
+{
+    const int64_t D = 2 * n - 1;
+    const int adrt_iter = num_iters(n) - 1 - step;
+    if (core_semantics)
+        bdrt_step_kernel<T, true><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
+    else
+        bdrt_step_kernel<T, false><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_iadrt_stage(const T *in, T *out, int64_t B, int64_t n, int stage, cudaStream_t s)
+{
+    const int64_t planes = B * 4;
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)(planes < 65535 ? planes : 65535), 1);
+    iadrt_stage_kernel<T><<<grid, 128, 0, s>>>(in, out, planes, (int)n, stage);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_fmg_restriction(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s)
+{
+    fmg_restriction_kernel<T><<<plane_grid((n - 1) * (n / 2), B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_fmg_prolongation(const T *in, T *out, int64_t B, int64_t h, int64_t w, cudaStream_t s)
+{
+    fmg_prolongation_kernel<T><<<plane_grid(4 * h * w, B), kThreads, 0, s>>>(in, out, B, h, w);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_fmg_highpass(const T *in, T *out, int64_t B, int64_t h, int64_t w, cudaStream_t s)
+{
+    fmg_highpass_kernel<T><<<plane_grid(h * w, B), kThreads, 0, s>>>(in, out, B, h, w);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_interp_to_cart(const T *in, T *out, const float *t, const int32_t *base, const float *h_base,
+                          const float *cosv, const int32_t *sgn, const T *factor, int64_t B, int64_t n,
+                          cudaStream_t s)
+{
+    interp_kernel<T><<<plane_grid(4 * n * n, B), kThreads, 0, s>>>(in, out, t, base, h_base, cosv, sgn, factor, B, (int)n, ilog2(n));
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_truncate(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s)
+{
+    truncate_kernel<T><<<plane_grid(n * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n));
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_truncate_mean(const T *in, T *out, int64_t B, int64_t n, T divisor, cudaStream_t s)
+{
+    truncate_mean_kernel<T><<<plane_grid(n * n, B), kThreads, 0, s>>>(in, out, B, (int)n, ilog2(n), divisor);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStream_t s)
+{
+    int64_t blocks = (count + kThreads - 1) / kThreads;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    if (blocks < 1) blocks = 1;
+    if (op == 0)
+        binary_kernel<T, 0><<<(unsigned)blocks, kThreads, 0, s>>>(a, b, out, count);
+    else
+        binary_kernel<T, 1><<<(unsigned)blocks, kThreads, 0, s>>>(a, b, out, count);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+#define INSTANTIATE(T)                                                                                  \
+    template int launch_adrt_init<T>(const T *, T *, int64_t, int64_t, cudaStream_t);                  \
+    template int launch_adrt_step<T>(const T *, T *, int64_t, int64_t, int, cudaStream_t);             \
+    template int launch_bdrt_step<T>(const T *, T *, int64_t, int64_t, int, bool, cudaStream_t);       \
+    template int launch_iadrt_stage<T>(const T *, T *, int64_t, int64_t, int, cudaStream_t);           \
+    template int launch_fmg_restriction<T>(const T *, T *, int64_t, int64_t, cudaStream_t);            \
+    template int launch_fmg_prolongation<T>(const T *, T *, int64_t, int64_t, int64_t, cudaStream_t);  \
+    template int launch_fmg_highpass<T>(const T *, T *, int64_t, int64_t, int64_t, cudaStream_t);      \
+    template int launch_interp_to_cart<T>(const T *, T *, const float *, const int32_t *, const float *, const float *, const int32_t *, const T *, int64_t, int64_t, cudaStream_t); \
+    template int launch_truncate<T>(const T *, T *, int64_t, int64_t, cudaStream_t);                   \
+    template int launch_truncate_mean<T>(const T *, T *, int64_t, int64_t, T, cudaStream_t);           \
+    template int launch_binary<T>(const T *, const T *, T *, int64_t, int, cudaStream_t);
+INSTANTIATE(float)
+INSTANTIATE(double)
+
+}  // namespace adrt_b200

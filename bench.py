@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Headline benchmark: ADRT forward + bdrt throughput (Gpixel/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--batch B] [--n SIDE] [--dtype f32|f64]
+
+One "step" = ``y = adrt(x)`` followed by ``z = bdrt(y)`` on one batch of
+synthetic images (BASELINE.json metric).  Default workload is
+the headline configuration ``64 x 2048^2 float32`` per GPU; with N > 1 (one
+process per GPU under torchrun) every rank transforms its own batch and no
+data-path collective is involved (batch items never interact), so the run is
+weak-scaled: value = N * B * n^2 / max-over-ranks time.
+
+Printed JSON (rank 0, one line):
+  value        device-resident Gpixel/s (x, y, z live in HBM; CUDA-event timed)
+  e2e          same metric through the NumPy-facing host API with pinned host
+               buffers, H2D + D2H inside the timed region
+  roofline     algorithmic bytes (25 n^2 - 12 n) * s * B of one step / measured
+               step time, against MEASURED_PEAKS.json's copy bandwidth
+  cpu_baseline the unmodified reference (oracle/_ref, C++/OpenMP) on this box's
+               host cores, bounded sample of the same workload
+``--impl reference`` times only that CPU reference and prints the same line
+shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "adrt_fwd_plus_bdrt_throughput"
+UNIT = "Gpixel/s"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def algorithmic_bytes(B: int, n: int, itemsize: int) -> int:
+    """Compulsory traffic of adrt + bdrt: every input read once, every output
+    written once = (n^2 + S) + 2 S elements per image, S = 4 (2n-1) n."""
+    return (25 * n * n - 12 * n) * itemsize * B
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------
+# CPU reference timing (oracle/_ref = the reference's own C++/OpenMP core)
+# --------------------------------------------------------------------------------
+def time_reference(n: int, np_dtype, budget_s: float, max_images: int, seed: int = 0):
+    """Time adrt_ref.adrt + adrt_ref.bdrt on a bounded batch; returns
+    (gpixel_per_s, images, seconds, kind, threads)."""
+    import numpy as np
+
+    threads = host_cores()
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    from oracle import ref_loader
+
+    if ref_loader.have_ref_cdefs():
+        ref = ref_loader.load_ref_cdefs()
+        kind = "reference"
+        fwd, bwd = ref.adrt, ref.bdrt
+    else:  # the plain-C port (single threaded)
+        from oracle import oracle as O
+
+        kind, threads = "port", 1
+        fwd, bwd = O.adrt, O.bdrt
+    rng = np.random.default_rng(seed)
+
+    def run(b):
+        x = rng.random((b, n, n), dtype=np.float32).astype(np_dtype, copy=False)
+        t0 = time.perf_counter()
+        y = fwd(x)
+        z = bwd(y)
+        dt = time.perf_counter() - t0
+        del y, z
+        return dt
+
+    t1 = run(1)  # also warms the thread pool / page faults
+    t1 = min(t1, run(1))
+    images = int(max(1, min(max_images, budget_s / max(t1, 1e-6))))
+    # keep host memory bounded: the reference needs ~3 sinograms per call
+    chunk = max(1, min(images, 8))
+    total, done = 0.0, 0
+    while done < images:
+        b = min(chunk, images - done)
+        total += run(b)
+        done += b
+    return images * n * n / total / 1e9, images, total, kind, threads
+
+
+def reference_arm(args, np_dtype):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    per_step_budget = max(2.0, min(20.0, 90.0 / (steps + args.warmup)))
+    vals, imgs, secs = [], 0, 0.0
+    kind, threads = "reference", host_cores()
+    for i in range(args.warmup + steps):
+        v, im, s, kind, threads = time_reference(args.n, np_dtype, per_step_budget, args.batch, seed=i)
+        if i >= args.warmup:
+            vals.append(v)
+            imgs, secs = im, s
+    value = sum(vals) / len(vals)
+    ms = 1e3 * (args.batch * args.n * args.n / 1e9) / value
+    sample = f"{imgs} of {args.batch} images of {args.n}^2 {args.dtype} per step ({secs:.2f} s), adrt+bdrt, OMP threads={threads}"
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {
+        "workload": f"adrt.adrt + adrt.bdrt on {args.batch} x {args.n}^2 {args.dtype} per GPU",
+        "batch_per_gpu": args.batch, "n": args.n,
+        "global_batch": args.batch * args.gpus,
+        "parallelism": f"batch-sharded x{args.gpus}, no collectives",
+        "l2": "inputs larger than L2 (image batch and sinogram are GBs); no explicit flush",
+    }
+
+
+# --------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+        0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+        0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": s[len(s) // 2] if s else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+# --------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------
+def ours(args, np_dtype):
+    import numpy as np
+    import torch
+
+    import adrt_b200 as adrt
+    from adrt_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    adrt.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    B, n = args.batch, args.n
+    tdtype = torch.float32 if args.dtype == "f32" else torch.float64
+    itemsize = 4 if args.dtype == "f32" else 8
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.rand((B, n, n), device=dev, dtype=tdtype, generator=g)
+    y = torch.empty((B, 4, 2 * n - 1, n), device=dev, dtype=tdtype)
+    z = torch.empty_like(y)
+
+    def step():
+        adrt.adrt(x, out=y)
+        adrt.bdrt(y, out=z)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    # per-transform split (not part of the timed region)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record(); adrt.adrt(x, out=y); ev[1].record(); adrt.bdrt(y, out=z); ev[2].record()
+    torch.cuda.synchronize()
+    t_adrt_ms, t_bdrt_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.adrt_b200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = lib.adrt_b200_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / args.steps
+    value = world * B * n * n / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the NumPy-facing API, pinned host buffers ----------
+    e2e = None
+    if not args.no_e2e:
+        del z
+        torch.cuda.empty_cache()
+        try:
+            hx = torch.empty((B, n, n), dtype=tdtype).pin_memory()
+            hy = torch.empty((B, 4, 2 * n - 1, n), dtype=tdtype).pin_memory()
+            hz = torch.empty((B, 4, 2 * n - 1, n), dtype=tdtype).pin_memory()
+            hx.copy_(x.cpu())
+            nx, ny, nz = hx.numpy(), hy.numpy(), hz.numpy()
+            e2e_steps = max(1, min(args.steps, args.e2e_steps))
+            adrt.adrt(nx, out=ny); adrt.bdrt(ny, out=nz)  # warm the staging buffers
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                adrt.adrt(nx, out=ny)
+                adrt.bdrt(ny, out=nz)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt_step = float(dt.item()) / e2e_steps
+            e2e = {
+                "value": world * B * n * n / dt_step / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": int(nx.nbytes + ny.nbytes),
+                "d2h_bytes_per_step": int(ny.nbytes + nz.nbytes),
+                "ms_per_step": dt_step * 1e3, "steps": e2e_steps,
+                "api": "adrt_b200.adrt / adrt_b200.bdrt on pinned numpy.ndarray (adrt_b200_host_adrt / _bdrt)",
+            }
+            # end-to-end result check on one image against the device-resident result
+            assert np.array_equal(ny[0], y[0].cpu().numpy()), "host path and device path disagree"
+        except Exception as exc:  # report, never fake
+            e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    abytes = algorithmic_bytes(B, n, itemsize)
+    achieved = abytes / (ms_step * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "kernel": "whole step (adrt then bdrt kernels of one batch on one GPU)",
+        "algorithmic_bytes_per_step": abytes,
+        "split": {
+            "adrt_ms": t_adrt_ms, "bdrt_ms": t_bdrt_ms,
+            "adrt_frac": (n * n + 4 * (2 * n - 1) * n) * itemsize * B / (t_adrt_ms * 1e-3) / 1e9 / peak,
+            "bdrt_frac": 2 * 4 * (2 * n - 1) * n * itemsize * B / (t_bdrt_ms * 1e-3) / 1e9 / peak,
+        },
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, imgs, secs, kind, threads = time_reference(n, np_dtype, args.cpu_budget, B)
+        cpu = {
+            "value": v, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{imgs} of {B} images of {n}^2 {args.dtype} ({secs:.2f} s), adrt+bdrt, OMP threads={threads}",
+        }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "mode": "fused" if lib.adrt_b200_get_mode() == 0 else "per-stage",
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--dtype", choices=["f32", "f64"], default="f32")
+    ap.add_argument("--mode", type=int, default=0, help="0 fused (default), 1 per-stage kernels")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU reference work")
+    args = ap.parse_args()
+    import numpy as np
+
+    np_dtype = np.float32 if args.dtype == "f32" else np.float64
+    if args.impl == "reference":
+        reference_arm(args, np_dtype)
+        return
+    from adrt_b200 import _lib
+
+    _lib.load().adrt_b200_set_mode(args.mode)
+    ours(args, np_dtype)
+
+
+if __name__ == "__main__":
+    main()

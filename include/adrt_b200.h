@@ -1,0 +1,153 @@
+/* adrt_b200 -- C ABI of the B200-native ADRT engine (sm_100a).
+ *
+ * This header is the drop-in boundary: one entry point per function of the
+ * reference's native module `adrt._adrt_cdefs`
+ * (/root/reference/src/adrt/adrt_cdefs_py.cpp:852-863).  Everything is plain
+ * C: raw pointers, int64 sizes, a dtype enum, an opaque cudaStream_t.  No
+ * Python, no torch types, no exceptions.  Every function returns 0 on
+ * success and a non-zero adrt_b200_status otherwise; adrt_b200_last_error()
+ * gives the message for the calling thread.
+ *
+ * Array layouts are the reference's public ones (C order):
+ *   image      (B, n, n)
+ *   sinogram   (B, 4, 2n-1, n)         "ADRT output shape"
+ *   cartesian  (B, n, 4n)
+ * n must be a power of two (adrt_cdefs_common.cpp:176-192).  Shape validity
+ * is re-checked here (status ADRT_B200_EINVAL) but the Python-visible error
+ * messages are produced by the shim above this ABI (adrt_b200/_adrt_cdefs.py).
+ *
+ * Two families:
+ *   adrt_b200_<op>(...)       device pointers, asynchronous on `stream`,
+ *                             caller-provided workspace (size from
+ *                             adrt_b200_<op>_workspace_bytes), no allocation,
+ *                             no synchronisation.
+ *   adrt_b200_host_<op>(...)  host pointers (pageable or pinned); performs the
+ *                             H2D / compute / D2H pipeline in batch chunks on
+ *                             device `device` and returns when the output is
+ *                             complete.  This is what the NumPy path calls.
+ */
+#ifndef ADRT_B200_H
+#define ADRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ADRT_B200_F32 = 0,
+    ADRT_B200_F64 = 1
+} adrt_b200_dtype;
+
+typedef enum {
+    ADRT_B200_OK = 0,
+    ADRT_B200_EINVAL = 1,    /* bad shape / dtype / step / null pointer          */
+    ADRT_B200_EWORKSPACE = 2,/* workspace too small                              */
+    ADRT_B200_ECUDA = 3,     /* a CUDA runtime call failed (see last_error)      */
+    ADRT_B200_ENOMEM = 4     /* host or device allocation failed                 */
+} adrt_b200_status;
+
+/* Library / device info ---------------------------------------------------- */
+int         adrt_b200_version(void);              /* 10000*major+100*minor+patch */
+const char *adrt_b200_last_error(void);           /* thread-local, never NULL    */
+int         adrt_b200_device_count(void);         /* <0 on CUDA error            */
+/* Tuning knob for tests / benchmarks: 0 = automatic (fused multi-stage
+ * kernels), 1 = force the one-kernel-per-stage path for adrt/bdrt.           */
+void        adrt_b200_set_mode(int mode);
+int         adrt_b200_get_mode(void);
+/* Number of kernels this library has launched since load (all threads).     */
+int64_t     adrt_b200_launch_count(void);
+
+/* Pure shape helpers (adrt_cdefs_common.cpp:140-142, 176-330) -------------- */
+int         adrt_b200_num_iters(int64_t n);
+
+/* Device-pointer family ---------------------------------------------------- */
+
+/* adrt.adrt: adrt_cdefs_py.cpp:275-341 -> adrt_basic (adrt_cdefs_adrt.hpp:101-212).
+ * in (B,n,n) -> out (B,4,2n-1,n). */
+size_t adrt_b200_adrt_workspace_bytes(int64_t B, int64_t n, int dtype);
+int    adrt_b200_adrt(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* adrt.bdrt: adrt_cdefs_py.cpp:482-548 -> bdrt_basic (adrt_cdefs_bdrt.hpp:121-187).
+ * in (B,4,2n-1,n) -> out same shape. */
+size_t adrt_b200_bdrt_workspace_bytes(int64_t B, int64_t n, int dtype);
+int    adrt_b200_bdrt(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* adrt.core.adrt_step / bdrt_step: adrt_cdefs_py.cpp:343-412, 550-619 ->
+ * adrt_step (adrt_cdefs_adrt.hpp:215-258), bdrt_step (adrt_cdefs_bdrt.hpp:190-244).
+ * 0 <= step < num_iters(n).  in/out (B,4,2n-1,n), must not alias. */
+int    adrt_b200_adrt_step(const void *in, void *out, int64_t B, int64_t n, int step,
+                           int dtype, void *stream);
+int    adrt_b200_bdrt_step(const void *in, void *out, int64_t B, int64_t n, int step,
+                           int dtype, void *stream);
+
+/* adrt.core.adrt_init (core.py:123-176; pure NumPy in the reference):
+ * in (B,n,n) -> out (B,4,2n-1,n). */
+int    adrt_b200_adrt_init(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                           void *stream);
+
+/* adrt.iadrt: adrt_cdefs_py.cpp:414-480 -> iadrt_basic (adrt_cdefs_iadrt.hpp:110-176). */
+size_t adrt_b200_iadrt_workspace_bytes(int64_t B, int64_t n, int dtype);
+int    adrt_b200_iadrt(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Press FMG operators: adrt_cdefs_py.cpp:684-850 -> adrt_cdefs_fmg.hpp:53-171.
+ * restriction (B,4,2n-1,n) -> (B,4,n-1,n/2), n even >= 2;
+ * prolongation (B,h,w) -> (B,2h,2w); highpass (B,h,w) -> same, h,w >= 2. */
+int    adrt_b200_fmg_restriction(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                                 void *stream);
+int    adrt_b200_fmg_prolongation(const void *in, void *out, int64_t B, int64_t h, int64_t w,
+                                  int dtype, void *stream);
+int    adrt_b200_fmg_highpass(const void *in, void *out, int64_t B, int64_t h, int64_t w,
+                              int dtype, void *stream);
+
+/* adrt.utils.interp_to_cart: adrt_cdefs_py.cpp:621-682 -> interp_adrtcart
+ * (adrt_cdefs_interp_adrtcart.hpp:61-114).  The (quadrant, height, slope,
+ * factor) table depends only on (n, dtype); it is computed on the host with
+ * the reference's float32 libm expressions, cached per device, and the gather
+ * runs on the GPU.  in (B,4,2n-1,n) -> out (B,n,4n), 2 <= n <= 2^22. */
+int    adrt_b200_interp_to_cart(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                                void *stream);
+
+/* Device-side glue used by the multigrid / CG drivers (the reference does
+ * these in NumPy on the host: core.py:318-331, utils.py:231-242).
+ *   truncate:        (B,4,2n-1,n) -> (B,4,n,n)                 utils.truncate
+ *   truncate_mean:   (B,4,2n-1,n) -> (B,n,n)
+ *                    = mean_q(truncate(a) / divisor), evaluated as
+ *                    (((t0/div + t1/div) + t2/div) + t3/div) / 4  (NumPy order)
+ *   sub / add:       out = a - b, out = a + b  (elementwise, count elements)
+ *   sub_inplace:     a -= b                                                  */
+int    adrt_b200_truncate(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream);
+int    adrt_b200_truncate_mean(const void *in, void *out, int64_t B, int64_t n, double divisor,
+                               int dtype, void *stream);
+int    adrt_b200_sub(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream);
+int    adrt_b200_add(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream);
+
+/* Host-pointer family (NumPy path) ----------------------------------------- *
+ * Same semantics as above with host buffers.  `device` is the CUDA ordinal.
+ * Buffers may be pageable or pinned (detected with cudaPointerGetAttributes;
+ * pinned buffers are copied directly, pageable ones go through an internal
+ * pinned staging ring filled by several host threads).                      */
+int adrt_b200_host_adrt(const void *in, void *out, int64_t B, int64_t n, int dtype, int device);
+int adrt_b200_host_bdrt(const void *in, void *out, int64_t B, int64_t n, int dtype, int device);
+int adrt_b200_host_iadrt(const void *in, void *out, int64_t B, int64_t n, int dtype, int device);
+int adrt_b200_host_adrt_step(const void *in, void *out, int64_t B, int64_t n, int step, int dtype, int device);
+int adrt_b200_host_bdrt_step(const void *in, void *out, int64_t B, int64_t n, int step, int dtype, int device);
+int adrt_b200_host_adrt_init(const void *in, void *out, int64_t B, int64_t n, int dtype, int device);
+int adrt_b200_host_fmg_restriction(const void *in, void *out, int64_t B, int64_t n, int dtype, int device);
+int adrt_b200_host_fmg_prolongation(const void *in, void *out, int64_t B, int64_t h, int64_t w, int dtype, int device);
+int adrt_b200_host_fmg_highpass(const void *in, void *out, int64_t B, int64_t h, int64_t w, int dtype, int device);
+int adrt_b200_host_interp_to_cart(const void *in, void *out, int64_t B, int64_t n, int dtype, int device);
+
+/* Pinned host memory helpers for callers that want the fast NumPy path.     */
+void *adrt_b200_host_alloc_pinned(size_t bytes);
+void  adrt_b200_host_free_pinned(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADRT_B200_H */
