@@ -1,12 +1,208 @@
-// Fused multi-stage ADRT / bdrt kernels (placeholder: per-stage path only).
+// Fused multi-stage ADRT / bdrt passes for sm_100a.
+//
+// One CTA = one tile of one group of one (image, quadrant) plane; the tile
+// algorithms are in fused_tile.h, the pass planning in fused_plan.h.  HBM
+// traffic per transform drops from 2*K sinogram sweeps (per-stage kernels) to
+// one sweep per pass (2 passes up to n = 4096 in fp32).
 #include "common.cuh"
+#include "fused_plan.h"
+
+#include <type_traits>
 
 namespace adrt_b200 {
 
-template <typename T> size_t fused_adrt_workspace_elems(int64_t, int64_t) { return (size_t)-1; }
-template <typename T> size_t fused_bdrt_workspace_elems(int64_t, int64_t) { return (size_t)-1; }
-template <typename T> int fused_adrt(const T *, T *, int64_t, int64_t, T *, size_t, cudaStream_t, bool *handled) { *handled = false; return ADRT_B200_OK; }
-template <typename T> int fused_bdrt(const T *, T *, int64_t, int64_t, T *, size_t, cudaStream_t, bool *handled) { *handled = false; return ADRT_B200_OK; }
+namespace {
+
+struct PassArgs {
+    int n, D, e;
+    long long in_pitch, out_pitch;
+    long long src_plane_stride, dst_plane_stride;  // elements between consecutive planes
+    int planes;
+};
+
+template <typename T, int M, int LOADK, int STOREK, bool kForward>
+__global__ void __launch_bounds__(tile::NT)
+pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
+{
+    using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
+                                           tile::BwdProgram<T, M, LOADK, STOREK>>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *bufA = reinterpret_cast<T *>(smem_raw);
+    T *bufB = bufA + tile::Geo<M>::G * tile::PITCH;
+
+    tile::TileCtx c;
+    c.n = a.n;
+    c.D = a.D;
+    c.e = a.e;
+    c.g = blockIdx.y;
+    c.k0 = c.g / a.e;
+    c.a_g = c.g % a.e;
+    c.d0 = blockIdx.x * tile::Geo<M>::TD;
+    c.in_pitch = a.in_pitch;
+    c.out_pitch = a.out_pitch;
+    c.q = 0;
+    const int mode = Prog::classify(c);
+    if (mode == tile::TILE_SKIP) return;
+
+    for (int plane = blockIdx.z; plane < a.planes; plane += gridDim.z) {
+        const T *sp;
+        if (LOADK == tile::LOAD_IMAGE) {
+            c.q = plane & 3;
+            sp = src + (long long)(plane >> 2) * a.src_plane_stride;
+        } else {
+            sp = src + (long long)plane * a.src_plane_stride;
+        }
+        T *dp = dst + (long long)plane * a.dst_plane_stride;
+        const int nph = mode == tile::TILE_ZERO ? 1 : Prog::kPhases;
+        for (int ph = 0; ph < nph; ++ph) {
+            Prog::phase(ph, mode, bufA, bufB, sp, dp, c, threadIdx.x);
+            __syncthreads();
+        }
+    }
+}
+
+template <typename T, int M, int LOADK, int STOREK, bool kForward>
+int launch_pass(const T *src, T *dst, const PassArgs &a, int grid_x, int grid_y, cudaStream_t s)
+{
+    auto kern = pass_kernel<T, M, LOADK, STOREK, kForward>;
+    const size_t smem = 2ull * tile::Geo<M>::G * tile::PITCH * sizeof(T);
+    // per device, so not cached in a static: a process may drive several GPUs
+    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)grid_x, (unsigned)grid_y, (unsigned)(a.planes < 65535 ? a.planes : 65535));
+    kern<<<grid, tile::NT, smem, s>>>(src, dst, a);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T, int M, bool kForward>
+int dispatch_kinds(int load, int store, const T *src, T *dst, const PassArgs &a, int gx, int gy, cudaStream_t s)
+{
+    using namespace tile;
+    if (kForward) {
+        if (load == LOAD_IMAGE && store == STORE_WROWS) return launch_pass<T, M, LOAD_IMAGE, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);
+        if (load == LOAD_IMAGE && store == STORE_QCOLS) return launch_pass<T, M, LOAD_IMAGE, STORE_QCOLS, kForward>(src, dst, a, gx, gy, s);
+        if (load == LOAD_WROWS && store == STORE_WROWS) return launch_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);
+        if (load == LOAD_WROWS && store == STORE_QCOLS) return launch_pass<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(src, dst, a, gx, gy, s);
+    } else {
+        if (load == LOAD_QCOLS && store == STORE_WROWS) return launch_pass<T, M, LOAD_QCOLS, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);
+        if (load == LOAD_QCOLS && store == STORE_QCOLS) return launch_pass<T, M, LOAD_QCOLS, STORE_QCOLS, kForward>(src, dst, a, gx, gy, s);
+        if (load == LOAD_WROWS && store == STORE_WROWS) return launch_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);
+        if (load == LOAD_WROWS && store == STORE_QCOLS) return launch_pass<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(src, dst, a, gx, gy, s);
+    }
+    set_error("internal: bad pass kinds %d/%d", load, store);
+    return ADRT_B200_EINVAL;
+}
+
+template <typename T, bool kForward>
+int dispatch_pass(const plan::Pass &p, const T *src, T *dst, const PassArgs &a, cudaStream_t s)
+{
+    switch (p.M) {
+    case 1: return dispatch_kinds<T, 1, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
+    case 2: return dispatch_kinds<T, 2, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
+    case 3: return dispatch_kinds<T, 3, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
+    case 4: return dispatch_kinds<T, 4, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
+    case 5: return dispatch_kinds<T, 5, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
+    case 6:
+        // two ping-pong tiles of 64 rows only fit in shared memory for 4-byte elements
+        if constexpr (sizeof(T) == 4) return dispatch_kinds<T, 6, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
+        break;
+    }
+    set_error("internal: unsupported stages per pass %d", p.M);
+    return ADRT_B200_EINVAL;
+}
+
+// Images per wave: the batch is processed in waves so that the R-layout
+// workspace of a wave can stay resident in the 126 MB L2 between the pass
+// that writes it and the pass that reads it.  0 = whole batch at once.
+int wave_images(int64_t B)
+{
+    const char *e = getenv("ADRT_B200_WAVE");  // read per call: tunable at run time
+    const int w = e ? atoi(e) : 0;
+    if (w <= 0 || w > B) return (int)B;
+    return w;
+}
+
+template <typename T, bool kForward>
+int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, T *ws, size_t ws_elems, cudaStream_t s)
+{
+    const int n = pl.n, D = pl.D;
+    const int wave = wave_images(B);
+    const size_t slot0 = pl.ws_slot_elems[0] * 4 * (size_t)wave;
+    const size_t slot1 = pl.ws_slot_elems[1] * 4 * (size_t)wave;
+    if (slot0 + slot1 > ws_elems) {
+        set_error("fused workspace too small: need %zu elements, got %zu", slot0 + slot1, ws_elems);
+        return ADRT_B200_EWORKSPACE;
+    }
+    T *slot[2] = {ws, ws + slot0};
+    const long long img_elems = (long long)n * n, sino_plane = (long long)D * n;
+    for (int64_t b0 = 0; b0 < B; b0 += wave) {
+        const int nb = (int)((B - b0) < wave ? (B - b0) : wave);
+        for (int i = 0; i < pl.npass; ++i) {
+            const plan::Pass &p = pl.pass[i];
+            PassArgs a;
+            a.n = n; a.D = D; a.e = 1 << p.s;
+            a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
+            a.planes = nb * 4;
+            const T *src;
+            T *dst;
+            if (p.src_buf < 0) {
+                if (kForward) { src = in + b0 * img_elems; a.src_plane_stride = img_elems; }
+                else { src = in + b0 * 4 * sino_plane; a.src_plane_stride = sino_plane; }
+            } else {
+                src = slot[p.src_buf];
+                a.src_plane_stride = (long long)n * p.in_pitch;
+            }
+            if (p.dst_buf < 0) {
+                dst = out + b0 * 4 * sino_plane;
+                a.dst_plane_stride = sino_plane;
+            } else {
+                dst = slot[p.dst_buf];
+                a.dst_plane_stride = (long long)n * p.out_pitch;
+            }
+            int rc = dispatch_pass<T, kForward>(p, src, dst, a, s);
+            if (rc != ADRT_B200_OK) return rc;
+        }
+    }
+    return ADRT_B200_OK;
+}
+
+}  // namespace
+
+template <typename T>
+size_t fused_adrt_workspace_elems(int64_t B, int64_t n)
+{
+    plan::Plan pl;
+    if (n > kMaxN || !plan::make_forward_plan(n, sizeof(T), &pl)) return (size_t)-1;
+    return (pl.ws_slot_elems[0] + pl.ws_slot_elems[1]) * 4 * (size_t)wave_images(B);
+}
+
+template <typename T>
+size_t fused_bdrt_workspace_elems(int64_t B, int64_t n)
+{
+    plan::Plan pl;
+    if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl)) return (size_t)-1;
+    return (pl.ws_slot_elems[0] + pl.ws_slot_elems[1]) * 4 * (size_t)wave_images(B);
+}
+
+template <typename T>
+int fused_adrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s, bool *handled)
+{
+    plan::Plan pl;
+    *handled = false;
+    if (n > kMaxN || !plan::make_forward_plan(n, sizeof(T), &pl)) return ADRT_B200_OK;
+    *handled = true;
+    return run_plan<T, true>(pl, in, out, B, ws, ws_elems, s);
+}
+
+template <typename T>
+int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s, bool *handled)
+{
+    plan::Plan pl;
+    *handled = false;
+    if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl)) return ADRT_B200_OK;
+    *handled = true;
+    return run_plan<T, false>(pl, in, out, B, ws, ws_elems, s);
+}
 
 #define INSTANTIATE(T)                                                      \
     template size_t fused_adrt_workspace_elems<T>(int64_t, int64_t);        \

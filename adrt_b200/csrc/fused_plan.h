@@ -1,0 +1,160 @@
+// Host-side planning of the fused passes: how the K = log2(n) butterfly stages
+// are split into passes, the R-layout workspace each pass writes and the grid
+// each pass needs.  Shared by the CUDA driver (fused_adrt.cu) and the host
+// emulator used by the CPU tests (tests/emu/emu_fused.cpp).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fused_tile.h"
+
+namespace adrt_b200 {
+namespace plan {
+
+constexpr int kMaxPasses = 4;
+
+struct Pass {
+    int M;            // stages fused in this pass
+    int s;            // stages done before it (block height e = 2^s)
+    int load;         // tile::LoadKind
+    int store;        // tile::StoreKind
+    long long in_pitch, out_pitch;  // row length (elements) of the R-layout workspaces
+    int src_buf, dst_buf;           // -1 = caller's input / output, else workspace slot 0/1
+    int grid_x, grid_y;             // d-tiles, groups
+};
+
+struct Plan {
+    int n, K, D;
+    int npass;
+    Pass pass[kMaxPasses];
+    size_t ws_slot_elems[2];  // per plane
+};
+
+inline int ilog2(int64_t n)
+{
+    int k = 0;
+    while ((int64_t(1) << k) < n) ++k;
+    return k;
+}
+
+// Largest M whose two ping-pong tile buffers fit in shared memory (227 KB).
+inline int max_stages_per_pass(size_t elem_size)
+{
+    int m = 1;
+    while (m < 6 && 2ull * (2ull << m) * tile::PITCH * elem_size <= 227ull * 1024) ++m;
+    return m;
+}
+
+// Split K stages into passes.  ADRT_B200_SPLIT="6,5" overrides (testing/tuning).
+inline std::vector<int> split_stages(int K, size_t elem_size, const char *env_name)
+{
+    std::vector<int> out;
+    if (const char *e = getenv(env_name)) {
+        int sum = 0;
+        const int cap = max_stages_per_pass(elem_size);
+        bool ok = true;
+        for (const char *p = e; *p;) {
+            int v = (int)strtol(p, const_cast<char **>(&p), 10);
+            if (v < 1 || v > cap) ok = false;
+            out.push_back(v);
+            sum += v;
+            if (*p == ',') ++p;
+        }
+        if (ok && sum == K && (int)out.size() <= kMaxPasses) return out;
+        out.clear();
+    }
+    const int cap = max_stages_per_pass(elem_size);
+    const int np = (K + cap - 1) / cap;
+    int left = K;
+    for (int i = 0; i < np; ++i) {
+        const int m = (left + (np - i) - 1) / (np - i);  // as even as possible, larger first
+        out.push_back(m);
+        left -= m;
+    }
+    return out;
+}
+
+inline long long fwd_pitch(int n, int s)
+{
+    const long long D = 2LL * n - 1, p = (long long)n + (1LL << s);
+    return p < D ? p : D;
+}
+
+inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
+{
+    const int n = (int)n64;
+    const int K = ilog2(n64);
+    if (K < 1) return false;
+    pl->n = n; pl->K = K; pl->D = 2 * n - 1;
+    const std::vector<int> ms = split_stages(K, elem_size, "ADRT_B200_SPLIT");
+    pl->npass = (int)ms.size();
+    pl->ws_slot_elems[0] = pl->ws_slot_elems[1] = 0;
+    int s = 0;
+    for (int i = 0; i < pl->npass; ++i) {
+        Pass &p = pl->pass[i];
+        const bool first = i == 0, last = i == pl->npass - 1;
+        p.M = ms[i];
+        p.s = s;
+        p.load = first ? tile::LOAD_IMAGE : tile::LOAD_WROWS;
+        p.store = last ? tile::STORE_QCOLS : tile::STORE_WROWS;
+        p.in_pitch = first ? 0 : fwd_pitch(n, s);
+        p.out_pitch = last ? 0 : fwd_pitch(n, s + p.M);
+        p.src_buf = first ? -1 : (i - 1) & 1;
+        p.dst_buf = last ? -1 : i & 1;
+        const int G = 1 << p.M;
+        const int TD = tile::XW - (G - 1);
+        const long long extent = last ? pl->D : p.out_pitch;  // offsets that can be non-zero / must be written
+        p.grid_x = (int)((extent + TD - 1) / TD);
+        p.grid_y = n / G;
+        if (!last) {
+            const size_t need = (size_t)n * (size_t)p.out_pitch;
+            if (need > pl->ws_slot_elems[p.dst_buf]) pl->ws_slot_elems[p.dst_buf] = need;
+        }
+        s += p.M;
+    }
+    return true;
+}
+
+// Transposed plan: forward pass i is undone by transposed pass npass-1-i.
+inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl)
+{
+    const int n = (int)n64;
+    const int K = ilog2(n64);
+    if (K < 1) return false;
+    pl->n = n; pl->K = K; pl->D = 2 * n - 1;
+    const std::vector<int> ms = split_stages(K, elem_size, "ADRT_B200_SPLIT_BDRT");
+    pl->npass = (int)ms.size();
+    pl->ws_slot_elems[0] = pl->ws_slot_elems[1] = 0;
+    int s = K;
+    for (int i = 0; i < pl->npass; ++i) {
+        Pass &p = pl->pass[i];
+        const bool first = i == 0, last = i == pl->npass - 1;
+        p.M = ms[pl->npass - 1 - i];
+        s -= p.M;
+        p.s = s;  // block height of the rows this pass PRODUCES is 2^s
+        p.load = first ? tile::LOAD_QCOLS : tile::LOAD_WROWS;
+        p.store = last ? tile::STORE_QCOLS : tile::STORE_WROWS;
+        p.in_pitch = first ? 0 : pl->D;
+        p.out_pitch = last ? 0 : pl->D;
+        p.src_buf = first ? -1 : (i - 1) & 1;
+        p.dst_buf = last ? -1 : i & 1;
+        const int G = 1 << p.M;
+        const int TD = tile::XW - (G - 1);
+        const long long e = 1LL << s;
+        const long long extent = pl->D + (e - 1) * (G - 1);  // tile coordinates that hold outputs
+        p.grid_x = (int)((extent + TD - 1) / TD);
+        p.grid_y = n / G;
+        if (!last) {
+            const size_t need = (size_t)n * (size_t)pl->D;
+            if (need > pl->ws_slot_elems[p.dst_buf]) pl->ws_slot_elems[p.dst_buf] = need;
+        }
+    }
+    return true;
+}
+
+}  // namespace plan
+}  // namespace adrt_b200

@@ -1,0 +1,109 @@
+// Host emulator of the fused CUDA passes (TEST INFRASTRUCTURE).
+//
+// Compiles adrt_b200/csrc/fused_tile.h + fused_plan.h as plain C++ and runs
+// every CTA of every pass sequentially: for each phase, for tid = 0..NT-1.
+// The arithmetic, index algebra, tiling, masking and workspace layouts are the
+// very code the GPU executes, so tests/test_emu_fused.py can compare the fused
+// algorithm bit-for-bit with the oracle without a GPU.  It is NOT a product
+// path: nothing in adrt_b200/ links or loads it.
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+#include <type_traits>
+#include <vector>
+
+#include "../../adrt_b200/csrc/fused_plan.h"
+
+using namespace adrt_b200;
+
+namespace {
+
+template <typename T, int M, int LOADK, int STOREK, bool kForward>
+void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int planes, long long sps, long long dps)
+{
+    using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
+                                           tile::BwdProgram<T, M, LOADK, STOREK>>::type;
+    std::vector<T> bufA((size_t)tile::Geo<M>::G * tile::PITCH), bufB((size_t)tile::Geo<M>::G * tile::PITCH);
+    const int e = 1 << p.s;
+    for (int plane = 0; plane < planes; ++plane)
+        for (int by = 0; by < p.grid_y; ++by)
+            for (int bx = 0; bx < p.grid_x; ++bx) {
+                tile::TileCtx c;
+                c.n = n; c.D = D; c.e = e; c.g = by; c.k0 = by / e; c.a_g = by % e;
+                c.d0 = bx * tile::Geo<M>::TD;
+                c.in_pitch = p.in_pitch; c.out_pitch = p.out_pitch;
+                c.q = 0;
+                const int mode = Prog::classify(c);
+                if (mode == tile::TILE_SKIP) continue;
+                const T *sp;
+                if (LOADK == tile::LOAD_IMAGE) { c.q = plane & 3; sp = src + (long long)(plane >> 2) * sps; }
+                else sp = src + (long long)plane * sps;
+                T *dp = dst + (long long)plane * dps;
+                // poison shared memory so that reads of never-written cells are visible
+                for (auto &v : bufA) v = T(1e30);
+                for (auto &v : bufB) v = T(-1e30);
+                const int nph = mode == tile::TILE_ZERO ? 1 : Prog::kPhases;
+                for (int ph = 0; ph < nph; ++ph)
+                    for (int tid = 0; tid < tile::NT; ++tid)
+                        Prog::phase(ph, mode, bufA.data(), bufB.data(), sp, dp, c, tid);
+            }
+}
+
+template <typename T, int M, bool kForward>
+void run_kinds(const plan::Pass &p, const T *src, T *dst, int n, int D, int planes, long long sps, long long dps)
+{
+    using namespace tile;
+    if (kForward) {
+        if (p.load == LOAD_IMAGE && p.store == STORE_WROWS) run_pass<T, M, LOAD_IMAGE, STORE_WROWS, kForward>(p, src, dst, n, D, planes, sps, dps);
+        else if (p.load == LOAD_IMAGE && p.store == STORE_QCOLS) run_pass<T, M, LOAD_IMAGE, STORE_QCOLS, kForward>(p, src, dst, n, D, planes, sps, dps);
+        else if (p.load == LOAD_WROWS && p.store == STORE_WROWS) run_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(p, src, dst, n, D, planes, sps, dps);
+        else run_pass<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(p, src, dst, n, D, planes, sps, dps);
+    } else {
+        if (p.load == LOAD_QCOLS && p.store == STORE_WROWS) run_pass<T, M, LOAD_QCOLS, STORE_WROWS, kForward>(p, src, dst, n, D, planes, sps, dps);
+        else if (p.load == LOAD_QCOLS && p.store == STORE_QCOLS) run_pass<T, M, LOAD_QCOLS, STORE_QCOLS, kForward>(p, src, dst, n, D, planes, sps, dps);
+        else if (p.load == LOAD_WROWS && p.store == STORE_WROWS) run_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(p, src, dst, n, D, planes, sps, dps);
+        else run_pass<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(p, src, dst, n, D, planes, sps, dps);
+    }
+}
+
+template <typename T, bool kForward>
+int run(const T *in, T *out, int64_t B, int64_t n64)
+{
+    plan::Plan pl;
+    const bool ok = kForward ? plan::make_forward_plan(n64, sizeof(T), &pl) : plan::make_transposed_plan(n64, sizeof(T), &pl);
+    if (!ok) return 1;
+    const int n = pl.n, D = pl.D, planes = (int)B * 4;
+    // workspaces start as NaN so that any read of a never-written element shows up
+    std::vector<T> ws0(pl.ws_slot_elems[0] * planes, T(NAN)), ws1(pl.ws_slot_elems[1] * planes, T(NAN));
+    T *slot[2] = {ws0.data(), ws1.data()};
+    const long long img = (long long)n * n, sino = (long long)D * n;
+    for (int i = 0; i < pl.npass; ++i) {
+        const plan::Pass &p = pl.pass[i];
+        const T *src;
+        T *dst;
+        long long sps, dps;
+        if (p.src_buf < 0) { src = in; sps = kForward ? img : sino; }
+        else { src = slot[p.src_buf]; sps = (long long)n * p.in_pitch; }
+        if (p.dst_buf < 0) { dst = out; dps = sino; }
+        else { dst = slot[p.dst_buf]; dps = (long long)n * p.out_pitch; }
+        switch (p.M) {
+        case 1: run_kinds<T, 1, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+        case 2: run_kinds<T, 2, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+        case 3: run_kinds<T, 3, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+        case 4: run_kinds<T, 4, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+        case 5: run_kinds<T, 5, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+        case 6: run_kinds<T, 6, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+        default: return 2;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+int emu_adrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, true>(in, out, B, n); }
+int emu_adrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run<double, true>(in, out, B, n); }
+int emu_bdrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, false>(in, out, B, n); }
+int emu_bdrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run<double, false>(in, out, B, n); }
+}
