@@ -21,14 +21,14 @@ struct PassArgs {
 };
 
 template <typename T, int M, int LOADK, int STOREK, bool kForward>
-__global__ void __launch_bounds__(tile::NT)
+__global__ void __launch_bounds__(tile::Geo<M>::NT)
 pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
 {
     using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
                                            tile::BwdProgram<T, M, LOADK, STOREK>>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *bufA = reinterpret_cast<T *>(smem_raw);
-    T *bufB = bufA + tile::Geo<M>::G * tile::PITCH;
+    T *bufB = bufA + tile::Geo<M>::G * tile::Pitch<T>::value;
 
     tile::TileCtx c;
     c.n = a.n;
@@ -65,11 +65,11 @@ template <typename T, int M, int LOADK, int STOREK, bool kForward>
 int launch_pass(const T *src, T *dst, const PassArgs &a, int grid_x, int grid_y, cudaStream_t s)
 {
     auto kern = pass_kernel<T, M, LOADK, STOREK, kForward>;
-    const size_t smem = 2ull * tile::Geo<M>::G * tile::PITCH * sizeof(T);
+    const size_t smem = 2ull * tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T);
     // per device, so not cached in a static: a process may drive several GPUs
     ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)grid_x, (unsigned)grid_y, (unsigned)(a.planes < 65535 ? a.planes : 65535));
-    kern<<<grid, tile::NT, smem, s>>>(src, dst, a);
+    kern<<<grid, tile::Geo<M>::NT, smem, s>>>(src, dst, a);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }

@@ -45,7 +45,8 @@ inline int ilog2(int64_t n)
 inline int max_stages_per_pass(size_t elem_size)
 {
     int m = 1;
-    while (m < 6 && 2ull * (2ull << m) * tile::PITCH * elem_size <= 227ull * 1024) ++m;
+    const size_t pitch = elem_size == 8 ? tile::Pitch<double>::value : tile::Pitch<float>::value;
+    while (m < 6 && 2ull * (2ull << m) * pitch * elem_size <= 227ull * 1024) ++m;
     return m;
 }
 
@@ -78,10 +79,20 @@ inline std::vector<int> split_stages(int K, size_t elem_size, const char *env_na
     return out;
 }
 
+inline long long round4(long long v) { return (v + 3) & ~3LL; }
+
+// Row length of the forward workspace after s stages: the support n + 2^s
+// (capped at D), rounded up so that rows stay 16-byte aligned.
 inline long long fwd_pitch(int n, int s)
 {
     const long long D = 2LL * n - 1, p = (long long)n + (1LL << s);
-    return p < D ? p : D;
+    return round4(p < D ? p : D);
+}
+
+inline int tile_td(int M)
+{
+    const int G = 1 << M;
+    return tile::XW - (G < 4 ? 4 : G);
 }
 
 inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
@@ -106,8 +117,8 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        const int TD = tile::XW - (G - 1);
-        const long long extent = last ? pl->D : p.out_pitch;  // offsets that can be non-zero / must be written
+        const int TD = tile_td(p.M);
+        const long long extent = last ? pl->D : p.out_pitch;  // offsets that must be written
         p.grid_x = (int)((extent + TD - 1) / TD);
         p.grid_y = n / G;
         if (!last) {
@@ -138,18 +149,18 @@ inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl)
         p.s = s;  // block height of the rows this pass PRODUCES is 2^s
         p.load = first ? tile::LOAD_QCOLS : tile::LOAD_WROWS;
         p.store = last ? tile::STORE_QCOLS : tile::STORE_WROWS;
-        p.in_pitch = first ? 0 : pl->D;
-        p.out_pitch = last ? 0 : pl->D;
+        p.in_pitch = first ? 0 : round4(pl->D);
+        p.out_pitch = last ? 0 : round4(pl->D);
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        const int TD = tile::XW - (G - 1);
+        const int TD = tile_td(p.M);
         const long long e = 1LL << s;
         const long long extent = pl->D + (e - 1) * (G - 1);  // tile coordinates that hold outputs
         p.grid_x = (int)((extent + TD - 1) / TD);
         p.grid_y = n / G;
         if (!last) {
-            const size_t need = (size_t)n * (size_t)pl->D;
+            const size_t need = (size_t)n * (size_t)round4(pl->D);
             if (need > pl->ws_slot_elems[p.dst_buf]) pl->ws_slot_elems[p.dst_buf] = need;
         }
     }

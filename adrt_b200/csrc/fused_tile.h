@@ -24,16 +24,19 @@
 // starts from angle 0.  Only rows of the same group interact, exactly like a
 // decimation-in-time FFT.
 //
-// Shared-memory tile: G rows (one per input/output row of the group) x XT
-// offsets, offset axis contiguous ("R-layout").  Offsets are padded by one
-// word per 32 (phys()), and the row pitch is odd, so that
-//   * a warp whose lanes own V = 8 consecutive offsets each reads/writes any
-//     uniformly shifted position without bank conflicts, and
-//   * a warp whose lanes walk the rows at a fixed offset (the transposing
-//     copies to/from the public (d, c) layout) is conflict free as well.
-// A thread computes a radix-4 butterfly (two stages) for 8 consecutive offsets
-// in registers: 38 shared loads and 32 stores for 66 adds, instead of the 128
-// loads / 64 stores of two separate stages.
+// Shared-memory tile: G rows x 256 offsets, offset axis contiguous, linear
+// (no padding inside a row), row pitch = 4 words mod 32.  A thread owns V = 4
+// consecutive offsets of one radix-4 butterfly (two stages): consecutive lanes
+// own consecutive 16-byte slots, so every LDS.128/STS.128 is conflict free,
+// and so are the transposing copies (lanes walk the rows, 16 bytes each).
+// Shifted operand windows are fetched as the enclosing aligned 16-byte slots
+// and the wanted elements are picked by *compile-time* register indices: the
+// alignment residue depends only on (angle mod 4), which is warp-uniform, so
+// each step is instantiated for the 4 residues and dispatched by a switch.
+// Outputs are always stored aligned.  In the transposed direction this means a
+// child row is stored with a skew (j * angle) relative to its logical offsets;
+// the next step folds the skew into its operand windows (again only the skew
+// mod 4 matters for code selection).
 //
 // Signed zeros / missing operands: the reference copies instead of adding when
 // the shifted operand does not exist.  Forward: positions below offset 0 hold
@@ -52,58 +55,115 @@
 namespace adrt_b200 {
 namespace tile {
 
-constexpr int V = 8;                 // consecutive offsets per thread
-constexpr int XW = 256;              // computed offsets per tile (32 lanes x V)
-constexpr int MARGIN = 8;            // slack for reads just outside the computed window
-constexpr int XT = XW + MARGIN;      // offsets held per row
-constexpr int NT = 256;              // threads per CTA
-constexpr int NWARP = NT / 32;
-constexpr int NCHUNK = XW / V;       // = 32: one warp covers one row-group
+constexpr int V = 4;                 // consecutive offsets per thread
+constexpr int XW = 256;              // offsets per tile row
+constexpr int NCHUNK = XW / V;       // 64 chunks per row
 
-ADRT_HD constexpr int phys(int xt) { return xt + (xt >> 5); }
-constexpr int PITCH = 273;           // >= phys(XT - 1) + 1 = 272, odd
+// 16-byte vector access -----------------------------------------------------------
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { static constexpr int L = 4; };
+template <> struct VecOf<double> { static constexpr int L = 2; };
+template <typename T> struct alignas(16) Pack { T v[VecOf<T>::L]; };
+
+// Row pitch (elements): >= XW + 8 slack for over-fetch, 16-byte multiple, and
+// = 4 words (mod 32) so that 8 lanes reading 16 bytes from 8 consecutive rows
+// hit 32 distinct banks.
+template <typename T> struct Pitch;
+template <> struct Pitch<float> { static constexpr int value = 260; };
+template <> struct Pitch<double> { static constexpr int value = 274; };
 
 enum LoadKind { LOAD_IMAGE = 0, LOAD_WROWS = 1, LOAD_QCOLS = 2 };
 enum StoreKind { STORE_WROWS = 0, STORE_QCOLS = 1 };
 
 template <int M> struct Geo {
     static constexpr int G = 1 << M;
-    static constexpr int HALO = G - 1;        // total shift consumed by M stages
+    // offsets consumed by M stages, rounded so that chunk boundaries stay aligned
+    static constexpr int HALO = G < 4 ? 4 : G;
     static constexpr int TD = XW - HALO;      // valid output offsets per tile
+    static constexpr int NT = G >= 64 ? 512 : 256;   // threads per CTA
+    static constexpr int NWARP = NT / 32;
 };
 
 // Everything a CTA needs to know about its tile.
 struct TileCtx {
     int n, D;          // image side, 2n-1
     int q;             // quadrant (image loader only)
-    int e;             // block height before the pass, 2^s
+    int e;             // block height before (forward) / after (transposed) the pass, 2^s
     int k0, a_g;       // group = k0*e + a_g
     int g;             // group index
     int d0;            // forward: first valid output offset; transposed: first input offset
-    long long in_pitch, out_pitch;   // elements per row of the R-layout workspaces
+    long long in_pitch, out_pitch;   // elements per row of the R-layout workspaces (multiples of 4)
 };
+
+// Load N consecutive elements that start Q elements after the 16-byte aligned
+// position `p` (Q compile time): ceil((Q+N)/L) vector loads + static selection.
+template <typename T, int N, int Q>
+ADRT_HD void load_window(const T *p, T (&dst)[N])
+{
+    constexpr int L = VecOf<T>::L;
+    constexpr int NV = (Q + N + L - 1) / L;
+    Pack<T> tmp[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) tmp[v] = *reinterpret_cast<const Pack<T> *>(p + v * L);
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = tmp[(Q + i) / L].v[(Q + i) % L];
+}
+
+template <typename T>
+ADRT_HD void store_chunk(T *p, const T (&src)[V])
+{
+    constexpr int L = VecOf<T>::L;
+#pragma unroll
+    for (int v = 0; v < V / L; ++v) {
+        Pack<T> t;
+#pragma unroll
+        for (int i = 0; i < L; ++i) t.v[i] = src[v * L + i];
+        *reinterpret_cast<Pack<T> *>(p + v * L) = t;
+    }
+}
+
+// residue of a non-negative start position (x multiple of 4) minus `shift`
+ADRT_HD constexpr int neg_mod(int shift, int L) { return ((-shift) % L + L) % L; }
 
 // ===========================================================================
 // forward
 // ===========================================================================
 
-// ---- loaders: fill rows j of buf with in_j[d0 - HALO - MARGIN - a_g*j + xt] ----
+// ---- loaders: row j of buf <- in_j[d0 - HALO - a_g*j + x], x in [0, XW) --------
 template <typename T, int M>
 ADRT_HD void fwd_load_wrows(T *buf, const T *src_plane, const TileCtx &c, int tid)
 {
-    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO;
+    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    constexpr int L = VecOf<T>::L;
     const int warp = tid >> 5, lane = tid & 31;
     const int sup = c.n + c.a_g;  // support of every input row of this group
     for (int j = warp; j < G; j += NWARP) {
         const T *row = src_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.in_pitch;
-        const int dbase = c.d0 - HALO - MARGIN - c.a_g * j;
-        for (int xt = lane; xt < XT; xt += 32) {
-            const int d = dbase + xt;
-            T v;
-            if (d < 0) v = T(-0.0);
-            else if (d < sup) v = row[d];
-            else v = T(0.0);
-            buf[j * PITCH + phys(xt)] = v;
+        const int dbase = c.d0 - HALO - c.a_g * j;
+        T *dst = buf + j * P;
+        if (dbase >= 0 && dbase + XW <= sup && (dbase % L) == 0) {
+            // fully inside the support and 16-byte aligned: vector copy
+#pragma unroll
+            for (int k = 0; k < XW / (32 * L); ++k) {
+                const int x = (k * 32 + lane) * L;
+                *reinterpret_cast<Pack<T> *>(dst + x) = *reinterpret_cast<const Pack<T> *>(row + dbase + x);
+            }
+        } else if (dbase >= 0 && dbase + XW <= sup) {
+            T v[XW / 32];
+#pragma unroll
+            for (int k = 0; k < XW / 32; ++k) v[k] = row[dbase + k * 32 + lane];
+#pragma unroll
+            for (int k = 0; k < XW / 32; ++k) dst[k * 32 + lane] = v[k];
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < XW / 32; ++k) {
+                const int x = k * 32 + lane, d = dbase + x;
+                T v;
+                if (d < 0) v = T(-0.0);
+                else if (d < sup) v = row[d];
+                else v = T(0.0);
+                dst[x] = v;
+            }
         }
     }
 }
@@ -115,37 +175,50 @@ ADRT_HD void fwd_load_wrows(T *buf, const T *src_plane, const TileCtx &c, int ti
 template <typename T, int M>
 ADRT_HD void fwd_load_image(T *buf, const T *img, const TileCtx &c, int tid)
 {
-    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO;
+    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     const int warp = tid >> 5, lane = tid & 31;
     const int n = c.n;
-    const int dbase = c.d0 - HALO - MARGIN;
+    const int dbase = c.d0 - HALO;
     const int rows = G < n ? G : n;
     if (c.q == 0 || c.q == 3) {
         // image rows are contiguous along d (reversed): lanes walk d
         for (int j = warp; j < rows; j += NWARP) {
             const int r = c.g * G + j;
             const T *row = img + (long long)(c.q == 0 ? r : n - 1 - r) * n;
-            for (int xt = lane; xt < XT; xt += 32) {
-                const int d = dbase + xt;
-                T v;
-                if (d < 0) v = T(-0.0);
-                else if (d < n) v = row[n - 1 - d];
-                else v = T(0.0);
-                buf[j * PITCH + phys(xt)] = v;
+            T *dst = buf + j * P;
+            if (dbase >= 0 && dbase + XW <= n) {
+                T v[XW / 32];
+#pragma unroll
+                for (int k = 0; k < XW / 32; ++k) v[k] = row[n - 1 - (dbase + k * 32 + lane)];
+#pragma unroll
+                for (int k = 0; k < XW / 32; ++k) dst[k * 32 + lane] = v[k];
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < XW / 32; ++k) {
+                    const int x = k * 32 + lane, d = dbase + x;
+                    T v;
+                    if (d < 0) v = T(-0.0);
+                    else if (d < n) v = row[n - 1 - d];
+                    else v = T(0.0);
+                    dst[x] = v;
+                }
             }
         }
     } else {
-        // image rows are contiguous along r: lanes walk the tile rows j
-        for (int xt = warp; xt < XT; xt += NWARP) {
-            const int d = dbase + xt;
-            const int px = phys(xt);
+        // image rows are contiguous along r: lanes walk the tile rows j, each
+        // thread gathers V consecutive offsets and stores them as one vector
+        for (int x = warp * V; x < XW; x += NWARP * V) {
             for (int j = lane; j < rows; j += 32) {
                 const int r = c.g * G + j;
-                T v;
-                if (d < 0) v = T(-0.0);
-                else if (d < n) v = (c.q == 1) ? img[(long long)(n - 1 - d) * n + r] : img[(long long)d * n + r];
-                else v = T(0.0);
-                buf[j * PITCH + px] = v;
+                T v[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const int d = dbase + x + i;
+                    if (d < 0) v[i] = T(-0.0);
+                    else if (d < n) v[i] = (c.q == 1) ? img[(long long)(n - 1 - d) * n + r] : img[(long long)d * n + r];
+                    else v[i] = T(0.0);
+                }
+                store_chunk<T>(buf + j * P + x, v);
             }
         }
     }
@@ -155,87 +228,111 @@ ADRT_HD void fwd_load_image(T *buf, const T *img, const TileCtx &c, int tid)
 //   u[k][al][d]  = in_{2k}[d] + in_{2k+1}[d - a - al]                 (stage t)
 //   out[p][d]    = u[0][p>>1][d] + u[1][p>>1][d - 2a - ceil(p/2)]     (stage t+1)
 // with input rows r_j = (k0*4 + j)*e + a, output rows k0*4e + 4a + p.
+// AM = a & 3 fixes the alignment residues of the three shifted windows.
+template <typename T, int AM>
+ADRT_HD void fwd_radix4_item(const T *in, T *out, int e, int k0, int a, int x)
+{
+    constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
+    constexpr int Q1 = neg_mod(AM + 1, L), Q2 = neg_mod(2 * AM + 2, L), Q3 = neg_mod(3 * AM + 3, L);
+    const T *r0 = in + ((k0 * 4 + 0) * e + a) * P;
+    const T *r1 = in + ((k0 * 4 + 1) * e + a) * P;
+    const T *r2 = in + ((k0 * 4 + 2) * e + a) * P;
+    const T *r3 = in + ((k0 * 4 + 3) * e + a) * P;
+    T y0[V], y1[V + 1], y2[V + 2], y3[V + 3];
+    load_window<T, V, 0>(r0 + x, y0);
+    load_window<T, V + 1, Q1>(r1 + (x - a - 1 - Q1), y1);
+    load_window<T, V + 2, Q2>(r2 + (x - 2 * a - 2 - Q2), y2);
+    load_window<T, V + 3, Q3>(r3 + (x - 3 * a - 3 - Q3), y3);
+    T u00[V], u01[V], u10[V + 2], u11[V + 2];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        u00[i] = y0[i] + y1[i + 1];
+        u01[i] = y0[i] + y1[i];
+    }
+#pragma unroll
+    for (int i = 0; i < V + 2; ++i) {
+        u10[i] = y2[i] + y3[i + 1];
+        u11[i] = y2[i] + y3[i];
+    }
+    T o0[V], o1[V], o2[V], o3[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        o0[i] = u00[i] + u10[i + 2];
+        o1[i] = u00[i] + u10[i + 1];
+        o2[i] = u01[i] + u11[i + 1];
+        o3[i] = u01[i] + u11[i];
+    }
+    T *o = out + (k0 * 4 * e + 4 * a) * P + x;
+    store_chunk<T>(o, o0);
+    store_chunk<T>(o + P, o1);
+    store_chunk<T>(o + 2 * P, o2);
+    store_chunk<T>(o + 3 * P, o3);
+}
+
 template <typename T, int M>
 ADRT_HD void fwd_radix4(const T *in, T *out, int t, int tid)
 {
-    constexpr int G = Geo<M>::G;
+    constexpr int G = Geo<M>::G, NT = Geo<M>::NT;
     const int e = 1 << t;
-    const int lo_out = 4 * e - 1;  // offsets below this are not valid after the step
+    const int lo_out = 4 * e;  // chunks below this would read before the row start
     for (int item = tid; item < (G / 4) * NCHUNK; item += NT) {
-        const int gi = item / NCHUNK, ch = item % NCHUNK;
-        if (V * ch + V <= lo_out) continue;
+        const int gi = item / NCHUNK, x = (item % NCHUNK) * V;
+        if (x < lo_out) continue;
         const int k0 = gi >> t, a = gi & (e - 1);
-        const int x = MARGIN + V * ch;
-        const T *r0 = in + ((k0 * 4 + 0) * e + a) * PITCH;
-        const T *r1 = in + ((k0 * 4 + 1) * e + a) * PITCH;
-        const T *r2 = in + ((k0 * 4 + 2) * e + a) * PITCH;
-        const T *r3 = in + ((k0 * 4 + 3) * e + a) * PITCH;
-        T y0[V], y1[V + 1], y2[V + 2], y3[V + 3];
-#pragma unroll
-        for (int i = 0; i < V; ++i) y0[i] = r0[phys(x + i)];
-#pragma unroll
-        for (int i = 0; i < V + 1; ++i) y1[i] = r1[phys(x - a - 1 + i)];
-#pragma unroll
-        for (int i = 0; i < V + 2; ++i) y2[i] = r2[phys(x - 2 * a - 2 + i)];
-#pragma unroll
-        for (int i = 0; i < V + 3; ++i) y3[i] = r3[phys(x - 3 * a - 3 + i)];
-        T u00[V], u01[V], u10[V + 2], u11[V + 2];
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            u00[i] = y0[i] + y1[i + 1];
-            u01[i] = y0[i] + y1[i];
-        }
-#pragma unroll
-        for (int i = 0; i < V + 2; ++i) {
-            u10[i] = y2[i] + y3[i + 1];
-            u11[i] = y2[i] + y3[i];
-        }
-        T *o = out + (k0 * 4 * e + 4 * a) * PITCH;
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const int px = phys(x + i);
-            o[0 * PITCH + px] = u00[i] + u10[i + 2];
-            o[1 * PITCH + px] = u00[i] + u10[i + 1];
-            o[2 * PITCH + px] = u01[i] + u11[i + 1];
-            o[3 * PITCH + px] = u01[i] + u11[i];
+        switch (a & 3) {
+        case 0: fwd_radix4_item<T, 0>(in, out, e, k0, a, x); break;
+        case 1: fwd_radix4_item<T, 1>(in, out, e, k0, a, x); break;
+        case 2: fwd_radix4_item<T, 2>(in, out, e, k0, a, x); break;
+        default: fwd_radix4_item<T, 3>(in, out, e, k0, a, x); break;
         }
     }
 }
 
 // ---- radix-2 step: local stage t ------------------------------------------------
+template <typename T, int BM>
+ADRT_HD void fwd_radix2_item(const T *in, T *out, int e, int k, int b, int x)
+{
+    constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
+    constexpr int Q = neg_mod(BM + 1, L);
+    const T *rA = in + ((2 * k) * e + b) * P;
+    const T *rB = in + ((2 * k + 1) * e + b) * P;
+    T yA[V], yB[V + 1];
+    load_window<T, V, 0>(rA + x, yA);
+    load_window<T, V + 1, Q>(rB + (x - b - 1 - Q), yB);
+    T oe[V], oo[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        oe[i] = yA[i] + yB[i + 1];
+        oo[i] = yA[i] + yB[i];
+    }
+    T *o = out + (k * 2 * e + 2 * b) * P + x;
+    store_chunk<T>(o, oe);
+    store_chunk<T>(o + P, oo);
+}
+
 template <typename T, int M>
 ADRT_HD void fwd_radix2(const T *in, T *out, int t, int tid)
 {
-    constexpr int G = Geo<M>::G;
+    constexpr int G = Geo<M>::G, NT = Geo<M>::NT;
     const int e = 1 << t;
-    const int lo_out = 2 * e - 1;
+    const int lo_out = 2 * e < 4 ? 4 : 2 * e;
     for (int item = tid; item < (G / 2) * NCHUNK; item += NT) {
-        const int gi = item / NCHUNK, ch = item % NCHUNK;
-        if (V * ch + V <= lo_out) continue;
+        const int gi = item / NCHUNK, x = (item % NCHUNK) * V;
+        if (x < lo_out) continue;
         const int k = gi >> t, b = gi & (e - 1);
-        const int x = MARGIN + V * ch;
-        const T *rA = in + ((2 * k) * e + b) * PITCH;
-        const T *rB = in + ((2 * k + 1) * e + b) * PITCH;
-        T yA[V], yB[V + 1];
-#pragma unroll
-        for (int i = 0; i < V; ++i) yA[i] = rA[phys(x + i)];
-#pragma unroll
-        for (int i = 0; i < V + 1; ++i) yB[i] = rB[phys(x - b - 1 + i)];
-        T *o = out + (k * 2 * e + 2 * b) * PITCH;
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const int px = phys(x + i);
-            o[px] = yA[i] + yB[i + 1];
-            o[PITCH + px] = yA[i] + yB[i];
+        switch (b & 3) {
+        case 0: fwd_radix2_item<T, 0>(in, out, e, k, b, x); break;
+        case 1: fwd_radix2_item<T, 1>(in, out, e, k, b, x); break;
+        case 2: fwd_radix2_item<T, 2>(in, out, e, k, b, x); break;
+        default: fwd_radix2_item<T, 3>(in, out, e, k, b, x); break;
         }
     }
 }
 
 // Number of barrier-separated compute steps for M stages (radix-4 first, one
-// radix-2 at the end when M is odd) and which buffer holds the result.
+// radix-2 at the end when M is odd).
 ADRT_HD constexpr int num_steps(int M) { return (M + 1) / 2; }
 
-// step i of the forward local transform; returns nothing, caller syncs.
 template <typename T, int M>
 ADRT_HD void fwd_step(T *bufA, T *bufB, int step, int tid)
 {
@@ -247,69 +344,87 @@ ADRT_HD void fwd_step(T *bufA, T *bufB, int step, int tid)
 }
 
 // ---- stores -----------------------------------------------------------------------
-// R-layout workspace: output row p -> row (g*G + p), offsets [d0, d0+TD) below the
-// support bound of the row (n + a'), a' = a_g*G + p; nothing else is ever read back.
+// R-layout workspace: output row p -> row (g*G + p), offsets [d0, d0+TD); the
+// row is zero above its support bound n + a' (a' = a_g*G + p) and is written
+// all the way to the pitch so that the next pass may read it blindly.
 template <typename T, int M>
-ADRT_HD void fwd_store_wrows(const T *buf, T *dst_plane, const TileCtx &c, int tid)
+ADRT_HD void fwd_store_wrows(const T *buf, T *dst_plane, const TileCtx &c, bool zero, int tid)
 {
-    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO;
+    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO, TD = Geo<M>::TD, NWARP = Geo<M>::NWARP;
+    constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
     const int warp = tid >> 5, lane = tid & 31;
     for (int p = warp; p < G; p += NWARP) {
         T *row = dst_plane + ((long long)c.g * G + p) * c.out_pitch;
         int lim = c.n + c.a_g * G + p;
         if (lim > c.D) lim = c.D;
-        for (int xc = HALO + lane; xc < XW; xc += 32) {
-            const int d = c.d0 + xc - HALO;
-            if (d < lim) row[d] = buf[p * PITCH + phys(MARGIN + xc)];
+        for (int xc = lane * L; xc < TD; xc += 32 * L) {
+            const int d = c.d0 + xc;
+            if (d >= c.out_pitch) break;
+            Pack<T> v;
+            if (!zero) v = *reinterpret_cast<const Pack<T> *>(buf + p * P + HALO + xc);
+#pragma unroll
+            for (int i = 0; i < L; ++i)
+                if (zero || d + i >= lim) v.v[i] = T(0.0);
+            *reinterpret_cast<Pack<T> *>(row + d) = v;   // pitch is a multiple of 4: never crosses the row end
         }
     }
 }
 
-// Public layout (D, n) of the plane: column g*G + p, all offsets < D.
+// Public layout (D, n) of the plane: column g*G + p, all offsets < D.  Lanes walk
+// the rows p (consecutive columns), each thread moves V consecutive offsets.
 template <typename T, int M>
-ADRT_HD void fwd_store_qcols(const T *buf, T *dst_plane, const TileCtx &c, int tid)
+ADRT_HD void store_qcols(const T *buf, T *dst_plane, const TileCtx &c, int xoff, bool zero, int tid)
 {
-    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO;
+    constexpr int G = Geo<M>::G, TD = Geo<M>::TD, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     const int warp = tid >> 5, lane = tid & 31;
-    for (int xc = HALO + warp; xc < XW; xc += NWARP) {
-        const int d = c.d0 + xc - HALO;
+    const int cols = G < c.n ? G : c.n;
+    for (int xc = warp * V; xc < TD; xc += NWARP * V) {
+        const int d = c.d0 + xc;
         if (d >= c.D) break;
-        const int px = phys(MARGIN + xc);
-        T *orow = dst_plane + (long long)d * c.n + c.g * G;
-        for (int p = lane; p < G; p += 32) orow[p] = buf[p * PITCH + px];
-    }
-}
-
-// Tile entirely above the support of all its output columns: plain zeros.
-template <typename T, int M>
-ADRT_HD void fwd_store_qcols_zero(T *dst_plane, const TileCtx &c, int tid)
-{
-    constexpr int G = Geo<M>::G, TD = Geo<M>::TD;
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int i = warp; i < TD; i += NWARP) {
-        const int d = c.d0 + i;
-        if (d >= c.D) break;
-        T *orow = dst_plane + (long long)d * c.n + c.g * G;
-        for (int p = lane; p < G; p += 32) orow[p] = T(0.0);
+        for (int p = lane; p < cols; p += 32) {
+            T v[V];
+            if (zero) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = T(0.0);
+            } else {
+                load_window<T, V, 0>(buf + p * P + xoff + xc, v);
+            }
+            T *o = dst_plane + (long long)d * c.n + c.g * G + p;
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (d + i < c.D) o[(long long)i * c.n] = v[i];
+        }
     }
 }
 
 // ===========================================================================
 // transposed (bdrt)
 // ===========================================================================
-// Tile coordinate xc = xt (margin on the right); input row p holds
-// in_p[d0 + xt].  Output row j is stored at offset d0 + xc - a_g*j.
+// Input row p holds in_p[d0 + x].  A row written by a step is stored with a
+// skew: logical position = stored position - skew, skew = j * angle of the row
+// in the step that produced it (0 for loaded rows and after the last step).
 
 template <typename T, int M>
 ADRT_HD void bwd_load_wrows(T *buf, const T *src_plane, const TileCtx &c, int tid)
 {
-    constexpr int G = Geo<M>::G;
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value, L = VecOf<T>::L;
     const int warp = tid >> 5, lane = tid & 31;
     for (int p = warp; p < G; p += NWARP) {
         const T *row = src_plane + ((long long)c.g * G + p) * c.in_pitch;
-        for (int xt = lane; xt < XT; xt += 32) {
-            const int d = c.d0 + xt;
-            buf[p * PITCH + phys(xt)] = d < c.D ? row[d] : T(0.0);
+        T *dst = buf + p * P;
+        if (c.d0 + XW <= c.D) {
+            // d0 and the pitch are multiples of 4: aligned vector copy
+#pragma unroll
+            for (int k = 0; k < XW / (32 * L); ++k) {
+                const int x = (k * 32 + lane) * L;
+                *reinterpret_cast<Pack<T> *>(dst + x) = *reinterpret_cast<const Pack<T> *>(row + c.d0 + x);
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < XW / 32; ++k) {
+                const int x = k * 32 + lane, d = c.d0 + x;
+                dst[x] = d < c.D ? row[d] : T(0.0);
+            }
         }
     }
 }
@@ -317,19 +432,23 @@ ADRT_HD void bwd_load_wrows(T *buf, const T *src_plane, const TileCtx &c, int ti
 template <typename T, int M>
 ADRT_HD void bwd_load_qcols(T *buf, const T *src_plane, const TileCtx &c, int tid)
 {
-    constexpr int G = Geo<M>::G;
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     const int warp = tid >> 5, lane = tid & 31;
     const int cols = G < c.n ? G : c.n;
-    for (int xt = warp; xt < XT; xt += NWARP) {
-        const int d = c.d0 + xt;
-        const int px = phys(xt);
-        const T *irow = src_plane + (long long)d * c.n + c.g * G;
-        for (int p = lane; p < cols; p += 32) buf[p * PITCH + px] = d < c.D ? irow[p] : T(0.0);
+    for (int x = warp * V; x < XW; x += NWARP * V) {
+        const int d = c.d0 + x;
+        for (int p = lane; p < cols; p += 32) {
+            const T *irow = src_plane + (long long)d * c.n + c.g * G + p;
+            T v[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[i] = (d + i < c.D) ? irow[(long long)i * c.n] : T(0.0);
+            store_chunk<T>(buf + p * P + x, v);
+        }
     }
 }
 
 // Missing-operand rule of bdrt_core (adrt_cdefs_bdrt.hpp:96-109) for a value read
-// at tile position `pos` from a row whose intermediate ends at `lim`.
+// at logical tile position `pos` from a row whose intermediate ends at `lim`.
 template <typename T, bool kMask>
 ADRT_HD T bmask(T v, int pos, int lim, bool odd)
 {
@@ -342,82 +461,113 @@ ADRT_HD T bmask(T v, int pos, int lim, bool odd)
 //   gu[1][b][d'] = gin[2b][d' + 2a + b] + gin[2b+1][d' + 2a + b + 1]
 //   out_{2k}[d]    = gu[k][0][d] + gu[k][1][d]
 //   out_{2k+1}[d'] = gu[k][0][d' + a] + gu[k][1][d' + a + 1]
-// `dt` = D - d0 and `ag` = global base angle give each row's end:
+// The thread reads the four parent windows at logical positions [x, x+4+p) and
+// produces child j at logical positions x - j*a + [0,4), stored at x (skew j*a).
+// Parent row p carries skew jp*(4a+p) (jp = index of the parent block in the
+// previous step, 0 if the rows were loaded); JP = jp & 3 fixes the residues.
+// `dt` = D - d0 and `ag` = global base angle give each row's logical end:
 //   parent rows (block k0 at stage t+2): dt + ag*k0*4e;  node k=1: + ag*2e.
-template <typename T, int M, bool kMask>
-ADRT_HD void bwd_radix4(const T *in, T *out, int t, int dt, int ag, int tid)
+template <typename T, bool kMask, int JP>
+ADRT_HD void bwd_radix4_item(const T *in, T *out, int e, int k0, int a, int x, int jp, int dt, int ag)
 {
-    constexpr int G = Geo<M>::G;
+    constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
+    constexpr int Q1 = (JP * 1) % L, Q2 = (JP * 2) % L, Q3 = (JP * 3) % L;
+    const T *ip = in + (k0 * 4 * e + 4 * a) * P;
+    const int s0 = jp * 4 * a;  // skew of parent 0; parent p adds jp*p
+    T g0[V], g1[V + 1], g2[V + 2], g3[V + 3];
+    load_window<T, V, 0>(ip + x + s0, g0);
+    load_window<T, V + 1, Q1>(ip + P + (x + s0 + jp - Q1), g1);
+    load_window<T, V + 2, Q2>(ip + 2 * P + (x + s0 + 2 * jp - Q2), g2);
+    load_window<T, V + 3, Q3>(ip + 3 * P + (x + s0 + 3 * jp - Q3), g3);
+    const int lim_p = dt + ag * (k0 * 4 * e);
+    const int lim_1 = lim_p + ag * 2 * e;
+    if (kMask) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) g0[i] = bmask<T, kMask>(g0[i], x + i, lim_p, false);
+#pragma unroll
+        for (int i = 0; i < V + 1; ++i) g1[i] = bmask<T, kMask>(g1[i], x + i, lim_p, true);
+#pragma unroll
+        for (int i = 0; i < V + 2; ++i) g2[i] = bmask<T, kMask>(g2[i], x + i, lim_p, false);
+#pragma unroll
+        for (int i = 0; i < V + 3; ++i) g3[i] = bmask<T, kMask>(g3[i], x + i, lim_p, true);
+    }
+    T u00[V], u01[V + 1], u10[V], u11[V + 1];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        u00[i] = g0[i] + g1[i];
+        u10[i] = g0[i] + g1[i + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < V + 1; ++i) {
+        // odd-angle children: a missing entry must act as -0.0 when it is the
+        // second operand below
+        u01[i] = bmask<T, kMask>(g2[i] + g3[i], x + i, lim_p, true);
+        u11[i] = bmask<T, kMask>(g2[i + 1] + g3[i + 2], x - 2 * a + i, lim_1, true);
+    }
+    T o0[V], o1[V], o2[V], o3[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        o0[i] = u00[i] + u01[i];
+        o1[i] = u00[i] + u01[i + 1];
+        o2[i] = u10[i] + u11[i];
+        o3[i] = u10[i] + u11[i + 1];
+    }
+    store_chunk<T>(out + ((k0 * 4 + 0) * e + a) * P + x, o0);
+    store_chunk<T>(out + ((k0 * 4 + 1) * e + a) * P + x, o1);
+    store_chunk<T>(out + ((k0 * 4 + 2) * e + a) * P + x, o2);
+    store_chunk<T>(out + ((k0 * 4 + 3) * e + a) * P + x, o3);
+}
+
+// rprev = radix of the step that produced the parent rows (0: they were loaded)
+template <typename T, int M, bool kMask>
+ADRT_HD void bwd_radix4(const T *in, T *out, int t, int rprev, int dt, int ag, int tid)
+{
+    constexpr int G = Geo<M>::G, NT = Geo<M>::NT, P = Pitch<T>::value;
     const int e = 1 << t;
     for (int item = tid; item < (G / 4) * NCHUNK; item += NT) {
-        const int gi = item / NCHUNK, ch = item % NCHUNK;
+        const int gi = item / NCHUNK, x = (item % NCHUNK) * V;
         const int k0 = gi >> t, a = gi & (e - 1);
-        const int x = V * ch;
-        const T *ip = in + (k0 * 4 * e + 4 * a) * PITCH;
-        const int lim_p = dt + ag * (k0 * 4 * e);
-        const int lim_1 = lim_p + ag * 2 * e;
-        T g0[V], g1[V + 1], g2[V + 2], g3[V + 3];
-#pragma unroll
-        for (int i = 0; i < V; ++i) g0[i] = bmask<T, kMask>(ip[0 * PITCH + phys(x + i)], x + i, lim_p, false);
-#pragma unroll
-        for (int i = 0; i < V + 1; ++i) g1[i] = bmask<T, kMask>(ip[1 * PITCH + phys(x + i)], x + i, lim_p, true);
-#pragma unroll
-        for (int i = 0; i < V + 2; ++i) g2[i] = bmask<T, kMask>(ip[2 * PITCH + phys(x + i)], x + i, lim_p, false);
-#pragma unroll
-        for (int i = 0; i < V + 3; ++i) g3[i] = bmask<T, kMask>(ip[3 * PITCH + phys(x + i)], x + i, lim_p, true);
-        T u00[V], u01[V + 1], u10[V], u11[V + 1];
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            u00[i] = g0[i] + g1[i];
-            u10[i] = g0[i] + g1[i + 1];
-        }
-#pragma unroll
-        for (int i = 0; i < V + 1; ++i) {
-            // odd-angle children: a missing entry must act as -0.0 when it is the
-            // second operand below
-            u01[i] = bmask<T, kMask>(g2[i] + g3[i], x + i, lim_p, true);
-            u11[i] = bmask<T, kMask>(g2[i + 1] + g3[i + 2], x - 2 * a + i, lim_1, true);
-        }
-        T *o0 = out + ((k0 * 4 + 0) * e + a) * PITCH;
-        T *o1 = out + ((k0 * 4 + 1) * e + a) * PITCH;
-        T *o2 = out + ((k0 * 4 + 2) * e + a) * PITCH;
-        T *o3 = out + ((k0 * 4 + 3) * e + a) * PITCH;
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-            const int p0 = x + i, p1 = x - a + i, p2 = x - 2 * a + i, p3 = x - 3 * a + i;
-            o0[phys(p0)] = u00[i] + u01[i];
-            if (p1 >= 0) o1[phys(p1)] = u00[i] + u01[i + 1];
-            if (p2 >= 0) o2[phys(p2)] = u10[i] + u11[i];
-            if (p3 >= 0) o3[phys(p3)] = u10[i] + u11[i + 1];
+        const int jp = rprev ? (k0 & (rprev - 1)) : 0;
+        // every window (and its over-fetch) must stay inside the row; chunks
+        // that would not only produce positions beyond the valid region
+        if (x + jp * (4 * a + 3) + V + 3 + 3 > P) continue;
+        switch (jp) {
+        case 0: bwd_radix4_item<T, kMask, 0>(in, out, e, k0, a, x, jp, dt, ag); break;
+        case 1: bwd_radix4_item<T, kMask, 1>(in, out, e, k0, a, x, jp, dt, ag); break;
+        case 2: bwd_radix4_item<T, kMask, 2>(in, out, e, k0, a, x, jp, dt, ag); break;
+        default: bwd_radix4_item<T, kMask, 3>(in, out, e, k0, a, x, jp, dt, ag); break;
         }
     }
 }
 
-// ---- transposed radix-2 step: from local stage t+1 rows back to stage t rows ----
+// ---- transposed radix-2 step (always the first transposed step: parents loaded) --
 template <typename T, int M, bool kMask>
 ADRT_HD void bwd_radix2(const T *in, T *out, int t, int dt, int ag, int tid)
 {
-    constexpr int G = Geo<M>::G;
+    constexpr int G = Geo<M>::G, NT = Geo<M>::NT, P = Pitch<T>::value;
     const int e = 1 << t;
     for (int item = tid; item < (G / 2) * NCHUNK; item += NT) {
-        const int gi = item / NCHUNK, ch = item % NCHUNK;
+        const int gi = item / NCHUNK, x = (item % NCHUNK) * V;
         const int k = gi >> t, b = gi & (e - 1);
-        const int x = V * ch;
-        const T *ip = in + (k * 2 * e + 2 * b) * PITCH;
+        const T *ip = in + (k * 2 * e + 2 * b) * P;
         const int lim_p = dt + ag * (k * 2 * e);
         T g0[V], g1[V + 1];
+        load_window<T, V, 0>(ip + x, g0);
+        load_window<T, V + 1, 0>(ip + P + x, g1);
+        if (kMask) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) g0[i] = bmask<T, kMask>(ip[phys(x + i)], x + i, lim_p, false);
+            for (int i = 0; i < V; ++i) g0[i] = bmask<T, kMask>(g0[i], x + i, lim_p, false);
 #pragma unroll
-        for (int i = 0; i < V + 1; ++i) g1[i] = bmask<T, kMask>(ip[PITCH + phys(x + i)], x + i, lim_p, true);
-        T *oA = out + ((2 * k) * e + b) * PITCH;
-        T *oB = out + ((2 * k + 1) * e + b) * PITCH;
+            for (int i = 0; i < V + 1; ++i) g1[i] = bmask<T, kMask>(g1[i], x + i, lim_p, true);
+        }
+        T oA[V], oB[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int pB = x - b + i;
-            oA[phys(x + i)] = g0[i] + g1[i];
-            if (pB >= 0) oB[phys(pB)] = g0[i] + g1[i + 1];
+            oA[i] = g0[i] + g1[i];
+            oB[i] = g0[i] + g1[i + 1];
         }
+        store_chunk<T>(out + ((2 * k) * e + b) * P + x, oA);
+        store_chunk<T>(out + ((2 * k + 1) * e + b) * P + x, oB);   // skew b
     }
 }
 
@@ -429,39 +579,33 @@ ADRT_HD void bwd_step(T *bufA, T *bufB, int step, int dt, int ag, int tid)
     const T *in = (step & 1) ? bufB : bufA;
     T *out = (step & 1) ? bufA : bufB;
     const int t = 2 * (num_steps(M) - 1 - step);
-    if (t + 2 <= M) bwd_radix4<T, M, kMask>(in, out, t, dt, ag, tid);
-    else bwd_radix2<T, M, kMask>(in, out, t, dt, ag, tid);
+    if (t + 2 <= M) {
+        // radix of the previous transposed step: 2 if that was the odd last stage
+        const int rprev = step == 0 ? 0 : ((t + 2 + 2 <= M) ? 4 : 2);
+        bwd_radix4<T, M, kMask>(in, out, t, rprev, dt, ag, tid);
+    } else {
+        bwd_radix2<T, M, kMask>(in, out, t, dt, ag, tid);
+    }
 }
 
 // Output row j -> workspace row (k0*G + j)*e + a_g at offset d0 + xc - a_g*j.
 template <typename T, int M>
 ADRT_HD void bwd_store_wrows(const T *buf, T *dst_plane, const TileCtx &c, bool zero, int tid)
 {
-    constexpr int G = Geo<M>::G, TD = Geo<M>::TD;
+    constexpr int G = Geo<M>::G, TD = Geo<M>::TD, NWARP = Geo<M>::NWARP, P = Pitch<T>::value, L = VecOf<T>::L;
     const int warp = tid >> 5, lane = tid & 31;
     for (int j = warp; j < G; j += NWARP) {
         T *row = dst_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.out_pitch;
-        const int shift = c.a_g * j;
-        for (int xc = lane; xc < TD; xc += 32) {
-            const int d = c.d0 + xc - shift;
-            if (d >= 0 && d < c.D) row[d] = zero ? T(0.0) : buf[j * PITCH + phys(xc)];
+        const int dbase = c.d0 - c.a_g * j;
+        if (!zero && (dbase % L) == 0 && dbase >= 0 && dbase + TD <= c.D) {
+            for (int xc = lane * L; xc < TD; xc += 32 * L)
+                *reinterpret_cast<Pack<T> *>(row + dbase + xc) = *reinterpret_cast<const Pack<T> *>(buf + j * P + xc);
+        } else {
+            for (int xc = lane; xc < TD; xc += 32) {
+                const int d = dbase + xc;
+                if (d >= 0 && d < c.D) row[d] = zero ? T(0.0) : buf[j * P + xc];
+            }
         }
-    }
-}
-
-// Public layout: column g*G + j (last transposed pass: e = 1, a_g = 0).
-template <typename T, int M>
-ADRT_HD void bwd_store_qcols(const T *buf, T *dst_plane, const TileCtx &c, int tid)
-{
-    constexpr int G = Geo<M>::G, TD = Geo<M>::TD;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int cols = G < c.n ? G : c.n;
-    for (int xc = warp; xc < TD; xc += NWARP) {
-        const int d = c.d0 + xc;
-        if (d >= c.D) break;
-        const int px = phys(xc);
-        T *orow = dst_plane + (long long)d * c.n + c.g * G;
-        for (int j = lane; j < cols; j += 32) orow[j] = buf[j * PITCH + px];
     }
 }
 
@@ -488,15 +632,22 @@ struct FwdProgram {
     {
         int sup = c.n + c.a_g * G + G - 1;  // first offset at which every output row is zero
         if (sup > c.D) sup = c.D;
-        if (c.d0 >= c.D) return TILE_SKIP;
-        if (c.d0 >= sup) return STOREK == STORE_QCOLS ? TILE_ZERO : TILE_SKIP;
+        if (STOREK == STORE_QCOLS) {
+            if (c.d0 >= c.D) return TILE_SKIP;
+        } else {
+            if (c.d0 >= c.out_pitch) return TILE_SKIP;
+        }
+        if (c.d0 >= sup) return TILE_ZERO;
         return TILE_FULL;
     }
 
     ADRT_HD static void phase(int ph, int mode, T *bufA, T *bufB, const T *src, T *dst, const TileCtx &c, int tid)
     {
         if (mode == TILE_ZERO) {
-            if (ph == 0) fwd_store_qcols_zero<T, M>(dst, c, tid);
+            if (ph == 0) {
+                if (STOREK == STORE_QCOLS) store_qcols<T, M>(bufA, dst, c, 0, true, tid);
+                else fwd_store_wrows<T, M>(bufA, dst, c, true, tid);
+            }
             return;
         }
         if (ph == 0) {
@@ -506,8 +657,8 @@ struct FwdProgram {
             fwd_step<T, M>(bufA, bufB, ph - 1, tid);
         } else {
             const T *res = (num_steps(M) & 1) ? bufB : bufA;
-            if (STOREK == STORE_QCOLS) fwd_store_qcols<T, M>(res, dst, c, tid);
-            else fwd_store_wrows<T, M>(res, dst, c, tid);
+            if (STOREK == STORE_QCOLS) store_qcols<T, M>(res, dst, c, Geo<M>::HALO, false, tid);
+            else fwd_store_wrows<T, M>(res, dst, c, false, tid);
         }
     }
 };
@@ -521,7 +672,7 @@ struct BwdProgram {
     {
         if (c.d0 >= c.D + c.a_g * (G - 1)) return TILE_SKIP;   // no output row reaches this far
         if (c.d0 >= c.D) return STOREK == STORE_QCOLS ? TILE_SKIP : TILE_ZERO;
-        if (c.d0 + XT > c.D) return TILE_FULL_MASKED;
+        if (c.d0 + XW + 8 > c.D) return TILE_FULL_MASKED;
         return TILE_FULL;
     }
 
@@ -539,7 +690,7 @@ struct BwdProgram {
             else bwd_step<T, M, false>(bufA, bufB, ph - 1, c.D - c.d0, c.a_g, tid);
         } else {
             const T *res = (num_steps(M) & 1) ? bufB : bufA;
-            if (STOREK == STORE_QCOLS) bwd_store_qcols<T, M>(res, dst, c, tid);
+            if (STOREK == STORE_QCOLS) store_qcols<T, M>(res, dst, c, 0, false, tid);
             else bwd_store_wrows<T, M>(res, dst, c, false, tid);
         }
     }

@@ -23,7 +23,10 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
 {
     using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
                                            tile::BwdProgram<T, M, LOADK, STOREK>>::type;
-    std::vector<T> bufA((size_t)tile::Geo<M>::G * tile::PITCH), bufB((size_t)tile::Geo<M>::G * tile::PITCH);
+    // Pack<T> accesses need 16-byte alignment: allocate as Pack vectors
+    const size_t cells = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value;
+    std::vector<tile::Pack<T>> storeA(cells / tile::VecOf<T>::L + 1), storeB(cells / tile::VecOf<T>::L + 1);
+    T *bufA = reinterpret_cast<T *>(storeA.data()), *bufB = reinterpret_cast<T *>(storeB.data());
     const int e = 1 << p.s;
     for (int plane = 0; plane < planes; ++plane)
         for (int by = 0; by < p.grid_y; ++by)
@@ -40,12 +43,11 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
                 else sp = src + (long long)plane * sps;
                 T *dp = dst + (long long)plane * dps;
                 // poison shared memory so that reads of never-written cells are visible
-                for (auto &v : bufA) v = T(1e30);
-                for (auto &v : bufB) v = T(-1e30);
+                for (size_t i = 0; i < cells; ++i) { bufA[i] = T(1e30); bufB[i] = T(-1e30); }
                 const int nph = mode == tile::TILE_ZERO ? 1 : Prog::kPhases;
                 for (int ph = 0; ph < nph; ++ph)
-                    for (int tid = 0; tid < tile::NT; ++tid)
-                        Prog::phase(ph, mode, bufA.data(), bufB.data(), sp, dp, c, tid);
+                    for (int tid = 0; tid < tile::Geo<M>::NT; ++tid)
+                        Prog::phase(ph, mode, bufA, bufB, sp, dp, c, tid);
             }
 }
 
