@@ -207,18 +207,41 @@ ADRT_HD void fwd_load_image(T *buf, const T *img, const TileCtx &c, int tid)
     } else {
         // image rows are contiguous along r: lanes walk the tile rows j, each
         // thread gathers V consecutive offsets and stores them as one vector
-        for (int x = warp * V; x < XW; x += NWARP * V) {
-            for (int j = lane; j < rows; j += 32) {
-                const int r = c.g * G + j;
-                T v[V];
+        constexpr int NIT = XW / (NWARP * V);
+        const bool fast = dbase >= 0 && dbase + XW <= n;
+        for (int j = lane; j < rows; j += 32) {
+            const int r = c.g * G + j;
+            T *b = buf + j * P;
+            if (fast) {
+                // q1 walks the image rows downwards, q2 upwards
+                const long long step = (c.q == 1) ? -(long long)n : (long long)n;
+                const T *ib = (c.q == 1) ? img + (long long)(n - 1 - dbase) * n + r : img + (long long)dbase * n + r;
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    const int d = dbase + x + i;
-                    if (d < 0) v[i] = T(-0.0);
-                    else if (d < n) v[i] = (c.q == 1) ? img[(long long)(n - 1 - d) * n + r] : img[(long long)d * n + r];
-                    else v[i] = T(0.0);
+                for (int it0 = 0; it0 < NIT; it0 += 2) {
+                    T v[2][V];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int x = ((it0 + u) * NWARP + warp) * V;
+#pragma unroll
+                        for (int i = 0; i < V; ++i) v[u][i] = ib[(long long)(x + i) * step];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) store_chunk<T>(b + ((it0 + u) * NWARP + warp) * V, v[u]);
                 }
-                store_chunk<T>(buf + j * P + x, v);
+            } else {
+#pragma unroll 2
+                for (int it = 0; it < NIT; ++it) {
+                    const int x = (it * NWARP + warp) * V;
+                    T v[V];
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        const int d = dbase + x + i;
+                        if (d < 0) v[i] = T(-0.0);
+                        else if (d < n) v[i] = (c.q == 1) ? img[(long long)(n - 1 - d) * n + r] : img[(long long)d * n + r];
+                        else v[i] = T(0.0);
+                    }
+                    store_chunk<T>(b + x, v);
+                }
             }
         }
     }
@@ -376,23 +399,33 @@ template <typename T, int M>
 ADRT_HD void store_qcols(const T *buf, T *dst_plane, const TileCtx &c, int xoff, bool zero, int tid)
 {
     constexpr int G = Geo<M>::G, TD = Geo<M>::TD, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    constexpr int NIT = (TD + NWARP * V - 1) / (NWARP * V);
     const int warp = tid >> 5, lane = tid & 31;
     const int cols = G < c.n ? G : c.n;
-    for (int xc = warp * V; xc < TD; xc += NWARP * V) {
-        const int d = c.d0 + xc;
-        if (d >= c.D) break;
-        for (int p = lane; p < cols; p += 32) {
+    const bool fast = c.d0 + TD <= c.D;
+    for (int p = lane; p < cols; p += 32) {
+        T *o = dst_plane + (long long)c.d0 * c.n + c.g * G + p;
+        const T *b = buf + p * P + xoff;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int xc = (it * NWARP + warp) * V;
+            if (xc >= TD) break;
             T v[V];
             if (zero) {
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = T(0.0);
             } else {
-                load_window<T, V, 0>(buf + p * P + xoff + xc, v);
+                load_window<T, V, 0>(b + xc, v);
             }
-            T *o = dst_plane + (long long)d * c.n + c.g * G + p;
+            T *oo = o + (long long)xc * c.n;
+            if (fast) {
 #pragma unroll
-            for (int i = 0; i < V; ++i)
-                if (d + i < c.D) o[(long long)i * c.n] = v[i];
+                for (int i = 0; i < V; ++i) oo[(long long)i * c.n] = v[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    if (c.d0 + xc + i < c.D) oo[(long long)i * c.n] = v[i];
+            }
         }
     }
 }
@@ -433,16 +466,38 @@ template <typename T, int M>
 ADRT_HD void bwd_load_qcols(T *buf, const T *src_plane, const TileCtx &c, int tid)
 {
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    constexpr int NIT = XW / (NWARP * V);
     const int warp = tid >> 5, lane = tid & 31;
     const int cols = G < c.n ? G : c.n;
-    for (int x = warp * V; x < XW; x += NWARP * V) {
-        const int d = c.d0 + x;
-        for (int p = lane; p < cols; p += 32) {
-            const T *irow = src_plane + (long long)d * c.n + c.g * G + p;
-            T v[V];
+    const bool fast = c.d0 + XW <= c.D;
+    for (int p = lane; p < cols; p += 32) {
+        const T *ib = src_plane + (long long)c.d0 * c.n + c.g * G + p;
+        T *b = buf + p * P;
+        if (fast) {
 #pragma unroll
-            for (int i = 0; i < V; ++i) v[i] = (d + i < c.D) ? irow[(long long)i * c.n] : T(0.0);
-            store_chunk<T>(buf + p * P + x, v);
+            for (int it0 = 0; it0 < NIT; it0 += 2) {
+                // two chunks (8 independent loads) in flight per thread
+                T v[2][V];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int x = ((it0 + u) * NWARP + warp) * V;
+                    const T *ir = ib + (long long)x * c.n;
+#pragma unroll
+                    for (int i = 0; i < V; ++i) v[u][i] = ir[(long long)i * c.n];
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) store_chunk<T>(b + ((it0 + u) * NWARP + warp) * V, v[u]);
+            }
+        } else {
+#pragma unroll 2
+            for (int it = 0; it < NIT; ++it) {
+                const int x = (it * NWARP + warp) * V;
+                const T *ir = ib + (long long)x * c.n;
+                T v[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = (c.d0 + x + i < c.D) ? ir[(long long)i * c.n] : T(0.0);
+                store_chunk<T>(b + x, v);
+            }
         }
     }
 }
@@ -593,17 +648,31 @@ template <typename T, int M>
 ADRT_HD void bwd_store_wrows(const T *buf, T *dst_plane, const TileCtx &c, bool zero, int tid)
 {
     constexpr int G = Geo<M>::G, TD = Geo<M>::TD, NWARP = Geo<M>::NWARP, P = Pitch<T>::value, L = VecOf<T>::L;
+    constexpr int NS = (TD + 31) / 32;
     const int warp = tid >> 5, lane = tid & 31;
     for (int j = warp; j < G; j += NWARP) {
         T *row = dst_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.out_pitch;
         const int dbase = c.d0 - c.a_g * j;
-        if (!zero && (dbase % L) == 0 && dbase >= 0 && dbase + TD <= c.D) {
-            for (int xc = lane * L; xc < TD; xc += 32 * L)
-                *reinterpret_cast<Pack<T> *>(row + dbase + xc) = *reinterpret_cast<const Pack<T> *>(buf + j * P + xc);
+        const T *b = buf + j * P;
+        const bool inside = dbase >= 0 && dbase + TD <= c.D;
+        if (!zero && inside && (dbase % L) == 0) {
+#pragma unroll
+            for (int k = 0; k < TD / (32 * L) + 1; ++k) {
+                const int xc = (k * 32 + lane) * L;
+                if (xc < TD) *reinterpret_cast<Pack<T> *>(row + dbase + xc) = *reinterpret_cast<const Pack<T> *>(b + xc);
+            }
+        } else if (!zero && inside) {
+            T v[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) v[k] = b[k * 32 + lane];   // reads past TD stay inside the tile row
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (k * 32 + lane < TD) row[dbase + k * 32 + lane] = v[k];
         } else {
-            for (int xc = lane; xc < TD; xc += 32) {
-                const int d = dbase + xc;
-                if (d >= 0 && d < c.D) row[d] = zero ? T(0.0) : buf[j * P + xc];
+#pragma unroll 2
+            for (int k = 0; k < NS; ++k) {
+                const int xc = k * 32 + lane, d = dbase + xc;
+                if (xc < TD && d >= 0 && d < c.D) row[d] = zero ? T(0.0) : b[xc];
             }
         }
     }
