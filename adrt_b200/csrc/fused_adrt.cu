@@ -21,7 +21,7 @@ struct PassArgs {
 };
 
 template <typename T, int M, int LOADK, int STOREK, bool kForward>
-__global__ void __launch_bounds__(tile::Geo<M>::NT)
+__global__ void __launch_bounds__(tile::Geo<M>::NT, tile::Geo<M>::G >= 64 ? 1 : 3)
 pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
 {
     using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
@@ -78,7 +78,7 @@ template <typename T, int M, bool kForward>
 int dispatch_kinds(int load, int store, const T *src, T *dst, const PassArgs &a, int gx, int gy, cudaStream_t s)
 {
     using namespace tile;
-    if (kForward) {
+    if constexpr (kForward) {
         if (load == LOAD_IMAGE && store == STORE_WROWS) return launch_pass<T, M, LOAD_IMAGE, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);
         if (load == LOAD_IMAGE && store == STORE_QCOLS) return launch_pass<T, M, LOAD_IMAGE, STORE_QCOLS, kForward>(src, dst, a, gx, gy, s);
         if (load == LOAD_WROWS && store == STORE_WROWS) return launch_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);

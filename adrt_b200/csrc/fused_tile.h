@@ -216,7 +216,7 @@ ADRT_HD void fwd_load_image(T *buf, const T *img, const TileCtx &c, int tid)
                 // q1 walks the image rows downwards, q2 upwards
                 const long long step = (c.q == 1) ? -(long long)n : (long long)n;
                 const T *ib = (c.q == 1) ? img + (long long)(n - 1 - dbase) * n + r : img + (long long)dbase * n + r;
-#pragma unroll
+#pragma unroll 1
                 for (int it0 = 0; it0 < NIT; it0 += 2) {
                     T v[2][V];
 #pragma unroll
@@ -406,7 +406,7 @@ ADRT_HD void store_qcols(const T *buf, T *dst_plane, const TileCtx &c, int xoff,
     for (int p = lane; p < cols; p += 32) {
         T *o = dst_plane + (long long)c.d0 * c.n + c.g * G + p;
         const T *b = buf + p * P + xoff;
-#pragma unroll
+#pragma unroll 2
         for (int it = 0; it < NIT; ++it) {
             const int xc = (it * NWARP + warp) * V;
             if (xc >= TD) break;
@@ -474,7 +474,7 @@ ADRT_HD void bwd_load_qcols(T *buf, const T *src_plane, const TileCtx &c, int ti
         const T *ib = src_plane + (long long)c.d0 * c.n + c.g * G + p;
         T *b = buf + p * P;
         if (fast) {
-#pragma unroll
+#pragma unroll 1
             for (int it0 = 0; it0 < NIT; it0 += 2) {
                 // two chunks (8 independent loads) in flight per thread
                 T v[2][V];
