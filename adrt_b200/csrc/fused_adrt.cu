@@ -21,14 +21,14 @@ struct PassArgs {
 };
 
 template <typename T, int M, int LOADK, int STOREK, bool kForward>
-__global__ void __launch_bounds__(tile::Geo<M>::NT, tile::Geo<M>::G >= 64 ? 1 : 3)
+__global__ void __launch_bounds__(tile::Geo<M>::NT, sizeof(T) == 8 ? tile::Geo<M>::MIN_CTAS / 2 : tile::Geo<M>::MIN_CTAS)
 pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
 {
     using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
                                            tile::BwdProgram<T, M, LOADK, STOREK>>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *bufA = reinterpret_cast<T *>(smem_raw);
-    T *bufB = bufA + tile::Geo<M>::G * tile::Pitch<T>::value;
+    T *buf = reinterpret_cast<T *>(smem_raw);
+    T regs[tile::NREG];
 
     tile::TileCtx c;
     c.n = a.n;
@@ -55,7 +55,7 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
         T *dp = dst + (long long)plane * a.dst_plane_stride;
         const int nph = mode == tile::TILE_ZERO ? 1 : Prog::kPhases;
         for (int ph = 0; ph < nph; ++ph) {
-            Prog::phase(ph, mode, bufA, bufB, sp, dp, c, threadIdx.x);
+            Prog::phase(ph, mode, buf, regs, sp, dp, c, threadIdx.x);
             __syncthreads();
         }
     }
@@ -65,7 +65,7 @@ template <typename T, int M, int LOADK, int STOREK, bool kForward>
 int launch_pass(const T *src, T *dst, const PassArgs &a, int grid_x, int grid_y, cudaStream_t s)
 {
     auto kern = pass_kernel<T, M, LOADK, STOREK, kForward>;
-    const size_t smem = 2ull * tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T);
+    const size_t smem = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T);
     // per device, so not cached in a static: a process may drive several GPUs
     ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)grid_x, (unsigned)grid_y, (unsigned)(a.planes < 65535 ? a.planes : 65535));
@@ -102,10 +102,7 @@ int dispatch_pass(const plan::Pass &p, const T *src, T *dst, const PassArgs &a, 
     case 3: return dispatch_kinds<T, 3, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
     case 4: return dispatch_kinds<T, 4, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
     case 5: return dispatch_kinds<T, 5, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
-    case 6:
-        // two ping-pong tiles of 64 rows only fit in shared memory for 4-byte elements
-        if constexpr (sizeof(T) == 4) return dispatch_kinds<T, 6, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
-        break;
+    case 6: return dispatch_kinds<T, 6, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
     }
     set_error("internal: unsupported stages per pass %d", p.M);
     return ADRT_B200_EINVAL;

@@ -41,12 +41,12 @@ inline int ilog2(int64_t n)
     return k;
 }
 
-// Largest M whose two ping-pong tile buffers fit in shared memory (227 KB).
+// Largest M whose (single, in-place) tile buffer fits in shared memory (227 KB).
 inline int max_stages_per_pass(size_t elem_size)
 {
     int m = 1;
     const size_t pitch = elem_size == 8 ? tile::Pitch<double>::value : tile::Pitch<float>::value;
-    while (m < 6 && 2ull * (2ull << m) * pitch * elem_size <= 227ull * 1024) ++m;
+    while (m < 6 && (2ull << m) * pitch * elem_size <= 227ull * 1024) ++m;
     return m;
 }
 

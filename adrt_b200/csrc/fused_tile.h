@@ -80,7 +80,8 @@ template <int M> struct Geo {
     // offsets consumed by M stages, rounded so that chunk boundaries stay aligned
     static constexpr int HALO = G < 4 ? 4 : G;
     static constexpr int TD = XW - HALO;      // valid output offsets per tile
-    static constexpr int NT = G >= 64 ? 512 : 256;   // threads per CTA
+    static constexpr int NT = G >= 64 ? 512 : 256;   // threads per CTA: one warp per radix-4 group
+    static constexpr int MIN_CTAS = G >= 64 ? 2 : 4; // launch-bounds target (caps registers at 64)
     static constexpr int NWARP = NT / 32;
 };
 
@@ -110,7 +111,7 @@ ADRT_HD void load_window(const T *p, T (&dst)[N])
 }
 
 template <typename T>
-ADRT_HD void store_chunk(T *p, const T (&src)[V])
+ADRT_HD void store_chunk(T *p, const T *src)
 {
     constexpr int L = VecOf<T>::L;
 #pragma unroll
@@ -247,20 +248,25 @@ ADRT_HD void fwd_load_image(T *buf, const T *img, const TileCtx &c, int tid)
     }
 }
 
+// Steps run IN PLACE on the single tile buffer: every thread first reads its
+// operand windows and computes its outputs into registers (xxx_compute), the
+// CTA synchronises, then the outputs are written over the tile (xxx_store) and
+// the CTA synchronises again.  A thread owns one butterfly group (one warp per
+// group) and the two chunks x = 4*lane and 4*lane + 128 of it, so row pointers
+// and the alignment variant are set up once for 2 x 4 offsets.
+constexpr int NREG = 32;   // outputs a thread holds across the barrier of a step
+constexpr int CHUNKS = 2;  // chunks per thread and group
+
 // ---- radix-4 step: local stages t and t+1 (e = 2^t) ---------------------------
 //   u[k][al][d]  = in_{2k}[d] + in_{2k+1}[d - a - al]                 (stage t)
 //   out[p][d]    = u[0][p>>1][d] + u[1][p>>1][d - 2a - ceil(p/2)]     (stage t+1)
 // with input rows r_j = (k0*4 + j)*e + a, output rows k0*4e + 4a + p.
 // AM = a & 3 fixes the alignment residues of the three shifted windows.
 template <typename T, int AM>
-ADRT_HD void fwd_radix4_item(const T *in, T *out, int e, int k0, int a, int x)
+ADRT_HD void fwd_radix4_chunk(const T *r0, const T *r1, const T *r2, const T *r3, int a, int x, T *o)
 {
-    constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
+    constexpr int L = VecOf<T>::L;
     constexpr int Q1 = neg_mod(AM + 1, L), Q2 = neg_mod(2 * AM + 2, L), Q3 = neg_mod(3 * AM + 3, L);
-    const T *r0 = in + ((k0 * 4 + 0) * e + a) * P;
-    const T *r1 = in + ((k0 * 4 + 1) * e + a) * P;
-    const T *r2 = in + ((k0 * 4 + 2) * e + a) * P;
-    const T *r3 = in + ((k0 * 4 + 3) * e + a) * P;
     T y0[V], y1[V + 1], y2[V + 2], y3[V + 3];
     load_window<T, V, 0>(r0 + x, y0);
     load_window<T, V + 1, Q1>(r1 + (x - a - 1 - Q1), y1);
@@ -277,93 +283,144 @@ ADRT_HD void fwd_radix4_item(const T *in, T *out, int e, int k0, int a, int x)
         u10[i] = y2[i] + y3[i + 1];
         u11[i] = y2[i] + y3[i];
     }
-    T o0[V], o1[V], o2[V], o3[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        o0[i] = u00[i] + u10[i + 2];
-        o1[i] = u00[i] + u10[i + 1];
-        o2[i] = u01[i] + u11[i + 1];
-        o3[i] = u01[i] + u11[i];
+        o[0 * V + i] = u00[i] + u10[i + 2];
+        o[1 * V + i] = u00[i] + u10[i + 1];
+        o[2 * V + i] = u01[i] + u11[i + 1];
+        o[3 * V + i] = u01[i] + u11[i];
     }
-    T *o = out + (k0 * 4 * e + 4 * a) * P + x;
-    store_chunk<T>(o, o0);
-    store_chunk<T>(o + P, o1);
-    store_chunk<T>(o + 2 * P, o2);
-    store_chunk<T>(o + 3 * P, o3);
+}
+
+template <typename T, int AM>
+ADRT_HD void fwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int lo_out, T (&o)[NREG])
+{
+    constexpr int P = Pitch<T>::value;
+    const T *r0 = buf + ((k0 * 4) * e + a) * P;
+    const T *r1 = r0 + e * P, *r2 = r1 + e * P, *r3 = r2 + e * P;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int x = (lane + 32 * c) * V;
+        if (x >= lo_out) fwd_radix4_chunk<T, AM>(r0, r1, r2, r3, a, x, &o[c * 4 * V]);
+    }
 }
 
 template <typename T, int M>
-ADRT_HD void fwd_radix4(const T *in, T *out, int t, int tid)
+ADRT_HD void fwd_radix4_compute(const T *buf, int t, int tid, T (&o)[NREG])
 {
-    constexpr int G = Geo<M>::G, NT = Geo<M>::NT;
-    const int e = 1 << t;
-    const int lo_out = 4 * e;  // chunks below this would read before the row start
-    for (int item = tid; item < (G / 4) * NCHUNK; item += NT) {
-        const int gi = item / NCHUNK, x = (item % NCHUNK) * V;
-        if (x < lo_out) continue;
-        const int k0 = gi >> t, a = gi & (e - 1);
-        switch (a & 3) {
-        case 0: fwd_radix4_item<T, 0>(in, out, e, k0, a, x); break;
-        case 1: fwd_radix4_item<T, 1>(in, out, e, k0, a, x); break;
-        case 2: fwd_radix4_item<T, 2>(in, out, e, k0, a, x); break;
-        default: fwd_radix4_item<T, 3>(in, out, e, k0, a, x); break;
+    constexpr int G = Geo<M>::G;
+    const int e = 1 << t, gi = tid >> 5, lane = tid & 31;
+    if (gi >= G / 4) return;
+    const int k0 = gi >> t, a = gi & (e - 1), lo_out = 4 * e;
+    switch (a & 3) {
+    case 0: fwd_radix4_group<T, 0>(buf, e, k0, a, lane, lo_out, o); break;
+    case 1: fwd_radix4_group<T, 1>(buf, e, k0, a, lane, lo_out, o); break;
+    case 2: fwd_radix4_group<T, 2>(buf, e, k0, a, lane, lo_out, o); break;
+    default: fwd_radix4_group<T, 3>(buf, e, k0, a, lane, lo_out, o); break;
+    }
+}
+
+template <typename T, int M>
+ADRT_HD void fwd_radix4_store(T *buf, int t, int tid, const T (&o)[NREG])
+{
+    constexpr int G = Geo<M>::G, P = Pitch<T>::value;
+    const int e = 1 << t, gi = tid >> 5, lane = tid & 31;
+    if (gi >= G / 4) return;
+    const int k0 = gi >> t, a = gi & (e - 1), lo_out = 4 * e;
+    T *orow = buf + (k0 * 4 * e + 4 * a) * P;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int x = (lane + 32 * c) * V;
+        if (x >= lo_out) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) store_chunk<T>(orow + p * P + x, &o[(c * 4 + p) * V]);
         }
     }
 }
 
-// ---- radix-2 step: local stage t ------------------------------------------------
+// ---- radix-2 step: local stage t; a thread serves two groups ---------------------
 template <typename T, int BM>
-ADRT_HD void fwd_radix2_item(const T *in, T *out, int e, int k, int b, int x)
+ADRT_HD void fwd_radix2_group(const T *buf, int e, int k, int b, int lane, int lo_out, T *o)
 {
     constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
     constexpr int Q = neg_mod(BM + 1, L);
-    const T *rA = in + ((2 * k) * e + b) * P;
-    const T *rB = in + ((2 * k + 1) * e + b) * P;
-    T yA[V], yB[V + 1];
-    load_window<T, V, 0>(rA + x, yA);
-    load_window<T, V + 1, Q>(rB + (x - b - 1 - Q), yB);
-    T oe[V], oo[V];
+    const T *rA = buf + ((2 * k) * e + b) * P;
+    const T *rB = rA + e * P;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        oe[i] = yA[i] + yB[i + 1];
-        oo[i] = yA[i] + yB[i];
-    }
-    T *o = out + (k * 2 * e + 2 * b) * P + x;
-    store_chunk<T>(o, oe);
-    store_chunk<T>(o + P, oo);
-}
-
-template <typename T, int M>
-ADRT_HD void fwd_radix2(const T *in, T *out, int t, int tid)
-{
-    constexpr int G = Geo<M>::G, NT = Geo<M>::NT;
-    const int e = 1 << t;
-    const int lo_out = 2 * e < 4 ? 4 : 2 * e;
-    for (int item = tid; item < (G / 2) * NCHUNK; item += NT) {
-        const int gi = item / NCHUNK, x = (item % NCHUNK) * V;
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int x = (lane + 32 * c) * V;
         if (x < lo_out) continue;
-        const int k = gi >> t, b = gi & (e - 1);
-        switch (b & 3) {
-        case 0: fwd_radix2_item<T, 0>(in, out, e, k, b, x); break;
-        case 1: fwd_radix2_item<T, 1>(in, out, e, k, b, x); break;
-        case 2: fwd_radix2_item<T, 2>(in, out, e, k, b, x); break;
-        default: fwd_radix2_item<T, 3>(in, out, e, k, b, x); break;
+        T yA[V], yB[V + 1];
+        load_window<T, V, 0>(rA + x, yA);
+        load_window<T, V + 1, Q>(rB + (x - b - 1 - Q), yB);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            o[(c * 2 + 0) * V + i] = yA[i] + yB[i + 1];
+            o[(c * 2 + 1) * V + i] = yA[i] + yB[i];
         }
     }
 }
 
-// Number of barrier-separated compute steps for M stages (radix-4 first, one
-// radix-2 at the end when M is odd).
+template <typename T, int M>
+ADRT_HD void fwd_radix2_compute(const T *buf, int t, int tid, T (&o)[NREG])
+{
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP;
+    const int e = 1 << t, lane = tid & 31, lo_out = 2 * e < 4 ? 4 : 2 * e;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int gi = (tid >> 5) + u * NWARP;
+        if (gi >= G / 2) continue;
+        const int k = gi >> t, b = gi & (e - 1);
+        T *ou = &o[u * CHUNKS * 2 * V];
+        switch (b & 3) {
+        case 0: fwd_radix2_group<T, 0>(buf, e, k, b, lane, lo_out, ou); break;
+        case 1: fwd_radix2_group<T, 1>(buf, e, k, b, lane, lo_out, ou); break;
+        case 2: fwd_radix2_group<T, 2>(buf, e, k, b, lane, lo_out, ou); break;
+        default: fwd_radix2_group<T, 3>(buf, e, k, b, lane, lo_out, ou); break;
+        }
+    }
+}
+
+template <typename T, int M>
+ADRT_HD void fwd_radix2_store(T *buf, int t, int tid, const T (&o)[NREG])
+{
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    const int e = 1 << t, lane = tid & 31, lo_out = 2 * e < 4 ? 4 : 2 * e;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int gi = (tid >> 5) + u * NWARP;
+        if (gi >= G / 2) continue;
+        const int k = gi >> t, b = gi & (e - 1);
+        T *orow = buf + (k * 2 * e + 2 * b) * P;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int x = (lane + 32 * c) * V;
+            if (x >= lo_out) {
+                store_chunk<T>(orow + x, &o[((u * CHUNKS + c) * 2 + 0) * V]);
+                store_chunk<T>(orow + P + x, &o[((u * CHUNKS + c) * 2 + 1) * V]);
+            }
+        }
+    }
+}
+
+// Number of compute steps for M stages (radix-4 first, one radix-2 at the end
+// when M is odd).  Each step is two barrier-separated phases (compute, store).
 ADRT_HD constexpr int num_steps(int M) { return (M + 1) / 2; }
 
 template <typename T, int M>
-ADRT_HD void fwd_step(T *bufA, T *bufB, int step, int tid)
+ADRT_HD void fwd_step_compute(const T *buf, int step, int tid, T (&o)[NREG])
 {
-    const T *in = (step & 1) ? bufB : bufA;
-    T *out = (step & 1) ? bufA : bufB;
     const int t = 2 * step;
-    if (t + 2 <= M) fwd_radix4<T, M>(in, out, t, tid);
-    else fwd_radix2<T, M>(in, out, t, tid);
+    if (t + 2 <= M) fwd_radix4_compute<T, M>(buf, t, tid, o);
+    else fwd_radix2_compute<T, M>(buf, t, tid, o);
+}
+
+template <typename T, int M>
+ADRT_HD void fwd_step_store(T *buf, int step, int tid, const T (&o)[NREG])
+{
+    const int t = 2 * step;
+    if (t + 2 <= M) fwd_radix4_store<T, M>(buf, t, tid, o);
+    else fwd_radix2_store<T, M>(buf, t, tid, o);
 }
 
 // ---- stores -----------------------------------------------------------------------
@@ -523,19 +580,16 @@ ADRT_HD T bmask(T v, int pos, int lim, bool odd)
 // `dt` = D - d0 and `ag` = global base angle give each row's logical end:
 //   parent rows (block k0 at stage t+2): dt + ag*k0*4e;  node k=1: + ag*2e.
 template <typename T, bool kMask, int JP>
-ADRT_HD void bwd_radix4_item(const T *in, T *out, int e, int k0, int a, int x, int jp, int dt, int ag)
+ADRT_HD void bwd_radix4_chunk(const T *ip, int a, int x, int jp, int lim_p, int lim_1, T *o)
 {
     constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
     constexpr int Q1 = (JP * 1) % L, Q2 = (JP * 2) % L, Q3 = (JP * 3) % L;
-    const T *ip = in + (k0 * 4 * e + 4 * a) * P;
     const int s0 = jp * 4 * a;  // skew of parent 0; parent p adds jp*p
     T g0[V], g1[V + 1], g2[V + 2], g3[V + 3];
     load_window<T, V, 0>(ip + x + s0, g0);
     load_window<T, V + 1, Q1>(ip + P + (x + s0 + jp - Q1), g1);
     load_window<T, V + 2, Q2>(ip + 2 * P + (x + s0 + 2 * jp - Q2), g2);
     load_window<T, V + 3, Q3>(ip + 3 * P + (x + s0 + 3 * jp - Q3), g3);
-    const int lim_p = dt + ag * (k0 * 4 * e);
-    const int lim_1 = lim_p + ag * 2 * e;
     if (kMask) {
 #pragma unroll
         for (int i = 0; i < V; ++i) g0[i] = bmask<T, kMask>(g0[i], x + i, lim_p, false);
@@ -559,88 +613,146 @@ ADRT_HD void bwd_radix4_item(const T *in, T *out, int e, int k0, int a, int x, i
         u01[i] = bmask<T, kMask>(g2[i] + g3[i], x + i, lim_p, true);
         u11[i] = bmask<T, kMask>(g2[i + 1] + g3[i + 2], x - 2 * a + i, lim_1, true);
     }
-    T o0[V], o1[V], o2[V], o3[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        o0[i] = u00[i] + u01[i];
-        o1[i] = u00[i] + u01[i + 1];
-        o2[i] = u10[i] + u11[i];
-        o3[i] = u10[i] + u11[i + 1];
+        o[0 * V + i] = u00[i] + u01[i];
+        o[1 * V + i] = u00[i] + u01[i + 1];
+        o[2 * V + i] = u10[i] + u11[i];
+        o[3 * V + i] = u10[i] + u11[i + 1];
     }
-    store_chunk<T>(out + ((k0 * 4 + 0) * e + a) * P + x, o0);
-    store_chunk<T>(out + ((k0 * 4 + 1) * e + a) * P + x, o1);
-    store_chunk<T>(out + ((k0 * 4 + 2) * e + a) * P + x, o2);
-    store_chunk<T>(out + ((k0 * 4 + 3) * e + a) * P + x, o3);
+}
+
+// every window (and its over-fetch) must stay inside the row; chunks that fail
+// this only produce positions beyond the valid region
+template <typename T>
+ADRT_HD bool bwd_chunk_ok(int x, int jp, int a)
+{
+    return x + jp * (4 * a + 3) + V + 3 + 3 <= Pitch<T>::value;
+}
+
+template <typename T, bool kMask, int JP>
+ADRT_HD void bwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int jp, int dt, int ag, T (&o)[NREG])
+{
+    constexpr int P = Pitch<T>::value;
+    const T *ip = buf + (k0 * 4 * e + 4 * a) * P;
+    const int lim_p = dt + ag * (k0 * 4 * e), lim_1 = lim_p + ag * 2 * e;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int x = (lane + 32 * c) * V;
+        if (bwd_chunk_ok<T>(x, jp, a)) bwd_radix4_chunk<T, kMask, JP>(ip, a, x, jp, lim_p, lim_1, &o[c * 4 * V]);
+    }
 }
 
 // rprev = radix of the step that produced the parent rows (0: they were loaded)
 template <typename T, int M, bool kMask>
-ADRT_HD void bwd_radix4(const T *in, T *out, int t, int rprev, int dt, int ag, int tid)
+ADRT_HD void bwd_radix4_compute(const T *buf, int t, int rprev, int dt, int ag, int tid, T (&o)[NREG])
 {
-    constexpr int G = Geo<M>::G, NT = Geo<M>::NT, P = Pitch<T>::value;
-    const int e = 1 << t;
-    for (int item = tid; item < (G / 4) * NCHUNK; item += NT) {
-        const int gi = item / NCHUNK, x = (item % NCHUNK) * V;
-        const int k0 = gi >> t, a = gi & (e - 1);
-        const int jp = rprev ? (k0 & (rprev - 1)) : 0;
-        // every window (and its over-fetch) must stay inside the row; chunks
-        // that would not only produce positions beyond the valid region
-        if (x + jp * (4 * a + 3) + V + 3 + 3 > P) continue;
-        switch (jp) {
-        case 0: bwd_radix4_item<T, kMask, 0>(in, out, e, k0, a, x, jp, dt, ag); break;
-        case 1: bwd_radix4_item<T, kMask, 1>(in, out, e, k0, a, x, jp, dt, ag); break;
-        case 2: bwd_radix4_item<T, kMask, 2>(in, out, e, k0, a, x, jp, dt, ag); break;
-        default: bwd_radix4_item<T, kMask, 3>(in, out, e, k0, a, x, jp, dt, ag); break;
+    constexpr int G = Geo<M>::G;
+    const int e = 1 << t, gi = tid >> 5, lane = tid & 31;
+    if (gi >= G / 4) return;
+    const int k0 = gi >> t, a = gi & (e - 1);
+    const int jp = rprev ? (k0 & (rprev - 1)) : 0;
+    switch (jp) {
+    case 0: bwd_radix4_group<T, kMask, 0>(buf, e, k0, a, lane, jp, dt, ag, o); break;
+    case 1: bwd_radix4_group<T, kMask, 1>(buf, e, k0, a, lane, jp, dt, ag, o); break;
+    case 2: bwd_radix4_group<T, kMask, 2>(buf, e, k0, a, lane, jp, dt, ag, o); break;
+    default: bwd_radix4_group<T, kMask, 3>(buf, e, k0, a, lane, jp, dt, ag, o); break;
+    }
+}
+
+template <typename T, int M>
+ADRT_HD void bwd_radix4_store(T *buf, int t, int rprev, int tid, const T (&o)[NREG])
+{
+    constexpr int G = Geo<M>::G, P = Pitch<T>::value;
+    const int e = 1 << t, gi = tid >> 5, lane = tid & 31;
+    if (gi >= G / 4) return;
+    const int k0 = gi >> t, a = gi & (e - 1);
+    const int jp = rprev ? (k0 & (rprev - 1)) : 0;
+    T *orow = buf + ((k0 * 4) * e + a) * P;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int x = (lane + 32 * c) * V;
+        if (bwd_chunk_ok<T>(x, jp, a)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) store_chunk<T>(orow + j * e * P + x, &o[(c * 4 + j) * V]);   // skew j*a
         }
     }
 }
 
 // ---- transposed radix-2 step (always the first transposed step: parents loaded) --
 template <typename T, int M, bool kMask>
-ADRT_HD void bwd_radix2(const T *in, T *out, int t, int dt, int ag, int tid)
+ADRT_HD void bwd_radix2_compute(const T *buf, int t, int dt, int ag, int tid, T (&o)[NREG])
 {
-    constexpr int G = Geo<M>::G, NT = Geo<M>::NT, P = Pitch<T>::value;
-    const int e = 1 << t;
-    for (int item = tid; item < (G / 2) * NCHUNK; item += NT) {
-        const int gi = item / NCHUNK, x = (item % NCHUNK) * V;
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    const int e = 1 << t, lane = tid & 31;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int gi = (tid >> 5) + u * NWARP;
+        if (gi >= G / 2) continue;
         const int k = gi >> t, b = gi & (e - 1);
-        const T *ip = in + (k * 2 * e + 2 * b) * P;
+        const T *ip = buf + (k * 2 * e + 2 * b) * P;
         const int lim_p = dt + ag * (k * 2 * e);
-        T g0[V], g1[V + 1];
-        load_window<T, V, 0>(ip + x, g0);
-        load_window<T, V + 1, 0>(ip + P + x, g1);
-        if (kMask) {
 #pragma unroll
-            for (int i = 0; i < V; ++i) g0[i] = bmask<T, kMask>(g0[i], x + i, lim_p, false);
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int x = (lane + 32 * c) * V;
+            T g0[V], g1[V + 1];
+            load_window<T, V, 0>(ip + x, g0);
+            load_window<T, V + 1, 0>(ip + P + x, g1);
+            if (kMask) {
 #pragma unroll
-            for (int i = 0; i < V + 1; ++i) g1[i] = bmask<T, kMask>(g1[i], x + i, lim_p, true);
+                for (int i = 0; i < V; ++i) g0[i] = bmask<T, kMask>(g0[i], x + i, lim_p, false);
+#pragma unroll
+                for (int i = 0; i < V + 1; ++i) g1[i] = bmask<T, kMask>(g1[i], x + i, lim_p, true);
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                o[((u * CHUNKS + c) * 2 + 0) * V + i] = g0[i] + g1[i];
+                o[((u * CHUNKS + c) * 2 + 1) * V + i] = g0[i] + g1[i + 1];
+            }
         }
-        T oA[V], oB[V];
+    }
+}
+
+template <typename T, int M>
+ADRT_HD void bwd_radix2_store(T *buf, int t, int tid, const T (&o)[NREG])
+{
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    const int e = 1 << t, lane = tid & 31;
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            oA[i] = g0[i] + g1[i];
-            oB[i] = g0[i] + g1[i + 1];
+    for (int u = 0; u < 2; ++u) {
+        const int gi = (tid >> 5) + u * NWARP;
+        if (gi >= G / 2) continue;
+        const int k = gi >> t, b = gi & (e - 1);
+        T *oA = buf + ((2 * k) * e + b) * P;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int x = (lane + 32 * c) * V;
+            store_chunk<T>(oA + x, &o[((u * CHUNKS + c) * 2 + 0) * V]);
+            store_chunk<T>(oA + e * P + x, &o[((u * CHUNKS + c) * 2 + 1) * V]);   // skew b
         }
-        store_chunk<T>(out + ((2 * k) * e + b) * P + x, oA);
-        store_chunk<T>(out + ((2 * k + 1) * e + b) * P + x, oB);   // skew b
     }
 }
 
 // Transposed steps run the forward schedule backwards: forward step i covers
 // local stages 2i (and 2i+1); transposed step i undoes forward step nsteps-1-i.
+ADRT_HD constexpr int bwd_step_t(int M, int step) { return 2 * (num_steps(M) - 1 - step); }
+// radix of the previous transposed step: 2 if that was the odd last stage
+ADRT_HD constexpr int bwd_step_rprev(int M, int step) { return step == 0 ? 0 : ((bwd_step_t(M, step) + 4 <= M) ? 4 : 2); }
+
 template <typename T, int M, bool kMask>
-ADRT_HD void bwd_step(T *bufA, T *bufB, int step, int dt, int ag, int tid)
+ADRT_HD void bwd_step_compute(const T *buf, int step, int dt, int ag, int tid, T (&o)[NREG])
 {
-    const T *in = (step & 1) ? bufB : bufA;
-    T *out = (step & 1) ? bufA : bufB;
-    const int t = 2 * (num_steps(M) - 1 - step);
-    if (t + 2 <= M) {
-        // radix of the previous transposed step: 2 if that was the odd last stage
-        const int rprev = step == 0 ? 0 : ((t + 2 + 2 <= M) ? 4 : 2);
-        bwd_radix4<T, M, kMask>(in, out, t, rprev, dt, ag, tid);
-    } else {
-        bwd_radix2<T, M, kMask>(in, out, t, dt, ag, tid);
-    }
+    const int t = bwd_step_t(M, step);
+    if (t + 2 <= M) bwd_radix4_compute<T, M, kMask>(buf, t, bwd_step_rprev(M, step), dt, ag, tid, o);
+    else bwd_radix2_compute<T, M, kMask>(buf, t, dt, ag, tid, o);
+}
+
+template <typename T, int M>
+ADRT_HD void bwd_step_store(T *buf, int step, int tid, const T (&o)[NREG])
+{
+    const int t = bwd_step_t(M, step);
+    if (t + 2 <= M) bwd_radix4_store<T, M>(buf, t, bwd_step_rprev(M, step), tid, o);
+    else bwd_radix2_store<T, M>(buf, t, tid, o);
 }
 
 // Output row j -> workspace row (k0*G + j)*e + a_g at offset d0 + xc - a_g*j.
@@ -691,10 +803,12 @@ namespace tile {
 
 enum TileMode { TILE_SKIP = 0, TILE_ZERO = 1, TILE_FULL = 2, TILE_FULL_MASKED = 3 };
 
+// Phases: 0 = load, then (compute, store) per step, last = store to global.
+// `regs` is the thread's private NREG-element array (registers on the GPU).
 template <typename T, int M, int LOADK, int STOREK>
 struct FwdProgram {
     static constexpr int G = Geo<M>::G;
-    static constexpr int kPhases = 2 + num_steps(M);
+    static constexpr int kPhases = 2 + 2 * num_steps(M);
 
     // c.d0 must already be set.
     ADRT_HD static int classify(const TileCtx &c)
@@ -710,24 +824,25 @@ struct FwdProgram {
         return TILE_FULL;
     }
 
-    ADRT_HD static void phase(int ph, int mode, T *bufA, T *bufB, const T *src, T *dst, const TileCtx &c, int tid)
+    ADRT_HD static void phase(int ph, int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
     {
         if (mode == TILE_ZERO) {
             if (ph == 0) {
-                if (STOREK == STORE_QCOLS) store_qcols<T, M>(bufA, dst, c, 0, true, tid);
-                else fwd_store_wrows<T, M>(bufA, dst, c, true, tid);
+                if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, 0, true, tid);
+                else fwd_store_wrows<T, M>(buf, dst, c, true, tid);
             }
             return;
         }
         if (ph == 0) {
-            if (LOADK == LOAD_IMAGE) fwd_load_image<T, M>(bufA, src, c, tid);
-            else fwd_load_wrows<T, M>(bufA, src, c, tid);
-        } else if (ph <= num_steps(M)) {
-            fwd_step<T, M>(bufA, bufB, ph - 1, tid);
+            if (LOADK == LOAD_IMAGE) fwd_load_image<T, M>(buf, src, c, tid);
+            else fwd_load_wrows<T, M>(buf, src, c, tid);
+        } else if (ph <= 2 * num_steps(M)) {
+            const int step = (ph - 1) >> 1;
+            if ((ph - 1) & 1) fwd_step_store<T, M>(buf, step, tid, regs);
+            else fwd_step_compute<T, M>(buf, step, tid, regs);
         } else {
-            const T *res = (num_steps(M) & 1) ? bufB : bufA;
-            if (STOREK == STORE_QCOLS) store_qcols<T, M>(res, dst, c, Geo<M>::HALO, false, tid);
-            else fwd_store_wrows<T, M>(res, dst, c, false, tid);
+            if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, Geo<M>::HALO, false, tid);
+            else fwd_store_wrows<T, M>(buf, dst, c, false, tid);
         }
     }
 };
@@ -735,7 +850,7 @@ struct FwdProgram {
 template <typename T, int M, int LOADK, int STOREK>
 struct BwdProgram {
     static constexpr int G = Geo<M>::G;
-    static constexpr int kPhases = 2 + num_steps(M);
+    static constexpr int kPhases = 2 + 2 * num_steps(M);
 
     ADRT_HD static int classify(const TileCtx &c)
     {
@@ -745,22 +860,23 @@ struct BwdProgram {
         return TILE_FULL;
     }
 
-    ADRT_HD static void phase(int ph, int mode, T *bufA, T *bufB, const T *src, T *dst, const TileCtx &c, int tid)
+    ADRT_HD static void phase(int ph, int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
     {
         if (mode == TILE_ZERO) {
-            if (ph == 0) bwd_store_wrows<T, M>(bufA, dst, c, true, tid);
+            if (ph == 0) bwd_store_wrows<T, M>(buf, dst, c, true, tid);
             return;
         }
         if (ph == 0) {
-            if (LOADK == LOAD_QCOLS) bwd_load_qcols<T, M>(bufA, src, c, tid);
-            else bwd_load_wrows<T, M>(bufA, src, c, tid);
-        } else if (ph <= num_steps(M)) {
-            if (mode == TILE_FULL_MASKED) bwd_step<T, M, true>(bufA, bufB, ph - 1, c.D - c.d0, c.a_g, tid);
-            else bwd_step<T, M, false>(bufA, bufB, ph - 1, c.D - c.d0, c.a_g, tid);
+            if (LOADK == LOAD_QCOLS) bwd_load_qcols<T, M>(buf, src, c, tid);
+            else bwd_load_wrows<T, M>(buf, src, c, tid);
+        } else if (ph <= 2 * num_steps(M)) {
+            const int step = (ph - 1) >> 1;
+            if ((ph - 1) & 1) bwd_step_store<T, M>(buf, step, tid, regs);
+            else if (mode == TILE_FULL_MASKED) bwd_step_compute<T, M, true>(buf, step, c.D - c.d0, c.a_g, tid, regs);
+            else bwd_step_compute<T, M, false>(buf, step, c.D - c.d0, c.a_g, tid, regs);
         } else {
-            const T *res = (num_steps(M) & 1) ? bufB : bufA;
-            if (STOREK == STORE_QCOLS) store_qcols<T, M>(res, dst, c, 0, false, tid);
-            else bwd_store_wrows<T, M>(res, dst, c, false, tid);
+            if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, 0, false, tid);
+            else bwd_store_wrows<T, M>(buf, dst, c, false, tid);
         }
     }
 };

@@ -25,8 +25,10 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
                                            tile::BwdProgram<T, M, LOADK, STOREK>>::type;
     // Pack<T> accesses need 16-byte alignment: allocate as Pack vectors
     const size_t cells = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value;
-    std::vector<tile::Pack<T>> storeA(cells / tile::VecOf<T>::L + 1), storeB(cells / tile::VecOf<T>::L + 1);
-    T *bufA = reinterpret_cast<T *>(storeA.data()), *bufB = reinterpret_cast<T *>(storeB.data());
+    std::vector<tile::Pack<T>> storeA(cells / tile::VecOf<T>::L + 1);
+    T *buf = reinterpret_cast<T *>(storeA.data());
+    // per-thread "registers" that live across the barriers of a step
+    std::vector<T> regfile((size_t)tile::Geo<M>::NT * tile::NREG);
     const int e = 1 << p.s;
     for (int plane = 0; plane < planes; ++plane)
         for (int by = 0; by < p.grid_y; ++by)
@@ -43,11 +45,12 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
                 else sp = src + (long long)plane * sps;
                 T *dp = dst + (long long)plane * dps;
                 // poison shared memory so that reads of never-written cells are visible
-                for (size_t i = 0; i < cells; ++i) { bufA[i] = T(1e30); bufB[i] = T(-1e30); }
+                for (size_t i = 0; i < cells; ++i) buf[i] = T(1e30);
+                for (auto &v : regfile) v = T(-1e30);
                 const int nph = mode == tile::TILE_ZERO ? 1 : Prog::kPhases;
                 for (int ph = 0; ph < nph; ++ph)
                     for (int tid = 0; tid < tile::Geo<M>::NT; ++tid)
-                        Prog::phase(ph, mode, bufA, bufB, sp, dp, c, tid);
+                        Prog::phase(ph, mode, buf, *reinterpret_cast<T(*)[tile::NREG]>(&regfile[(size_t)tid * tile::NREG]), sp, dp, c, tid);
             }
 }
 

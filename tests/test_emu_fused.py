@@ -89,9 +89,10 @@ def test_forced_splits(emu, n, split):
     _check(emu, n, 1, np.float32, split)
 
 
-def test_f32_six_stage_pass(emu):
-    _check(emu, 128, 1, np.float32, "6,1")
-    _check(emu, 128, 1, np.float32, "1,6")
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_six_stage_pass(emu, dt):
+    _check(emu, 128, 1, dt, "6,1")
+    _check(emu, 128, 1, dt, "1,6")
 
 
 def test_medium_default(emu):
