@@ -20,6 +20,18 @@ struct PassArgs {
     int planes;
 };
 
+// The phases of a full tile, unrolled at compile time with a barrier after each.
+template <typename Prog, typename T, int PH>
+__device__ __forceinline__ void all_phases(int mode, T *buf, T (&regs)[tile::NREG], const T *sp, T *dp,
+                                           const tile::TileCtx &c, int tid)
+{
+    if constexpr (PH < Prog::kPhases) {
+        Prog::template phase_ct<PH>(mode, buf, regs, sp, dp, c, tid);
+        __syncthreads();
+        all_phases<Prog, T, PH + 1>(mode, buf, regs, sp, dp, c, tid);
+    }
+}
+
 template <typename T, int M, int LOADK, int STOREK, bool kForward>
 __global__ void __launch_bounds__(tile::Geo<M>::NT, sizeof(T) == 8 ? tile::Geo<M>::MIN_CTAS / 2 : tile::Geo<M>::MIN_CTAS)
 pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
@@ -53,10 +65,10 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
             sp = src + (long long)plane * a.src_plane_stride;
         }
         T *dp = dst + (long long)plane * a.dst_plane_stride;
-        const int nph = mode == tile::TILE_ZERO ? 1 : Prog::kPhases;
-        for (int ph = 0; ph < nph; ++ph) {
-            Prog::phase(ph, mode, buf, regs, sp, dp, c, threadIdx.x);
-            __syncthreads();
+        if (mode == tile::TILE_ZERO) {
+            Prog::zero_tile(buf, dp, c, threadIdx.x);
+        } else {
+            all_phases<Prog, T, 0>(mode, buf, regs, sp, dp, c, threadIdx.x);
         }
     }
 }

@@ -305,13 +305,14 @@ ADRT_HD void fwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int 
     }
 }
 
-template <typename T, int M>
-ADRT_HD void fwd_radix4_compute(const T *buf, int t, int tid, T (&o)[NREG])
+template <typename T, int M, int t>
+ADRT_HD void fwd_radix4_compute(const T *buf, int tid, T (&o)[NREG])
 {
     constexpr int G = Geo<M>::G;
-    const int e = 1 << t, gi = tid >> 5, lane = tid & 31;
+    constexpr int e = 1 << t, lo_out = 4 * e;
+    const int gi = tid >> 5, lane = tid & 31;
     if (gi >= G / 4) return;
-    const int k0 = gi >> t, a = gi & (e - 1), lo_out = 4 * e;
+    const int k0 = gi >> t, a = gi & (e - 1);
     switch (a & 3) {
     case 0: fwd_radix4_group<T, 0>(buf, e, k0, a, lane, lo_out, o); break;
     case 1: fwd_radix4_group<T, 1>(buf, e, k0, a, lane, lo_out, o); break;
@@ -320,13 +321,14 @@ ADRT_HD void fwd_radix4_compute(const T *buf, int t, int tid, T (&o)[NREG])
     }
 }
 
-template <typename T, int M>
-ADRT_HD void fwd_radix4_store(T *buf, int t, int tid, const T (&o)[NREG])
+template <typename T, int M, int t>
+ADRT_HD void fwd_radix4_store(T *buf, int tid, const T (&o)[NREG])
 {
     constexpr int G = Geo<M>::G, P = Pitch<T>::value;
-    const int e = 1 << t, gi = tid >> 5, lane = tid & 31;
+    constexpr int e = 1 << t, lo_out = 4 * e;
+    const int gi = tid >> 5, lane = tid & 31;
     if (gi >= G / 4) return;
-    const int k0 = gi >> t, a = gi & (e - 1), lo_out = 4 * e;
+    const int k0 = gi >> t, a = gi & (e - 1);
     T *orow = buf + (k0 * 4 * e + 4 * a) * P;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
@@ -361,11 +363,12 @@ ADRT_HD void fwd_radix2_group(const T *buf, int e, int k, int b, int lane, int l
     }
 }
 
-template <typename T, int M>
-ADRT_HD void fwd_radix2_compute(const T *buf, int t, int tid, T (&o)[NREG])
+template <typename T, int M, int t>
+ADRT_HD void fwd_radix2_compute(const T *buf, int tid, T (&o)[NREG])
 {
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP;
-    const int e = 1 << t, lane = tid & 31, lo_out = 2 * e < 4 ? 4 : 2 * e;
+    constexpr int e = 1 << t, lo_out = 2 * e < 4 ? 4 : 2 * e;
+    const int lane = tid & 31;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int gi = (tid >> 5) + u * NWARP;
@@ -381,11 +384,12 @@ ADRT_HD void fwd_radix2_compute(const T *buf, int t, int tid, T (&o)[NREG])
     }
 }
 
-template <typename T, int M>
-ADRT_HD void fwd_radix2_store(T *buf, int t, int tid, const T (&o)[NREG])
+template <typename T, int M, int t>
+ADRT_HD void fwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
 {
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
-    const int e = 1 << t, lane = tid & 31, lo_out = 2 * e < 4 ? 4 : 2 * e;
+    constexpr int e = 1 << t, lo_out = 2 * e < 4 ? 4 : 2 * e;
+    const int lane = tid & 31;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int gi = (tid >> 5) + u * NWARP;
@@ -407,20 +411,20 @@ ADRT_HD void fwd_radix2_store(T *buf, int t, int tid, const T (&o)[NREG])
 // when M is odd).  Each step is two barrier-separated phases (compute, store).
 ADRT_HD constexpr int num_steps(int M) { return (M + 1) / 2; }
 
-template <typename T, int M>
-ADRT_HD void fwd_step_compute(const T *buf, int step, int tid, T (&o)[NREG])
+template <typename T, int M, int STEP>
+ADRT_HD void fwd_step_compute(const T *buf, int tid, T (&o)[NREG])
 {
-    const int t = 2 * step;
-    if (t + 2 <= M) fwd_radix4_compute<T, M>(buf, t, tid, o);
-    else fwd_radix2_compute<T, M>(buf, t, tid, o);
+    constexpr int t = 2 * STEP;
+    if constexpr (t + 2 <= M) fwd_radix4_compute<T, M, t>(buf, tid, o);
+    else fwd_radix2_compute<T, M, t>(buf, tid, o);
 }
 
-template <typename T, int M>
-ADRT_HD void fwd_step_store(T *buf, int step, int tid, const T (&o)[NREG])
+template <typename T, int M, int STEP>
+ADRT_HD void fwd_step_store(T *buf, int tid, const T (&o)[NREG])
 {
-    const int t = 2 * step;
-    if (t + 2 <= M) fwd_radix4_store<T, M>(buf, t, tid, o);
-    else fwd_radix2_store<T, M>(buf, t, tid, o);
+    constexpr int t = 2 * STEP;
+    if constexpr (t + 2 <= M) fwd_radix4_store<T, M, t>(buf, tid, o);
+    else fwd_radix2_store<T, M, t>(buf, tid, o);
 }
 
 // ---- stores -----------------------------------------------------------------------
@@ -644,11 +648,12 @@ ADRT_HD void bwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int 
 }
 
 // rprev = radix of the step that produced the parent rows (0: they were loaded)
-template <typename T, int M, bool kMask>
-ADRT_HD void bwd_radix4_compute(const T *buf, int t, int rprev, int dt, int ag, int tid, T (&o)[NREG])
+template <typename T, int M, bool kMask, int t, int rprev>
+ADRT_HD void bwd_radix4_compute(const T *buf, int dt, int ag, int tid, T (&o)[NREG])
 {
     constexpr int G = Geo<M>::G;
-    const int e = 1 << t, gi = tid >> 5, lane = tid & 31;
+    constexpr int e = 1 << t;
+    const int gi = tid >> 5, lane = tid & 31;
     if (gi >= G / 4) return;
     const int k0 = gi >> t, a = gi & (e - 1);
     const int jp = rprev ? (k0 & (rprev - 1)) : 0;
@@ -660,11 +665,12 @@ ADRT_HD void bwd_radix4_compute(const T *buf, int t, int rprev, int dt, int ag, 
     }
 }
 
-template <typename T, int M>
-ADRT_HD void bwd_radix4_store(T *buf, int t, int rprev, int tid, const T (&o)[NREG])
+template <typename T, int M, int t, int rprev>
+ADRT_HD void bwd_radix4_store(T *buf, int tid, const T (&o)[NREG])
 {
     constexpr int G = Geo<M>::G, P = Pitch<T>::value;
-    const int e = 1 << t, gi = tid >> 5, lane = tid & 31;
+    constexpr int e = 1 << t;
+    const int gi = tid >> 5, lane = tid & 31;
     if (gi >= G / 4) return;
     const int k0 = gi >> t, a = gi & (e - 1);
     const int jp = rprev ? (k0 & (rprev - 1)) : 0;
@@ -680,11 +686,12 @@ ADRT_HD void bwd_radix4_store(T *buf, int t, int rprev, int tid, const T (&o)[NR
 }
 
 // ---- transposed radix-2 step (always the first transposed step: parents loaded) --
-template <typename T, int M, bool kMask>
-ADRT_HD void bwd_radix2_compute(const T *buf, int t, int dt, int ag, int tid, T (&o)[NREG])
+template <typename T, int M, bool kMask, int t>
+ADRT_HD void bwd_radix2_compute(const T *buf, int dt, int ag, int tid, T (&o)[NREG])
 {
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
-    const int e = 1 << t, lane = tid & 31;
+    constexpr int e = 1 << t;
+    const int lane = tid & 31;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int gi = (tid >> 5) + u * NWARP;
@@ -713,11 +720,12 @@ ADRT_HD void bwd_radix2_compute(const T *buf, int t, int dt, int ag, int tid, T 
     }
 }
 
-template <typename T, int M>
-ADRT_HD void bwd_radix2_store(T *buf, int t, int tid, const T (&o)[NREG])
+template <typename T, int M, int t>
+ADRT_HD void bwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
 {
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
-    const int e = 1 << t, lane = tid & 31;
+    constexpr int e = 1 << t;
+    const int lane = tid & 31;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int gi = (tid >> 5) + u * NWARP;
@@ -739,20 +747,20 @@ ADRT_HD constexpr int bwd_step_t(int M, int step) { return 2 * (num_steps(M) - 1
 // radix of the previous transposed step: 2 if that was the odd last stage
 ADRT_HD constexpr int bwd_step_rprev(int M, int step) { return step == 0 ? 0 : ((bwd_step_t(M, step) + 4 <= M) ? 4 : 2); }
 
-template <typename T, int M, bool kMask>
-ADRT_HD void bwd_step_compute(const T *buf, int step, int dt, int ag, int tid, T (&o)[NREG])
+template <typename T, int M, bool kMask, int STEP>
+ADRT_HD void bwd_step_compute(const T *buf, int dt, int ag, int tid, T (&o)[NREG])
 {
-    const int t = bwd_step_t(M, step);
-    if (t + 2 <= M) bwd_radix4_compute<T, M, kMask>(buf, t, bwd_step_rprev(M, step), dt, ag, tid, o);
-    else bwd_radix2_compute<T, M, kMask>(buf, t, dt, ag, tid, o);
+    constexpr int t = bwd_step_t(M, STEP);
+    if constexpr (t + 2 <= M) bwd_radix4_compute<T, M, kMask, t, bwd_step_rprev(M, STEP)>(buf, dt, ag, tid, o);
+    else bwd_radix2_compute<T, M, kMask, t>(buf, dt, ag, tid, o);
 }
 
-template <typename T, int M>
-ADRT_HD void bwd_step_store(T *buf, int step, int tid, const T (&o)[NREG])
+template <typename T, int M, int STEP>
+ADRT_HD void bwd_step_store(T *buf, int tid, const T (&o)[NREG])
 {
-    const int t = bwd_step_t(M, step);
-    if (t + 2 <= M) bwd_radix4_store<T, M>(buf, t, bwd_step_rprev(M, step), tid, o);
-    else bwd_radix2_store<T, M>(buf, t, tid, o);
+    constexpr int t = bwd_step_t(M, STEP);
+    if constexpr (t + 2 <= M) bwd_radix4_store<T, M, t, bwd_step_rprev(M, STEP)>(buf, tid, o);
+    else bwd_radix2_store<T, M, t>(buf, tid, o);
 }
 
 // Output row j -> workspace row (k0*G + j)*e + a_g at offset d0 + xc - a_g*j.
@@ -824,22 +832,25 @@ struct FwdProgram {
         return TILE_FULL;
     }
 
-    ADRT_HD static void phase(int ph, int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
+    // whole tile is zeros: just write them
+    ADRT_HD static void zero_tile(T *buf, T *dst, const TileCtx &c, int tid)
     {
-        if (mode == TILE_ZERO) {
-            if (ph == 0) {
-                if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, 0, true, tid);
-                else fwd_store_wrows<T, M>(buf, dst, c, true, tid);
-            }
-            return;
-        }
-        if (ph == 0) {
+        if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, 0, true, tid);
+        else fwd_store_wrows<T, M>(buf, dst, c, true, tid);
+    }
+
+    // phase PH of a full tile; every per-step quantity is a compile-time constant
+    template <int PH>
+    ADRT_HD static void phase_ct(int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
+    {
+        (void)mode;
+        if constexpr (PH == 0) {
             if (LOADK == LOAD_IMAGE) fwd_load_image<T, M>(buf, src, c, tid);
             else fwd_load_wrows<T, M>(buf, src, c, tid);
-        } else if (ph <= 2 * num_steps(M)) {
-            const int step = (ph - 1) >> 1;
-            if ((ph - 1) & 1) fwd_step_store<T, M>(buf, step, tid, regs);
-            else fwd_step_compute<T, M>(buf, step, tid, regs);
+        } else if constexpr (PH <= 2 * num_steps(M)) {
+            constexpr int step = (PH - 1) >> 1;
+            if constexpr ((PH - 1) & 1) fwd_step_store<T, M, step>(buf, tid, regs);
+            else fwd_step_compute<T, M, step>(buf, tid, regs);
         } else {
             if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, Geo<M>::HALO, false, tid);
             else fwd_store_wrows<T, M>(buf, dst, c, false, tid);
@@ -860,26 +871,39 @@ struct BwdProgram {
         return TILE_FULL;
     }
 
-    ADRT_HD static void phase(int ph, int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
+    ADRT_HD static void zero_tile(T *buf, T *dst, const TileCtx &c, int tid)
     {
-        if (mode == TILE_ZERO) {
-            if (ph == 0) bwd_store_wrows<T, M>(buf, dst, c, true, tid);
-            return;
-        }
-        if (ph == 0) {
+        bwd_store_wrows<T, M>(buf, dst, c, true, tid);
+    }
+
+    template <int PH>
+    ADRT_HD static void phase_ct(int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
+    {
+        if constexpr (PH == 0) {
             if (LOADK == LOAD_QCOLS) bwd_load_qcols<T, M>(buf, src, c, tid);
             else bwd_load_wrows<T, M>(buf, src, c, tid);
-        } else if (ph <= 2 * num_steps(M)) {
-            const int step = (ph - 1) >> 1;
-            if ((ph - 1) & 1) bwd_step_store<T, M>(buf, step, tid, regs);
-            else if (mode == TILE_FULL_MASKED) bwd_step_compute<T, M, true>(buf, step, c.D - c.d0, c.a_g, tid, regs);
-            else bwd_step_compute<T, M, false>(buf, step, c.D - c.d0, c.a_g, tid, regs);
+        } else if constexpr (PH <= 2 * num_steps(M)) {
+            constexpr int step = (PH - 1) >> 1;
+            if constexpr ((PH - 1) & 1) bwd_step_store<T, M, step>(buf, tid, regs);
+            else if (mode == TILE_FULL_MASKED) bwd_step_compute<T, M, true, step>(buf, c.D - c.d0, c.a_g, tid, regs);
+            else bwd_step_compute<T, M, false, step>(buf, c.D - c.d0, c.a_g, tid, regs);
         } else {
             if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, 0, false, tid);
             else bwd_store_wrows<T, M>(buf, dst, c, false, tid);
         }
     }
 };
+
+// Run-time phase index -> compile-time phase (host emulator; the CUDA kernel
+// unrolls the sequence instead).
+template <typename Prog, typename T, int PH = 0>
+ADRT_HD void run_phase(int ph, int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
+{
+    if constexpr (PH < Prog::kPhases) {
+        if (ph == PH) Prog::template phase_ct<PH>(mode, buf, regs, src, dst, c, tid);
+        else run_phase<Prog, T, PH + 1>(ph, mode, buf, regs, src, dst, c, tid);
+    }
+}
 
 }  // namespace tile
 }  // namespace adrt_b200

@@ -47,10 +47,13 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
                 // poison shared memory so that reads of never-written cells are visible
                 for (size_t i = 0; i < cells; ++i) buf[i] = T(1e30);
                 for (auto &v : regfile) v = T(-1e30);
-                const int nph = mode == tile::TILE_ZERO ? 1 : Prog::kPhases;
-                for (int ph = 0; ph < nph; ++ph)
+                if (mode == tile::TILE_ZERO) {
+                    for (int tid = 0; tid < tile::Geo<M>::NT; ++tid) Prog::zero_tile(buf, dp, c, tid);
+                    continue;
+                }
+                for (int ph = 0; ph < Prog::kPhases; ++ph)
                     for (int tid = 0; tid < tile::Geo<M>::NT; ++tid)
-                        Prog::phase(ph, mode, buf, *reinterpret_cast<T(*)[tile::NREG]>(&regfile[(size_t)tid * tile::NREG]), sp, dp, c, tid);
+                        tile::run_phase<Prog, T>(ph, mode, buf, *reinterpret_cast<T(*)[tile::NREG]>(&regfile[(size_t)tid * tile::NREG]), sp, dp, c, tid);
             }
 }
 
