@@ -1,0 +1,74 @@
+"""CPU, world_size 2 over gloo: the batch-sharding host logic used for multi-GPU
+runs (shard bounds, max-over-ranks timing, result gathering).  The per-rank
+transform is the CPU oracle here -- the test is about the sharding, which is
+the same code path bench.py drives with NCCL on GPUs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from adrt_b200._shard import gather_batch, max_over_ranks, shard_bounds
+    from oracle import oracle as O
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, n = 5, 16  # uneven split on purpose
+        x = np.random.default_rng(0).standard_normal((B, n, n)).astype(np.float32)
+        lo, hi = shard_bounds(B, world, rank)
+        local = torch.from_numpy(O.adrt(x[lo:hi]))
+        full = gather_batch(local, dist)
+        ok = full.numpy().tobytes() == O.adrt(x).tobytes()
+        t = max_over_ranks(10.0 + rank, dist)
+        q.put((rank, lo, hi, ok, t))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds():
+    from adrt_b200._shard import shard_bounds
+
+    for B in (1, 5, 64, 67):
+        for world in (1, 2, 4, 8):
+            cuts = [shard_bounds(B, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == B
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def test_two_rank_gloo_sharded_transform():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [(r[1], r[2]) for r in res] == [(0, 3), (3, 5)]
+    assert all(r[3] for r in res), "gathered sharded result differs from the unsharded one"
+    assert all(r[4] == 11.0 for r in res), "max over ranks"
