@@ -464,11 +464,13 @@ ADRT_HD void store_qcols(const T *buf, T *dst_plane, const TileCtx &c, int xoff,
     const int warp = tid >> 5, lane = tid & 31;
     const int cols = G < c.n ? G : c.n;
     const bool fast = c.d0 + TD <= c.D;
+    const long long n1 = c.n;
     for (int p = lane; p < cols; p += 32) {
-        T *o = dst_plane + (long long)c.d0 * c.n + c.g * G + p;
-        const T *b = buf + p * P + xoff;
-#pragma unroll 2
-        for (int it = 0; it < NIT; ++it) {
+        T *o = dst_plane + (long long)(c.d0 + warp * V) * n1 + c.g * G + p;   // row d0 + warp*V, column p
+        const T *b = buf + p * P + xoff + warp * V;
+        const long long ostep = (long long)NWARP * V * n1;
+#pragma unroll 3
+        for (int it = 0; it < NIT; ++it, o += ostep, b += NWARP * V) {
             const int xc = (it * NWARP + warp) * V;
             if (xc >= TD) break;
             T v[V];
@@ -476,16 +478,17 @@ ADRT_HD void store_qcols(const T *buf, T *dst_plane, const TileCtx &c, int xoff,
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = T(0.0);
             } else {
-                load_window<T, V, 0>(b + xc, v);
+                load_window<T, V, 0>(b, v);
             }
-            T *oo = o + (long long)xc * c.n;
             if (fast) {
-#pragma unroll
-                for (int i = 0; i < V; ++i) oo[(long long)i * c.n] = v[i];
+                o[0] = v[0];
+                o[n1] = v[1];
+                o[2 * n1] = v[2];
+                o[3 * n1] = v[3];
             } else {
 #pragma unroll
                 for (int i = 0; i < V; ++i)
-                    if (c.d0 + xc + i < c.D) oo[(long long)i * c.n] = v[i];
+                    if (c.d0 + xc + i < c.D) o[i * n1] = v[i];
             }
         }
     }
@@ -502,18 +505,34 @@ template <typename T, int M>
 ADRT_HD void bwd_load_wrows(T *buf, const T *src_plane, const TileCtx &c, int tid)
 {
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value, L = VecOf<T>::L;
+    constexpr int RPW = (G + NWARP - 1) / NWARP;       // rows per warp
+    constexpr int NV = XW / (32 * L);                  // vectors per lane and row
     const int warp = tid >> 5, lane = tid & 31;
-    for (int p = warp; p < G; p += NWARP) {
-        const T *row = src_plane + ((long long)c.g * G + p) * c.in_pitch;
-        T *dst = buf + p * P;
-        if (c.d0 + XW <= c.D) {
-            // d0 and the pitch are multiples of 4: aligned vector copy
+    if (c.d0 + XW <= c.D) {
+        // d0 and the pitch are multiples of 4: aligned vector copy, pointers advanced by constants
+        const T *rp = src_plane + ((long long)c.g * G + warp) * c.in_pitch + c.d0 + lane * L;
+        T *dp = buf + warp * P + lane * L;
+        const long long rstep = (long long)NWARP * c.in_pitch;
 #pragma unroll
-            for (int k = 0; k < XW / (32 * L); ++k) {
-                const int x = (k * 32 + lane) * L;
-                *reinterpret_cast<Pack<T> *>(dst + x) = *reinterpret_cast<const Pack<T> *>(row + c.d0 + x);
-            }
-        } else {
+        for (int r0 = 0; r0 < RPW; r0 += 2) {
+            Pack<T> v[2][NV];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (r0 + u < RPW && warp + (r0 + u) * NWARP < G) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) v[u][k] = *reinterpret_cast<const Pack<T> *>(rp + (r0 + u) * rstep + k * 32 * L);
+                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (r0 + u < RPW && warp + (r0 + u) * NWARP < G) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) *reinterpret_cast<Pack<T> *>(dp + (r0 + u) * NWARP * P + k * 32 * L) = v[u][k];
+                }
+        }
+    } else {
+        for (int p = warp; p < G; p += NWARP) {
+            const T *row = src_plane + ((long long)c.g * G + p) * c.in_pitch;
+            T *dst = buf + p * P;
 #pragma unroll 4
             for (int k = 0; k < XW / 32; ++k) {
                 const int x = k * 32 + lane, d = c.d0 + x;
@@ -531,33 +550,30 @@ ADRT_HD void bwd_load_qcols(T *buf, const T *src_plane, const TileCtx &c, int ti
     const int warp = tid >> 5, lane = tid & 31;
     const int cols = G < c.n ? G : c.n;
     const bool fast = c.d0 + XW <= c.D;
+    const long long n1 = c.n;
     for (int p = lane; p < cols; p += 32) {
-        const T *ib = src_plane + (long long)c.d0 * c.n + c.g * G + p;
-        T *b = buf + p * P;
+        const T *ir = src_plane + (long long)(c.d0 + warp * V) * n1 + c.g * G + p;
+        T *b = buf + p * P + warp * V;
+        const long long istep = (long long)NWARP * V * n1;
         if (fast) {
 #pragma unroll 1
-            for (int it0 = 0; it0 < NIT; it0 += 2) {
+            for (int it0 = 0; it0 < NIT; it0 += 2, ir += 2 * istep, b += 2 * NWARP * V) {
                 // two chunks (8 independent loads) in flight per thread
-                T v[2][V];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int x = ((it0 + u) * NWARP + warp) * V;
-                    const T *ir = ib + (long long)x * c.n;
-#pragma unroll
-                    for (int i = 0; i < V; ++i) v[u][i] = ir[(long long)i * c.n];
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) store_chunk<T>(b + ((it0 + u) * NWARP + warp) * V, v[u]);
+                T v0[V], v1[V];
+                v0[0] = ir[0]; v0[1] = ir[n1]; v0[2] = ir[2 * n1]; v0[3] = ir[3 * n1];
+                const T *ir1 = ir + istep;
+                v1[0] = ir1[0]; v1[1] = ir1[n1]; v1[2] = ir1[2 * n1]; v1[3] = ir1[3 * n1];
+                store_chunk<T>(b, v0);
+                store_chunk<T>(b + NWARP * V, v1);
             }
         } else {
 #pragma unroll 2
             for (int it = 0; it < NIT; ++it) {
                 const int x = (it * NWARP + warp) * V;
-                const T *ir = ib + (long long)x * c.n;
                 T v[V];
 #pragma unroll
-                for (int i = 0; i < V; ++i) v[i] = (c.d0 + x + i < c.D) ? ir[(long long)i * c.n] : T(0.0);
-                store_chunk<T>(b + x, v);
+                for (int i = 0; i < V; ++i) v[i] = (c.d0 + x + i < c.D) ? ir[it * istep + i * n1] : T(0.0);
+                store_chunk<T>(b + it * NWARP * V, v);
             }
         }
     }
