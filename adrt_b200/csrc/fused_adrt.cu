@@ -14,7 +14,7 @@ namespace adrt_b200 {
 namespace {
 
 struct PassArgs {
-    int n, D, e, loge;
+    int n, D, e, loge, next_g;
     long long in_pitch, out_pitch;
     long long src_plane_stride, dst_plane_stride;  // elements between consecutive planes
     int planes;
@@ -49,7 +49,8 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
     c.g = blockIdx.y;
     c.k0 = c.g >> a.loge;
     c.a_g = c.g & (a.e - 1);
-    c.d0 = blockIdx.x * tile::Geo<M>::TD;
+    c.d0 = blockIdx.x * Prog::TD;
+    c.next_g = a.next_g;
     c.in_pitch = a.in_pitch;
     c.out_pitch = a.out_pitch;
     c.q = 0;
@@ -149,7 +150,7 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, T *ws, size_t
         for (int i = 0; i < pl.npass; ++i) {
             const plan::Pass &p = pl.pass[i];
             PassArgs a;
-            a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s;
+            a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g;
             a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
             a.planes = nb * 4;
             const T *src;

@@ -25,6 +25,7 @@ struct Pass {
     long long in_pitch, out_pitch;  // row length (elements) of the R-layout workspaces
     int src_buf, dst_buf;           // -1 = caller's input / output, else workspace slot 0/1
     int grid_x, grid_y;             // d-tiles, groups
+    int next_g;                     // forward: group size of the pass reading this pass's workspace (0: none)
 };
 
 struct Plan {
@@ -83,16 +84,17 @@ inline long long round4(long long v) { return (v + 3) & ~3LL; }
 
 // Row length of the forward workspace after s stages: the support n + 2^s
 // (capped at D), rounded up so that rows stay 16-byte aligned.
+// (+3: rows are stored with a skew of up to 3 elements, see tile::fwd_row_skew)
 inline long long fwd_pitch(int n, int s)
 {
     const long long D = 2LL * n - 1, p = (long long)n + (1LL << s);
-    return round4(p < D ? p : D);
+    return round4((p < D ? p : D) + 3);
 }
 
-inline int tile_td(int M)
+inline int tile_td(int M, int store)
 {
     const int G = 1 << M;
-    return tile::XW - (G < 4 ? 4 : G);
+    return tile::XW - (G < 4 ? 4 : G) - (store == tile::STORE_WROWS ? 4 : 0);
 }
 
 inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
@@ -117,7 +119,8 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        const int TD = tile_td(p.M);
+        const int TD = tile_td(p.M, p.store);
+        p.next_g = last ? 0 : (1 << ms[i + 1]);
         const long long extent = last ? pl->D : p.out_pitch;  // offsets that must be written
         p.grid_x = (int)((extent + TD - 1) / TD);
         p.grid_y = n / G;
@@ -154,7 +157,8 @@ inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl)
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        const int TD = tile_td(p.M);
+        const int TD = tile_td(p.M, p.store);
+        p.next_g = 0;
         const long long e = 1LL << s;
         const long long extent = pl->D + (e - 1) * (G - 1);  // tile coordinates that hold outputs
         p.grid_x = (int)((extent + TD - 1) / TD);

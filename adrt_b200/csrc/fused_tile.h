@@ -79,7 +79,6 @@ template <int M> struct Geo {
     static constexpr int G = 1 << M;
     // offsets consumed by M stages, rounded so that chunk boundaries stay aligned
     static constexpr int HALO = G < 4 ? 4 : G;
-    static constexpr int TD = XW - HALO;      // valid output offsets per tile
     static constexpr int NT = G >= 64 ? 512 : 256;   // threads per CTA: one warp per radix-4 group
     static constexpr int MIN_CTAS = G >= 64 ? 2 : 4; // launch-bounds target (caps registers at 64)
     static constexpr int NWARP = NT / 32;
@@ -94,7 +93,21 @@ struct TileCtx {
     int g;             // group index
     int d0;            // forward: first valid output offset; transposed: first input offset
     long long in_pitch, out_pitch;   // elements per row of the R-layout workspaces (multiples of 4)
+    int next_g;        // forward: group size (rows) of the pass that will read the workspace, 0 if none
 };
+
+// Valid offsets a tile produces.  Passes that store workspace rows give up 4
+// more offsets: a row may be shifted by up to 3 elements against the 16-byte
+// grid of global memory (forward: storage skew, transposed: a_g*j), and each
+// tile then owns whole aligned 16-byte chunks of every row.
+template <int M, int STOREK> struct TileTD {
+    static constexpr int value = XW - Geo<M>::HALO - (STOREK == STORE_WROWS ? 4 : 0);
+};
+
+// Forward workspace rows are stored with a skew of s = (a * j) & 3 elements,
+// (a = angle of the row, j = its index inside the group of the pass that reads
+// it) so that the reader's shifted row start d - a*j lands on a 16-byte boundary.
+ADRT_HD int fwd_row_skew(int angle, int j) { return (angle * j) & 3; }
 
 // Load N consecutive elements that start Q elements after the 16-byte aligned
 // position `p` (Q compile time): ceil((Q+N)/L) vector loads + static selection.
@@ -130,38 +143,34 @@ ADRT_HD constexpr int neg_mod(int shift, int L) { return ((-shift) % L + L) % L;
 // forward
 // ===========================================================================
 
-// ---- loaders: row j of buf <- in_j[d0 - HALO - a_g*j + x], x in [0, XW) --------
-template <typename T, int M>
+// ---- loaders: row j of buf <- in_j[d0 - LH - a_g*j + x], x in [0, XW) ----------
+// (LH = tile position of offset d0).  The stored row is skewed by (a_g*j)&3, which
+// makes the global start 16-byte aligned.
+template <typename T, int M, int LH>
 ADRT_HD void fwd_load_wrows(T *buf, const T *src_plane, const TileCtx &c, int tid)
 {
-    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     constexpr int L = VecOf<T>::L;
     const int warp = tid >> 5, lane = tid & 31;
     const int sup = c.n + c.a_g;  // support of every input row of this group
     for (int j = warp; j < G; j += NWARP) {
         const T *row = src_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.in_pitch;
-        const int dbase = c.d0 - HALO - c.a_g * j;
+        const int dbase = c.d0 - LH - c.a_g * j;          // logical offset of x = 0
+        const int gbase = dbase + fwd_row_skew(c.a_g, j);  // its position in the stored row (multiple of 4)
         T *dst = buf + j * P;
-        if (dbase >= 0 && dbase + XW <= sup && (dbase % L) == 0) {
-            // fully inside the support and 16-byte aligned: vector copy
+        if (dbase >= 0 && dbase + XW <= sup) {
+            Pack<T> v[XW / (32 * L)];
 #pragma unroll
-            for (int k = 0; k < XW / (32 * L); ++k) {
-                const int x = (k * 32 + lane) * L;
-                *reinterpret_cast<Pack<T> *>(dst + x) = *reinterpret_cast<const Pack<T> *>(row + dbase + x);
-            }
-        } else if (dbase >= 0 && dbase + XW <= sup) {
-            T v[XW / 32];
+            for (int k = 0; k < XW / (32 * L); ++k) v[k] = *reinterpret_cast<const Pack<T> *>(row + gbase + (k * 32 + lane) * L);
 #pragma unroll
-            for (int k = 0; k < XW / 32; ++k) v[k] = row[dbase + k * 32 + lane];
-#pragma unroll
-            for (int k = 0; k < XW / 32; ++k) dst[k * 32 + lane] = v[k];
+            for (int k = 0; k < XW / (32 * L); ++k) *reinterpret_cast<Pack<T> *>(dst + (k * 32 + lane) * L) = v[k];
         } else {
 #pragma unroll 4
             for (int k = 0; k < XW / 32; ++k) {
                 const int x = k * 32 + lane, d = dbase + x;
                 T v;
                 if (d < 0) v = T(-0.0);
-                else if (d < sup) v = row[d];
+                else if (d < sup) v = row[gbase + x];
                 else v = T(0.0);
                 dst[x] = v;
             }
@@ -173,13 +182,13 @@ ADRT_HD void fwd_load_wrows(T *buf, const T *src_plane, const TileCtx &c, int ti
 // r = g*G + j of quadrant q (core.py:169-176):
 //   q0: I[r][d] = x[r, n-1-d]      q1: I[r][d] = x[n-1-d, r]
 //   q2: I[r][d] = x[d, r]          q3: I[r][d] = x[n-1-r, n-1-d]
-template <typename T, int M>
+template <typename T, int M, int LH>
 ADRT_HD void fwd_load_image(T *buf, const T *img, const TileCtx &c, int tid)
 {
-    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     const int warp = tid >> 5, lane = tid & 31;
     const int n = c.n;
-    const int dbase = c.d0 - HALO;
+    const int dbase = c.d0 - LH;
     const int rows = G < n ? G : n;
     if (c.q == 0 || c.q == 3) {
         // image rows are contiguous along d (reversed): lanes walk d
@@ -188,11 +197,19 @@ ADRT_HD void fwd_load_image(T *buf, const T *img, const TileCtx &c, int tid)
             const T *row = img + (long long)(c.q == 0 ? r : n - 1 - r) * n;
             T *dst = buf + j * P;
             if (dbase >= 0 && dbase + XW <= n) {
-                T v[XW / 32];
+                // offsets x..x+3 are image columns n-1-d-3 .. n-1-d: one aligned vector, reversed
+                // (n and d are multiples of 4 here)
+                constexpr int NV = XW / (32 * V);
+                T v[NV][V];
 #pragma unroll
-                for (int k = 0; k < XW / 32; ++k) v[k] = row[n - 1 - (dbase + k * 32 + lane)];
+                for (int k = 0; k < NV; ++k) load_window<T, V, 0>(row + (n - V - (dbase + (k * 32 + lane) * V)), v[k]);
 #pragma unroll
-                for (int k = 0; k < XW / 32; ++k) dst[k * 32 + lane] = v[k];
+                for (int k = 0; k < NV; ++k) {
+                    T r[V];
+#pragma unroll
+                    for (int i = 0; i < V; ++i) r[i] = v[k][V - 1 - i];
+                    store_chunk<T>(dst + (k * 32 + lane) * V, r);
+                }
             } else {
 #pragma unroll 4
                 for (int k = 0; k < XW / 32; ++k) {
@@ -428,38 +445,61 @@ ADRT_HD void fwd_step_store(T *buf, int tid, const T (&o)[NREG])
 }
 
 // ---- stores -----------------------------------------------------------------------
-// R-layout workspace: output row p -> row (g*G + p), offsets [d0, d0+TD); the
-// row is zero above its support bound n + a' (a' = a_g*G + p) and is written
-// all the way to the pitch so that the next pass may read it blindly.
-template <typename T, int M>
+// R-layout workspace: output row p -> row (g*G + p), stored with the skew the next
+// pass wants.  The tile owns the aligned global chunks [d0, d0 + TD) of every row;
+// chunk position gp holds offsets gp - s .., read from the tile at LH + (gp - d0) - s.
+// Rows are zero above their support bound n + a' and are written up to the pitch.
+template <typename T, int M, int LH, int TD, int S>
+ADRT_HD void fwd_store_row(const T *b, T *row, const TileCtx &c, int lim, bool zero, int lane)
+{
+    constexpr int Q = (4 - S) & 3;
+#pragma unroll
+    for (int k = 0; k < (TD / V + 31) / 32; ++k) {
+        const int xc = (k * 32 + lane) * V;      // gp - d0
+        const int gp = c.d0 + xc;
+        if (xc < TD && gp < c.out_pitch) {
+            T v[V];
+            if (zero) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = T(0.0);
+            } else {
+                load_window<T, V, Q>(b + (LH + xc - S - Q), v);
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    if (gp - S + i >= lim) v[i] = T(0.0);
+            }
+            store_chunk<T>(row + gp, v);
+        }
+    }
+}
+
+template <typename T, int M, int LH, int TD>
 ADRT_HD void fwd_store_wrows(const T *buf, T *dst_plane, const TileCtx &c, bool zero, int tid)
 {
-    constexpr int G = Geo<M>::G, HALO = Geo<M>::HALO, TD = Geo<M>::TD, NWARP = Geo<M>::NWARP;
-    constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     const int warp = tid >> 5, lane = tid & 31;
     for (int p = warp; p < G; p += NWARP) {
         T *row = dst_plane + ((long long)c.g * G + p) * c.out_pitch;
-        int lim = c.n + c.a_g * G + p;
+        const int ang = c.a_g * G + p;
+        int lim = c.n + ang;
         if (lim > c.D) lim = c.D;
-        for (int xc = lane * L; xc < TD; xc += 32 * L) {
-            const int d = c.d0 + xc;
-            if (d >= c.out_pitch) break;
-            Pack<T> v;
-            if (!zero) v = *reinterpret_cast<const Pack<T> *>(buf + p * P + HALO + xc);
-#pragma unroll
-            for (int i = 0; i < L; ++i)
-                if (zero || d + i >= lim) v.v[i] = T(0.0);
-            *reinterpret_cast<Pack<T> *>(row + d) = v;   // pitch is a multiple of 4: never crosses the row end
+        const int s = c.next_g ? fwd_row_skew(ang, c.k0 & (c.next_g - 1)) : 0;
+        const T *b = buf + p * P;
+        switch (s) {
+        case 0: fwd_store_row<T, M, LH, TD, 0>(b, row, c, lim, zero, lane); break;
+        case 1: fwd_store_row<T, M, LH, TD, 1>(b, row, c, lim, zero, lane); break;
+        case 2: fwd_store_row<T, M, LH, TD, 2>(b, row, c, lim, zero, lane); break;
+        default: fwd_store_row<T, M, LH, TD, 3>(b, row, c, lim, zero, lane); break;
         }
     }
 }
 
 // Public layout (D, n) of the plane: column g*G + p, all offsets < D.  Lanes walk
 // the rows p (consecutive columns), each thread moves V consecutive offsets.
-template <typename T, int M>
+template <typename T, int M, int TD>
 ADRT_HD void store_qcols(const T *buf, T *dst_plane, const TileCtx &c, int xoff, bool zero, int tid)
 {
-    constexpr int G = Geo<M>::G, TD = Geo<M>::TD, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     constexpr int NIT = (TD + NWARP * V - 1) / (NWARP * V);
     const int warp = tid >> 5, lane = tid & 31;
     const int cols = G < c.n ? G : c.n;
@@ -779,37 +819,50 @@ ADRT_HD void bwd_step_store(T *buf, int tid, const T (&o)[NREG])
     else bwd_radix2_store<T, M, t>(buf, tid, o);
 }
 
-// Output row j -> workspace row (k0*G + j)*e + a_g at offset d0 + xc - a_g*j.
-template <typename T, int M>
+// Output row j -> workspace row (k0*G + j)*e + a_g; tile position xc is offset
+// d0 - a_g*j + xc.  The tile owns the aligned chunks [ceil4(dbase), ceil4(dbase) + TD)
+// of the row (valid tile positions reach TD + 3); Q = (a_g*j) & 3 is the residue of
+// the tile-side window.
+template <typename T, int M, int TD, int Q>
+ADRT_HD void bwd_store_row(const T *b, T *row, const TileCtx &c, int dbase, bool zero, int lane)
+{
+#pragma unroll
+    for (int k = 0; k < (TD / V + 31) / 32; ++k) {
+        const int xa = (k * 32 + lane) * V;       // aligned tile position below the window
+        const int gp = dbase + Q + xa;            // aligned global offset of the chunk
+        if (xa < TD && gp + V > 0 && gp < c.D) {
+            T v[V];
+            if (zero) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = T(0.0);
+            } else {
+                load_window<T, V, Q>(b + xa, v);
+            }
+            if (gp >= 0 && gp + V <= c.D) {
+                store_chunk<T>(row + gp, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    if (gp + i >= 0 && gp + i < c.D) row[gp + i] = v[i];
+            }
+        }
+    }
+}
+
+template <typename T, int M, int TD>
 ADRT_HD void bwd_store_wrows(const T *buf, T *dst_plane, const TileCtx &c, bool zero, int tid)
 {
-    constexpr int G = Geo<M>::G, TD = Geo<M>::TD, NWARP = Geo<M>::NWARP, P = Pitch<T>::value, L = VecOf<T>::L;
-    constexpr int NS = (TD + 31) / 32;
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     const int warp = tid >> 5, lane = tid & 31;
     for (int j = warp; j < G; j += NWARP) {
         T *row = dst_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.out_pitch;
         const int dbase = c.d0 - c.a_g * j;
         const T *b = buf + j * P;
-        const bool inside = dbase >= 0 && dbase + TD <= c.D;
-        if (!zero && inside && (dbase % L) == 0) {
-#pragma unroll
-            for (int k = 0; k < TD / (32 * L) + 1; ++k) {
-                const int xc = (k * 32 + lane) * L;
-                if (xc < TD) *reinterpret_cast<Pack<T> *>(row + dbase + xc) = *reinterpret_cast<const Pack<T> *>(b + xc);
-            }
-        } else if (!zero && inside) {
-            T v[NS];
-#pragma unroll
-            for (int k = 0; k < NS; ++k) v[k] = b[k * 32 + lane];   // reads past TD stay inside the tile row
-#pragma unroll
-            for (int k = 0; k < NS; ++k)
-                if (k * 32 + lane < TD) row[dbase + k * 32 + lane] = v[k];
-        } else {
-#pragma unroll 2
-            for (int k = 0; k < NS; ++k) {
-                const int xc = k * 32 + lane, d = dbase + xc;
-                if (xc < TD && d >= 0 && d < c.D) row[d] = zero ? T(0.0) : b[xc];
-            }
+        switch ((c.a_g * j) & 3) {
+        case 0: bwd_store_row<T, M, TD, 0>(b, row, c, dbase, zero, lane); break;
+        case 1: bwd_store_row<T, M, TD, 1>(b, row, c, dbase, zero, lane); break;
+        case 2: bwd_store_row<T, M, TD, 2>(b, row, c, dbase, zero, lane); break;
+        default: bwd_store_row<T, M, TD, 3>(b, row, c, dbase, zero, lane); break;
         }
     }
 }
@@ -833,6 +886,8 @@ template <typename T, int M, int LOADK, int STOREK>
 struct FwdProgram {
     static constexpr int G = Geo<M>::G;
     static constexpr int kPhases = 2 + 2 * num_steps(M);
+    static constexpr int TD = TileTD<M, STOREK>::value;   // offsets produced per tile
+    static constexpr int LH = XW - TD;                    // tile position of offset d0
 
     // c.d0 must already be set.
     ADRT_HD static int classify(const TileCtx &c)
@@ -851,8 +906,8 @@ struct FwdProgram {
     // whole tile is zeros: just write them
     ADRT_HD static void zero_tile(T *buf, T *dst, const TileCtx &c, int tid)
     {
-        if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, 0, true, tid);
-        else fwd_store_wrows<T, M>(buf, dst, c, true, tid);
+        if (STOREK == STORE_QCOLS) store_qcols<T, M, TD>(buf, dst, c, 0, true, tid);
+        else fwd_store_wrows<T, M, LH, TD>(buf, dst, c, true, tid);
     }
 
     // phase PH of a full tile; every per-step quantity is a compile-time constant
@@ -861,15 +916,15 @@ struct FwdProgram {
     {
         (void)mode;
         if constexpr (PH == 0) {
-            if (LOADK == LOAD_IMAGE) fwd_load_image<T, M>(buf, src, c, tid);
-            else fwd_load_wrows<T, M>(buf, src, c, tid);
+            if (LOADK == LOAD_IMAGE) fwd_load_image<T, M, LH>(buf, src, c, tid);
+            else fwd_load_wrows<T, M, LH>(buf, src, c, tid);
         } else if constexpr (PH <= 2 * num_steps(M)) {
             constexpr int step = (PH - 1) >> 1;
             if constexpr ((PH - 1) & 1) fwd_step_store<T, M, step>(buf, tid, regs);
             else fwd_step_compute<T, M, step>(buf, tid, regs);
         } else {
-            if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, Geo<M>::HALO, false, tid);
-            else fwd_store_wrows<T, M>(buf, dst, c, false, tid);
+            if (STOREK == STORE_QCOLS) store_qcols<T, M, TD>(buf, dst, c, LH, false, tid);
+            else fwd_store_wrows<T, M, LH, TD>(buf, dst, c, false, tid);
         }
     }
 };
@@ -878,6 +933,7 @@ template <typename T, int M, int LOADK, int STOREK>
 struct BwdProgram {
     static constexpr int G = Geo<M>::G;
     static constexpr int kPhases = 2 + 2 * num_steps(M);
+    static constexpr int TD = TileTD<M, STOREK>::value;
 
     ADRT_HD static int classify(const TileCtx &c)
     {
@@ -889,7 +945,7 @@ struct BwdProgram {
 
     ADRT_HD static void zero_tile(T *buf, T *dst, const TileCtx &c, int tid)
     {
-        bwd_store_wrows<T, M>(buf, dst, c, true, tid);
+        bwd_store_wrows<T, M, TD>(buf, dst, c, true, tid);
     }
 
     template <int PH>
@@ -904,8 +960,8 @@ struct BwdProgram {
             else if (mode == TILE_FULL_MASKED) bwd_step_compute<T, M, true, step>(buf, c.D - c.d0, c.a_g, tid, regs);
             else bwd_step_compute<T, M, false, step>(buf, c.D - c.d0, c.a_g, tid, regs);
         } else {
-            if (STOREK == STORE_QCOLS) store_qcols<T, M>(buf, dst, c, 0, false, tid);
-            else bwd_store_wrows<T, M>(buf, dst, c, false, tid);
+            if (STOREK == STORE_QCOLS) store_qcols<T, M, TD>(buf, dst, c, 0, false, tid);
+            else bwd_store_wrows<T, M, TD>(buf, dst, c, false, tid);
         }
     }
 };

@@ -35,7 +35,8 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
             for (int bx = 0; bx < p.grid_x; ++bx) {
                 tile::TileCtx c;
                 c.n = n; c.D = D; c.e = e; c.g = by; c.k0 = by / e; c.a_g = by % e;
-                c.d0 = bx * tile::Geo<M>::TD;
+                c.d0 = bx * Prog::TD;
+                c.next_g = p.next_g;
                 c.in_pitch = p.in_pitch; c.out_pitch = p.out_pitch;
                 c.q = 0;
                 const int mode = Prog::classify(c);
