@@ -315,9 +315,20 @@ def ours(args, np_dtype):
     peak, peak_src = measured_peak_gbs()
     abytes = algorithmic_bytes(B, n, itemsize)
     achieved = abytes / (ms_step * 1e-3) / 1e9
+    # DRAM bytes actually moved per step, from the committed ncu --set full capture
+    # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the
+    # four pass kernels, per image) -- only valid for the configuration it was taken on.
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if tj["n"] == n and tj["dtype"] == args.dtype and lib.adrt_b200_get_mode() == 0:
+            traffic = tj["dram_bytes_per_image_fwd_plus_bdrt"] * B
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "kernel": "whole step (adrt then bdrt kernels of one batch on one GPU)",
         "algorithmic_bytes_per_step": abytes,
         "split": {
