@@ -70,7 +70,11 @@ def time_reference(n: int, np_dtype, budget_s: float, max_images: int, seed: int
     import numpy as np
 
     threads = host_cores()
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to
+    # use every host core, so set it explicitly (before libgomp initialises).
+    if "ADRT_B200_REF_THREADS" in os.environ:
+        threads = int(os.environ["ADRT_B200_REF_THREADS"])
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     from oracle import ref_loader
 
     if ref_loader.have_ref_cdefs():
