@@ -78,7 +78,8 @@ template <typename T, int M, int LOADK, int STOREK, bool kForward>
 int launch_pass(const T *src, T *dst, const PassArgs &a, int grid_x, int grid_y, cudaStream_t s)
 {
     auto kern = pass_kernel<T, M, LOADK, STOREK, kForward>;
-    const size_t smem = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T);
+    size_t smem = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T);
+    if (const char *e = getenv("ADRT_B200_SMEM_PAD_KB")) smem += (size_t)atoi(e) * 1024;  // occupancy experiments
     // per device, so not cached in a static: a process may drive several GPUs
     ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)grid_x, (unsigned)grid_y, (unsigned)(a.planes < 65535 ? a.planes : 65535));

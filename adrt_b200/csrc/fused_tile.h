@@ -123,6 +123,17 @@ ADRT_HD void load_window(const T *p, T (&dst)[N])
     for (int i = 0; i < N; ++i) dst[i] = tmp[(Q + i) / L].v[(Q + i) % L];
 }
 
+// one 16-byte vector
+template <typename T>
+ADRT_HD void store_cv(T *p, const T *src)
+{
+    constexpr int L = VecOf<T>::L;
+    Pack<T> t;
+#pragma unroll
+    for (int i = 0; i < L; ++i) t.v[i] = src[i];
+    *reinterpret_cast<Pack<T> *>(p) = t;
+}
+
 template <typename T>
 ADRT_HD void store_chunk(T *p, const T *src)
 {
@@ -272,7 +283,9 @@ ADRT_HD void fwd_load_image(T *buf, const T *img, const TileCtx &c, int tid)
 // group) and the two chunks x = 4*lane and 4*lane + 128 of it, so row pointers
 // and the alignment variant are set up once for 2 x 4 offsets.
 constexpr int NREG = 32;   // outputs a thread holds across the barrier of a step
-constexpr int CHUNKS = 2;  // chunks per thread and group
+// In the butterfly steps a chunk is ONE 16-byte vector (4 floats / 2 doubles), so that
+// consecutive lanes always touch consecutive 16-byte slots (conflict free for both
+// types); a thread owns XW / (32 * chunk) chunks of its group: 2 (float) or 4 (double).
 
 // ---- radix-4 step: local stages t and t+1 (e = 2^t) ---------------------------
 //   u[k][al][d]  = in_{2k}[d] + in_{2k+1}[d - a - al]                 (stage t)
@@ -282,6 +295,8 @@ constexpr int CHUNKS = 2;  // chunks per thread and group
 template <typename T, int AM>
 ADRT_HD void fwd_radix4_chunk(const T *r0, const T *r1, const T *r2, const T *r3, int a, int x, T *o)
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int L = VecOf<T>::L;
     constexpr int Q1 = neg_mod(AM + 1, L), Q2 = neg_mod(2 * AM + 2, L), Q3 = neg_mod(3 * AM + 3, L);
     T y0[V], y1[V + 1], y2[V + 2], y3[V + 3];
@@ -312,6 +327,8 @@ ADRT_HD void fwd_radix4_chunk(const T *r0, const T *r1, const T *r2, const T *r3
 template <typename T, int AM>
 ADRT_HD void fwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int lo_out, T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int P = Pitch<T>::value;
     const T *r0 = buf + ((k0 * 4) * e + a) * P;
     const T *r1 = r0 + e * P, *r2 = r1 + e * P, *r3 = r2 + e * P;
@@ -325,6 +342,8 @@ ADRT_HD void fwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int 
 template <typename T, int M, int t>
 ADRT_HD void fwd_radix4_compute(const T *buf, int tid, T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int G = Geo<M>::G;
     constexpr int e = 1 << t, lo_out = 4 * e;
     const int gi = tid >> 5, lane = tid & 31;
@@ -341,6 +360,8 @@ ADRT_HD void fwd_radix4_compute(const T *buf, int tid, T (&o)[NREG])
 template <typename T, int M, int t>
 ADRT_HD void fwd_radix4_store(T *buf, int tid, const T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int G = Geo<M>::G, P = Pitch<T>::value;
     constexpr int e = 1 << t, lo_out = 4 * e;
     const int gi = tid >> 5, lane = tid & 31;
@@ -352,7 +373,7 @@ ADRT_HD void fwd_radix4_store(T *buf, int tid, const T (&o)[NREG])
         const int x = (lane + 32 * c) * V;
         if (x >= lo_out) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p) store_chunk<T>(orow + p * P + x, &o[(c * 4 + p) * V]);
+            for (int p = 0; p < 4; ++p) store_cv<T>(orow + p * P + x, &o[(c * 4 + p) * V]);
         }
     }
 }
@@ -361,6 +382,8 @@ ADRT_HD void fwd_radix4_store(T *buf, int tid, const T (&o)[NREG])
 template <typename T, int BM>
 ADRT_HD void fwd_radix2_group(const T *buf, int e, int k, int b, int lane, int lo_out, T *o)
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
     constexpr int Q = neg_mod(BM + 1, L);
     const T *rA = buf + ((2 * k) * e + b) * P;
@@ -383,6 +406,8 @@ ADRT_HD void fwd_radix2_group(const T *buf, int e, int k, int b, int lane, int l
 template <typename T, int M, int t>
 ADRT_HD void fwd_radix2_compute(const T *buf, int tid, T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP;
     constexpr int e = 1 << t, lo_out = 2 * e < 4 ? 4 : 2 * e;
     const int lane = tid & 31;
@@ -404,6 +429,8 @@ ADRT_HD void fwd_radix2_compute(const T *buf, int tid, T (&o)[NREG])
 template <typename T, int M, int t>
 ADRT_HD void fwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     constexpr int e = 1 << t, lo_out = 2 * e < 4 ? 4 : 2 * e;
     const int lane = tid & 31;
@@ -417,8 +444,8 @@ ADRT_HD void fwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
         for (int c = 0; c < CHUNKS; ++c) {
             const int x = (lane + 32 * c) * V;
             if (x >= lo_out) {
-                store_chunk<T>(orow + x, &o[((u * CHUNKS + c) * 2 + 0) * V]);
-                store_chunk<T>(orow + P + x, &o[((u * CHUNKS + c) * 2 + 1) * V]);
+                store_cv<T>(orow + x, &o[((u * CHUNKS + c) * 2 + 0) * V]);
+                store_cv<T>(orow + P + x, &o[((u * CHUNKS + c) * 2 + 1) * V]);
             }
         }
     }
@@ -642,6 +669,8 @@ ADRT_HD T bmask(T v, int pos, int lim, bool odd)
 template <typename T, bool kMask, int JP>
 ADRT_HD void bwd_radix4_chunk(const T *ip, int a, int x, int jp, int lim_p, int lim_1, T *o)
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
     constexpr int Q1 = (JP * 1) % L, Q2 = (JP * 2) % L, Q3 = (JP * 3) % L;
     const int s0 = jp * 4 * a;  // skew of parent 0; parent p adds jp*p
@@ -687,12 +716,16 @@ ADRT_HD void bwd_radix4_chunk(const T *ip, int a, int x, int jp, int lim_p, int 
 template <typename T>
 ADRT_HD bool bwd_chunk_ok(int x, int jp, int a)
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     return x + jp * (4 * a + 3) + V + 3 + 3 <= Pitch<T>::value;
 }
 
 template <typename T, bool kMask, int JP>
 ADRT_HD void bwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int jp, int dt, int ag, T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int P = Pitch<T>::value;
     const T *ip = buf + (k0 * 4 * e + 4 * a) * P;
     const int lim_p = dt + ag * (k0 * 4 * e), lim_1 = lim_p + ag * 2 * e;
@@ -707,6 +740,8 @@ ADRT_HD void bwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int 
 template <typename T, int M, bool kMask, int t, int rprev>
 ADRT_HD void bwd_radix4_compute(const T *buf, int dt, int ag, int tid, T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int G = Geo<M>::G;
     constexpr int e = 1 << t;
     const int gi = tid >> 5, lane = tid & 31;
@@ -724,6 +759,8 @@ ADRT_HD void bwd_radix4_compute(const T *buf, int dt, int ag, int tid, T (&o)[NR
 template <typename T, int M, int t, int rprev>
 ADRT_HD void bwd_radix4_store(T *buf, int tid, const T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int G = Geo<M>::G, P = Pitch<T>::value;
     constexpr int e = 1 << t;
     const int gi = tid >> 5, lane = tid & 31;
@@ -736,7 +773,7 @@ ADRT_HD void bwd_radix4_store(T *buf, int tid, const T (&o)[NREG])
         const int x = (lane + 32 * c) * V;
         if (bwd_chunk_ok<T>(x, jp, a)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) store_chunk<T>(orow + j * e * P + x, &o[(c * 4 + j) * V]);   // skew j*a
+            for (int j = 0; j < 4; ++j) store_cv<T>(orow + j * e * P + x, &o[(c * 4 + j) * V]);   // skew j*a
         }
     }
 }
@@ -745,6 +782,8 @@ ADRT_HD void bwd_radix4_store(T *buf, int tid, const T (&o)[NREG])
 template <typename T, int M, bool kMask, int t>
 ADRT_HD void bwd_radix2_compute(const T *buf, int dt, int ag, int tid, T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     constexpr int e = 1 << t;
     const int lane = tid & 31;
@@ -779,6 +818,8 @@ ADRT_HD void bwd_radix2_compute(const T *buf, int dt, int ag, int tid, T (&o)[NR
 template <typename T, int M, int t>
 ADRT_HD void bwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
 {
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
+    (void)CHUNKS;
     constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
     constexpr int e = 1 << t;
     const int lane = tid & 31;
@@ -791,8 +832,8 @@ ADRT_HD void bwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
             const int x = (lane + 32 * c) * V;
-            store_chunk<T>(oA + x, &o[((u * CHUNKS + c) * 2 + 0) * V]);
-            store_chunk<T>(oA + e * P + x, &o[((u * CHUNKS + c) * 2 + 1) * V]);   // skew b
+            store_cv<T>(oA + x, &o[((u * CHUNKS + c) * 2 + 0) * V]);
+            store_cv<T>(oA + e * P + x, &o[((u * CHUNKS + c) * 2 + 1) * V]);   // skew b
         }
     }
 }
