@@ -937,10 +937,12 @@ struct FwdProgram {
         if (sup > c.D) sup = c.D;
         if (STOREK == STORE_QCOLS) {
             if (c.d0 >= c.D) return TILE_SKIP;
+            if (c.d0 >= sup) return TILE_ZERO;
         } else {
             if (c.d0 >= c.out_pitch) return TILE_SKIP;
+            // stored rows are skewed by up to 3 elements: position d0 holds offset d0 - s
+            if (c.d0 - 3 >= sup) return TILE_ZERO;
         }
-        if (c.d0 >= sup) return TILE_ZERO;
         return TILE_FULL;
     }
 

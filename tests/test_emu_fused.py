@@ -95,6 +95,13 @@ def test_six_stage_pass(emu, dt):
     _check(emu, 128, 1, dt, "1,6")
 
 
+def test_skewed_rows_near_tile_boundary(emu):
+    # regression: a group whose support ends within 3 offsets below a tile boundary of a
+    # workspace-storing pass (rows are stored with a skew of up to 3 elements)
+    _check(emu, 512, 1, np.float32, "6,2,1")
+    _check(emu, 1024, 1, np.float32, "6,3,1")
+
+
 def test_medium_default(emu):
     # K = 9: two passes (5, 4); several d-tiles per group, masked boundary tiles
     _check(emu, 512, 1, np.float32)
