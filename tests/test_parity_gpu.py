@@ -219,6 +219,40 @@ def test_fmg_step_batch_bit_exact():
         _eq(got_t.cpu().numpy(), want, "fmg_step tensor path")
 
 
+def test_cg_recipe_matches_scipy_on_oracle():
+    """docs/examples.cginverse.md:40-67: CG on the normal equations; compare with
+    SciPy's cg driven by the CPU oracle operators (tolerance: both stop at rtol 1e-6)."""
+    from scipy.sparse.linalg import LinearOperator, cg
+
+    from adrt_b200 import recipes
+
+    n = 16
+    xs = np.linspace(-1, 1, n)
+    xx, yy = np.meshgrid(xs, xs)
+    img = np.exp(-6 * (xx ** 2 + (yy - 0.2) ** 2)).astype(np.float64)
+    b = O.adrt(img)
+
+    def matvec(v):
+        y = O.bdrt(O.adrt(v.reshape(n, n)))
+        return O.truncate(y).mean(axis=0).ravel()
+
+    A = LinearOperator((n * n, n * n), matvec=matvec, dtype=np.float64)
+    want, info = cg(A, O.truncate(O.bdrt(b)).mean(axis=0).ravel(), rtol=1e-10, atol=0.0)
+    assert info == 0
+    got, iters = recipes.iadrt_cg(b, rtol=1e-10, return_info=True)
+    assert iters > 3
+    np.testing.assert_allclose(got, want.reshape(n, n), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(got, img, rtol=1e-5, atol=1e-6)
+    # the operator itself is bit-exact apart from NumPy's pairwise mean vs our sequential one
+    import torch
+
+    v = make_image(4, (n, n), np.float64)
+    nv = recipes.normal_operator(torch.from_numpy(v).cuda()).cpu().numpy()
+    np.testing.assert_allclose(nv, matvec(v.ravel()).reshape(n, n), rtol=1e-13, atol=1e-13)
+    with pytest.raises(ValueError, match="batch dimension not supported"):
+        recipes.iadrt_cg(np.zeros((2, 4, 31, 16)))
+
+
 def test_iadrt_roundtrip():
     # reference tests/test_iadrt.py:185-223
     for n in (16, 32):
