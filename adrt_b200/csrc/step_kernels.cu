@@ -62,26 +62,47 @@ adrt_init_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, 
     }
 }
 
+// kVec consecutive outputs leave a thread as one aligned vector store
+template <typename T, int kVec> struct alignas(sizeof(T) * kVec) OutVec { T v[kVec]; };
+
+template <typename T, int kVec>
+__device__ __forceinline__ void store_outvec(T *o, const T (&v)[kVec])
+{
+    OutVec<T, kVec> t;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) t.v[i] = v[i];
+    *reinterpret_cast<OutVec<T, kVec> *>(o) = t;
+}
+
 // ---- adrt_step: adrt_cdefs_adrt.hpp:215-258 -----------------------------------
 template <typename T>
+__device__ __forceinline__ T adrt_step_one(const T *__restrict__ I, int64_t d, int c, int n, int iter)
+{
+    const int e = 1 << iter;
+    const int a = c & (2 * e - 1);
+    const int cA = (c - a) + (a >> 1);
+    const int sh = (a + 1) >> 1;
+    const T av = I[d * n + cA];
+    const T bv = (d >= sh) ? I[(d - sh) * n + cA + e] : T(-0.0);
+    return av + bv;
+}
+
+// kVec = 4 consecutive columns per thread (one 16/32-byte store), n % 4 == 0
+template <typename T, int kVec>
 __global__ void __launch_bounds__(kThreads)
 adrt_step_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int logn, int iter)
 {
     const int64_t D = 2 * (int64_t)n - 1;
-    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t idx = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kVec;
     if (idx >= D * n) return;
-    const int d = (int)(idx >> logn), c = (int)(idx & (n - 1));
-    const int e = 1 << iter;
-    const int a = c & (2 * e - 1);
-    const int base = c - a;  // k * 2e
-    const int cA = base + (a >> 1);
-    const int cB = cA + e;
-    const int sh = (a + 1) >> 1;
+    const int64_t d = idx >> logn;
+    const int c = (int)(idx & (n - 1));
     for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
         const T *I = in + p * D * n;
-        const T av = I[(int64_t)d * n + cA];
-        const T bv = (d >= sh) ? I[(int64_t)(d - sh) * n + cB] : T(-0.0);
-        out[p * D * n + idx] = av + bv;
+        T v[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) v[i] = adrt_step_one<T>(I, d, c + i, n, iter);
+        store_outvec<T, kVec>(out + p * D * n + idx, v);
     }
 }
 
@@ -90,29 +111,33 @@ adrt_step_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, 
 // step semantics: missing operands are +0 and are still added (aval=0; bval=0).
 // core semantics: last valid row is a copy of la_val, rows past it are +0.
 template <typename T, bool kCore>
+__device__ __forceinline__ T bdrt_step_one(const T *__restrict__ I, int64_t d, int c, int n, int64_t D, int adrt_iter)
+{
+    const int e = 1 << adrt_iter;
+    const int cb = c >> adrt_iter, ci = c & (e - 1);
+    const int beta = 2 * (ci + e * (cb >> 1));
+    if (!(cb & 1)) return I[d * n + beta] + I[d * n + beta + 1];
+    const int64_t r = d + ci;
+    const T av = (r < D) ? I[r * n + beta] : T(0.0);
+    const T bv = (r + 1 < D) ? I[(r + 1) * n + beta + 1] : (kCore ? T(-0.0) : T(0.0));
+    return av + bv;
+}
+
+template <typename T, bool kCore, int kVec>
 __global__ void __launch_bounds__(kThreads)
 bdrt_step_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int logn, int adrt_iter)
 {
     const int64_t D = 2 * (int64_t)n - 1;
-    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t idx = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * kVec;
     if (idx >= D * n) return;
-    const int d = (int)(idx >> logn), c = (int)(idx & (n - 1));
-    const int e = 1 << adrt_iter;
-    const int cb = c >> adrt_iter, ci = c & (e - 1);
-    const int beta = 2 * (ci + e * (cb >> 1));
-    const bool odd = cb & 1;
-    const int64_t r = odd ? (int64_t)d + ci : d;
+    const int64_t d = idx >> logn;
+    const int c = (int)(idx & (n - 1));
     for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
         const T *I = in + p * D * n;
-        T av, bv;
-        if (!odd) {
-            av = I[r * n + beta];
-            bv = I[r * n + beta + 1];
-        } else {
-            av = (r < D) ? I[r * n + beta] : T(0.0);
-            bv = (r + 1 < D) ? I[(r + 1) * n + beta + 1] : (kCore ? T(-0.0) : T(0.0));
-        }
-        out[p * D * n + idx] = av + bv;
+        T v[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) v[i] = bdrt_step_one<T, kCore>(I, d, c + i, n, D, adrt_iter);
+        store_outvec<T, kVec>(out + p * D * n + idx, v);
     }
 }
 
@@ -308,7 +333,10 @@ template <typename T>
 int launch_adrt_step(const T *in, T *out, int64_t B, int64_t n, int step, cudaStream_t s)
 {
     const int64_t D = 2 * n - 1;
-    adrt_step_kernel<T><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), step);
+    if (n % 4 == 0)
+        adrt_step_kernel<T, 4><<<plane_grid(D * n / 4, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), step);
+    else
+        adrt_step_kernel<T, 1><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), step);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }
@@ -318,10 +346,12 @@ int launch_bdrt_step(const T *in, T *out, int64_t B, int64_t n, int step, bool c
 {
     const int64_t D = 2 * n - 1;
     const int adrt_iter = num_iters(n) - 1 - step;
-    if (core_semantics)
-        bdrt_step_kernel<T, true><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
-    else
-        bdrt_step_kernel<T, false><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
+    const bool vec = n % 4 == 0;
+    const dim3 grid = plane_grid(vec ? D * n / 4 : D * n, B * 4);
+    if (core_semantics && vec) bdrt_step_kernel<T, true, 4><<<grid, kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
+    else if (core_semantics) bdrt_step_kernel<T, true, 1><<<grid, kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
+    else if (vec) bdrt_step_kernel<T, false, 4><<<grid, kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
+    else bdrt_step_kernel<T, false, 1><<<grid, kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }
