@@ -117,6 +117,19 @@ def test_large_vs_oracle(mode, dn, n, B):
         _eq(adrt.bdrt(y), O.bdrt(y), f"bdrt n={n}")
 
 
+def test_many_planes(mode):
+    """More (image, quadrant) planes than gridDim.z allows: kernels loop over planes."""
+    for n in (4, 16):
+        B = 17000  # 68000 planes > 65535
+        x = make_image(8, (B, n, n), np.float32)
+        y = adrt.adrt(x)
+        _eq(y, O.adrt(x), f"adrt B={B} n={n}")
+        _eq(adrt.bdrt(y), O.bdrt(y), f"bdrt B={B} n={n}")
+        if mode == 0:
+            _eq(adrt.core.adrt_step(y, 1), O.adrt_step(y, 1), "adrt_step many planes")
+            _eq(adrt.iadrt(y[:100]), O.iadrt(y[:100]), "iadrt")
+
+
 def test_special_values(mode):
     """NaN / Inf propagate, negative zeros keep their sign (SURVEY 8a exactness)."""
     n = 32
