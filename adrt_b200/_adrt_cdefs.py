@@ -398,3 +398,64 @@ def sub(a, b, /, *, out=None):
 
 def add(a, b, /, *, out=None):
     return _binary("add", a, b, out)
+
+
+def adrt_quadrants(a, q_first, q_count, /, *, out=None):
+    """Quadrants ``q_first .. q_first+q_count-1`` of ``adrt(a)`` only:
+    ``(B?, n, n)`` -> ``(B?, q_count, 2n-1, n)``.  CUDA tensors only; used to shard
+    one large image over several GPUs (the four quadrants are independent)."""
+    arr = _extract_array(a)
+    if not arr.is_torch:
+        raise TypeError("adrt_quadrants is a device-only helper (CUDA tensors)")
+    shape = _array_shape(arr, 2, 3)
+    b, r, c = shape
+    if not (r == c and _is_pow2(c)):
+        raise ValueError("array must be square with a power of two shape")
+    q_first, q_count = operator.index(q_first), operator.index(q_count)
+    if not (0 <= q_first and 1 <= q_count and q_first + q_count <= 4):
+        raise ValueError(f"bad quadrant range {q_first}+{q_count}")
+    res = _result_shape(arr, (b, q_count, 2 * c - 1, c), drop=-1)
+    lib = _lib.load()
+    code = _dtype_code(arr)
+    _lib.require_device()
+    ret = _empty_like(arr, res, out)
+    import torch
+
+    t = arr.obj
+    with torch.cuda.device(t.device):
+        nbytes = lib.adrt_b200_adrt_quadrants_workspace_bytes(b, c, code, q_count)
+        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=t.device)
+        rc = lib.adrt_b200_adrt_quadrants(t.data_ptr(), ret.data_ptr(), b, c, code, q_first, q_count,
+                                          ws.data_ptr(), int(nbytes), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "adrt_quadrants")
+    return ret
+
+
+def bdrt_planes(a, /, *, out=None):
+    """Back-projection of independent ``(2n-1, n)`` planes: ``(..., 2n-1, n)`` -> same
+    shape (any leading dims, e.g. a subset of quadrants).  CUDA tensors only."""
+    if not (_is_torch_tensor(a) and a.is_cuda):
+        raise TypeError("bdrt_planes is a device-only helper (CUDA tensors)")
+    a = a.contiguous()
+    n = a.shape[-1]
+    if a.ndim < 2 or a.shape[-2] != 2 * n - 1 or not _is_pow2(n):
+        raise ValueError("array must have a valid ADRT output shape")
+    arr = _extract_array(a)
+    code = _dtype_code(arr)
+    planes = 1
+    for s in a.shape[:-2]:
+        planes *= int(s)
+    if planes < 1:
+        raise ValueError("all array dimensions must be nonzero, but found zero in dimension 0")
+    lib = _lib.load()
+    _lib.require_device()
+    ret = _empty_like(arr, arr.shape, out)
+    import torch
+
+    with torch.cuda.device(a.device):
+        nbytes = lib.adrt_b200_bdrt_planes_workspace_bytes(planes, n, code)
+        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=a.device)
+        rc = lib.adrt_b200_bdrt_planes(a.data_ptr(), ret.data_ptr(), planes, n, code, ws.data_ptr(), int(nbytes),
+                                       torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "bdrt_planes")
+    return ret

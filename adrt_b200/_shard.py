@@ -45,3 +45,75 @@ def gather_batch(local, dist=None):
     out = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(out, padded)
     return torch.cat([o[:k] for o, k in zip(out, counts)], dim=0)
+
+
+# ---------------------------------------------------------------------------
+# One large image over several GPUs: quadrant sharding
+# ---------------------------------------------------------------------------
+# The four quadrants of adrt are independent transforms of four orientations of
+# the image (adrt_cdefs_adrt.hpp:124-175) and bdrt treats planes independently,
+# so `truncate(bdrt(adrt(x)))` splits 4 ways with the image replicated and ONE
+# exchange per application: an all-gather of the four truncated (n, n)
+# back-projections, summed locally in the fixed order ((t0+t1)+t2)+t3 so that
+# the result is bit-identical to the single-GPU `np.mean(..., axis=-3)` order.
+
+def quadrant_owner_range(world: int, rank: int) -> tuple[int, int]:
+    """Quadrants [q_first, q_first + q_count) owned by `rank` when `world` in {1, 2, 4}
+    ranks share one image (ranks >= 4 own nothing: angle-block sharding inside a
+    quadrant is not implemented yet)."""
+    if world >= 4:
+        return (rank, 1) if rank < 4 else (0, 0)
+    per = 4 // world
+    return rank * per, per
+
+
+def truncate_quadrant(z, q: int):
+    """utils.truncate for a single quadrant plane ``(..., 2n-1, n)`` -> ``(..., n, n)``."""
+    n = z.shape[-1]
+    sq = z[..., :n, :]
+    if q == 0:
+        return sq.flip(-2).transpose(-1, -2)
+    if q == 1:
+        return sq.flip(-2)
+    if q == 2:
+        return sq
+    return sq.flip((-1, -2)).transpose(-1, -2)
+
+
+def _local_quadrant_backprojections(x, q_first, q_count):
+    from . import _adrt_cdefs as cd
+
+    y = cd.adrt_quadrants(x, q_first, q_count)
+    z = cd.bdrt_planes(y)
+    return [truncate_quadrant(z[..., i, :, :], q_first + i).contiguous() for i in range(q_count)]
+
+
+def sharded_normal_operator(x, dist=None, *, local_fn=_local_quadrant_backprojections):
+    """``mean_q(truncate(bdrt(adrt(x))))`` with the quadrants spread over the ranks of
+    the default process group.  `x` ``(n, n)`` or ``(B, n, n)`` must be replicated
+    on every rank; the result is replicated too and bit-identical to the
+    single-GPU ``recipes.normal_operator``.  `local_fn(x, q_first, q_count)` returns
+    the rank's truncated back-projections (overridable so that CPU tests can
+    exercise the exchange with the oracle)."""
+    import torch
+
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    q_first, q_count = quadrant_owner_range(world, rank)
+    mine = local_fn(x, q_first, q_count) if q_count else []
+    if world == 1:
+        parts = mine
+    else:
+        per = max(1, 4 // min(world, 4))
+        # fixed-size buffer per rank: `per` images, zero for ranks that own nothing
+        local = torch.zeros((per, *x.shape), dtype=x.dtype, device=x.device)
+        for i, t in enumerate(mine):
+            local[i] = t
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        parts = []
+        for r in range(min(world, 4)):
+            qf, qc = quadrant_owner_range(world, r)
+            parts += [gathered[r][i] for i in range(qc)]
+    t0, t1, t2, t3 = parts
+    return (((t0 + t1) + t2) + t3) / 4

@@ -96,7 +96,7 @@ template <typename T>
 size_t adrt_ws_elems(int64_t B, int64_t n)
 {
     if (g_mode.load() == 0) {
-        size_t f = fused_adrt_workspace_elems<T>(B, n);
+        size_t f = fused_adrt_workspace_elems<T>(B, n, 4);
         if (f != (size_t)-1) return f;
     }
     return num_iters(n) == 0 ? 0 : (size_t)sino_elems(B, n);
@@ -106,7 +106,7 @@ template <typename T>
 size_t bdrt_ws_elems(int64_t B, int64_t n)
 {
     if (g_mode.load() == 0) {
-        size_t f = fused_bdrt_workspace_elems<T>(B, n);
+        size_t f = fused_bdrt_workspace_elems<T>(B, n, 4);
         if (f != (size_t)-1) return f;
     }
     return num_iters(n) <= 1 ? 0 : (size_t)sino_elems(B, n);
@@ -122,7 +122,7 @@ int adrt_impl(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_bytes,
     }
     if (g_mode.load() == 0) {
         bool handled = false;
-        int rc = fused_adrt<T>(in, out, B, n, ws, ws_bytes / sizeof(T), s, &handled);
+        int rc = fused_adrt<T>(in, out, B, n, 0, 4, ws, ws_bytes / sizeof(T), s, &handled);
         if (rc != ADRT_B200_OK || handled) return rc;
     }
     return adrt_by_steps<T>(in, out, B, n, ws, s);
@@ -138,7 +138,7 @@ int bdrt_impl(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_bytes,
     }
     if (g_mode.load() == 0) {
         bool handled = false;
-        int rc = fused_bdrt<T>(in, out, B, n, ws, ws_bytes / sizeof(T), s, &handled);
+        int rc = fused_bdrt<T>(in, out, B, n, 4, ws, ws_bytes / sizeof(T), s, &handled);
         if (rc != ADRT_B200_OK || handled) return rc;
     }
     return bdrt_by_steps<T>(in, out, B, n, ws, s);
@@ -242,6 +242,41 @@ int get_interp_table(int device, int64_t n, int dtype, cudaStream_t s, InterpTab
 
 using namespace adrt_b200;
 
+template <typename T>
+int adrt_quadrants_impl(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_bytes,
+                        cudaStream_t s)
+{
+    if (n == 1) {  // K = 0: every quadrant is the image itself
+        for (int64_t b = 0; b < B; ++b)
+            for (int q = 0; q < q_count; ++q)
+                ADRT_CUDA_CHECK(cudaMemcpyAsync(out + b * q_count + q, in + b, sizeof(T), cudaMemcpyDeviceToDevice, s));
+        return ADRT_B200_OK;
+    }
+    const size_t need = fused_adrt_workspace_elems<T>(B, n, q_count) * sizeof(T);
+    if (need > 0 && (!ws || ws_bytes < need)) {
+        set_error("adrt_quadrants workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return ADRT_B200_EWORKSPACE;
+    }
+    bool handled = false;
+    return fused_adrt<T>(in, out, B, n, q_first, q_count, ws, ws_bytes / sizeof(T), s, &handled);
+}
+
+template <typename T>
+int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, T *ws, size_t ws_bytes, cudaStream_t s)
+{
+    if (n == 1) {
+        ADRT_CUDA_CHECK(cudaMemcpyAsync(out, in, sizeof(T) * planes, cudaMemcpyDeviceToDevice, s));
+        return ADRT_B200_OK;
+    }
+    const size_t need = fused_bdrt_workspace_elems<T>(planes, n, 1) * sizeof(T);
+    if (need > 0 && (!ws || ws_bytes < need)) {
+        set_error("bdrt_planes workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return ADRT_B200_EWORKSPACE;
+    }
+    bool handled = false;
+    return fused_bdrt<T>(in, out, planes, n, 1, ws, ws_bytes / sizeof(T), s, &handled);
+}
+
 #define DISPATCH(dtype, CALL_F32, CALL_F64) ((dtype) == ADRT_B200_F64 ? (CALL_F64) : (CALL_F32))
 
 extern "C" {
@@ -287,6 +322,40 @@ int adrt_b200_bdrt(const void *in, void *out, int64_t B, int64_t n, int dtype, v
     return DISPATCH(dtype,
                     bdrt_impl<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes, as_stream(stream)),
                     bdrt_impl<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes, as_stream(stream)));
+}
+
+// ---- quadrant / plane subsets (single-image multi-GPU sharding) -------------------
+size_t adrt_b200_adrt_quadrants_workspace_bytes(int64_t B, int64_t n, int dtype, int q_count)
+{
+    if (B <= 0 || !is_pow2(n) || n > kMaxN || n < 2 || !dtype_ok(dtype) || q_count < 1 || q_count > 4) return 0;
+    return DISPATCH(dtype, fused_adrt_workspace_elems<float>(B, n, q_count) * 4, fused_adrt_workspace_elems<double>(B, n, q_count) * 8);
+}
+
+int adrt_b200_adrt_quadrants(const void *in, void *out, int64_t B, int64_t n, int dtype, int q_first, int q_count,
+                             void *ws, size_t ws_bytes, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    ADRT_REQUIRE(q_first >= 0 && q_count >= 1 && q_first + q_count <= 4, "bad quadrant range %d+%d", q_first, q_count);
+    return DISPATCH(dtype,
+                    adrt_quadrants_impl<float>((const float *)in, (float *)out, B, n, q_first, q_count, (float *)ws, ws_bytes, as_stream(stream)),
+                    adrt_quadrants_impl<double>((const double *)in, (double *)out, B, n, q_first, q_count, (double *)ws, ws_bytes, as_stream(stream)));
+}
+
+size_t adrt_b200_bdrt_planes_workspace_bytes(int64_t planes, int64_t n, int dtype)
+{
+    if (planes <= 0 || !is_pow2(n) || n > kMaxN || n < 2 || !dtype_ok(dtype)) return 0;
+    return DISPATCH(dtype, fused_bdrt_workspace_elems<float>(planes, n, 1) * 4, fused_bdrt_workspace_elems<double>(planes, n, 1) * 8);
+}
+
+int adrt_b200_bdrt_planes(const void *in, void *out, int64_t planes, int64_t n, int dtype, void *ws, size_t ws_bytes,
+                          void *stream)
+{
+    int rc = check_image(in, out, planes, n, dtype);
+    if (rc) return rc;
+    return DISPATCH(dtype,
+                    bdrt_planes_impl<float>((const float *)in, (float *)out, planes, n, (float *)ws, ws_bytes, as_stream(stream)),
+                    bdrt_planes_impl<double>((const double *)in, (double *)out, planes, n, (double *)ws, ws_bytes, as_stream(stream)));
 }
 
 int adrt_b200_adrt_step(const void *in, void *out, int64_t B, int64_t n, int step, int dtype, void *stream)

@@ -71,9 +71,10 @@ template <typename T> int launch_binary(const T *a, const T *b, T *out, int64_t 
 
 // Fused multi-stage paths (fused_adrt.cu).  Return ADRT_B200_OK or an error;
 // `handled` is false when the shape is left to the per-stage path.
-template <typename T> size_t fused_adrt_workspace_elems(int64_t B, int64_t n);
-template <typename T> size_t fused_bdrt_workspace_elems(int64_t B, int64_t n);
-template <typename T> int fused_adrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
-template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
+// B images with q_count planes each (forward: quadrants q_first..q_first+q_count-1).
+template <typename T> size_t fused_adrt_workspace_elems(int64_t B, int64_t n, int q_count);
+template <typename T> size_t fused_bdrt_workspace_elems(int64_t B, int64_t n, int q_count);
+template <typename T> int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
+template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
 
 }  // namespace adrt_b200

@@ -18,6 +18,7 @@ struct PassArgs {
     long long in_pitch, out_pitch;
     long long src_plane_stride, dst_plane_stride;  // elements between consecutive planes
     int planes;
+    int q_first, q_count;   // image loader: plane -> (image = plane / q_count, quadrant = q_first + plane % q_count)
 };
 
 // The phases of a full tile, unrolled at compile time with a barrier after each.
@@ -60,8 +61,8 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
     for (int plane = blockIdx.z; plane < a.planes; plane += gridDim.z) {
         const T *sp;
         if (LOADK == tile::LOAD_IMAGE) {
-            c.q = plane & 3;
-            sp = src + (long long)(plane >> 2) * a.src_plane_stride;
+            c.q = a.q_first + plane % a.q_count;
+            sp = src + (long long)(plane / a.q_count) * a.src_plane_stride;
         } else {
             sp = src + (long long)plane * a.src_plane_stride;
         }
@@ -134,12 +135,15 @@ int wave_images(int64_t B)
 }
 
 template <typename T, bool kForward>
-int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, T *ws, size_t ws_elems, cudaStream_t s)
+int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, int q_count, T *ws, size_t ws_elems,
+             cudaStream_t s)
 {
+    // B images of q_count planes each (forward: quadrants q_first .. q_first+q_count-1 of
+    // every image; transposed: any plane count, the quadrant identity does not matter)
     const int n = pl.n, D = pl.D;
     const int wave = wave_images(B);
-    const size_t slot0 = pl.ws_slot_elems[0] * 4 * (size_t)wave;
-    const size_t slot1 = pl.ws_slot_elems[1] * 4 * (size_t)wave;
+    const size_t slot0 = pl.ws_slot_elems[0] * q_count * (size_t)wave;
+    const size_t slot1 = pl.ws_slot_elems[1] * q_count * (size_t)wave;
     if (slot0 + slot1 > ws_elems) {
         set_error("fused workspace too small: need %zu elements, got %zu", slot0 + slot1, ws_elems);
         return ADRT_B200_EWORKSPACE;
@@ -153,18 +157,19 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, T *ws, size_t
             PassArgs a;
             a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g;
             a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
-            a.planes = nb * 4;
+            a.planes = nb * q_count;
+            a.q_first = q_first; a.q_count = q_count;
             const T *src;
             T *dst;
             if (p.src_buf < 0) {
                 if (kForward) { src = in + b0 * img_elems; a.src_plane_stride = img_elems; }
-                else { src = in + b0 * 4 * sino_plane; a.src_plane_stride = sino_plane; }
+                else { src = in + b0 * q_count * sino_plane; a.src_plane_stride = sino_plane; }
             } else {
                 src = slot[p.src_buf];
                 a.src_plane_stride = (long long)n * p.in_pitch;
             }
             if (p.dst_buf < 0) {
-                dst = out + b0 * 4 * sino_plane;
+                dst = out + b0 * q_count * sino_plane;
                 a.dst_plane_stride = sino_plane;
             } else {
                 dst = slot[p.dst_buf];
@@ -180,46 +185,48 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, T *ws, size_t
 }  // namespace
 
 template <typename T>
-size_t fused_adrt_workspace_elems(int64_t B, int64_t n)
+size_t fused_adrt_workspace_elems(int64_t B, int64_t n, int q_count)
 {
     plan::Plan pl;
     if (n > kMaxN || !plan::make_forward_plan(n, sizeof(T), &pl)) return (size_t)-1;
-    return (pl.ws_slot_elems[0] + pl.ws_slot_elems[1]) * 4 * (size_t)wave_images(B);
+    return (pl.ws_slot_elems[0] + pl.ws_slot_elems[1]) * q_count * (size_t)wave_images(B);
 }
 
 template <typename T>
-size_t fused_bdrt_workspace_elems(int64_t B, int64_t n)
+size_t fused_bdrt_workspace_elems(int64_t B, int64_t n, int q_count)
 {
     plan::Plan pl;
     if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl)) return (size_t)-1;
-    return (pl.ws_slot_elems[0] + pl.ws_slot_elems[1]) * 4 * (size_t)wave_images(B);
+    return (pl.ws_slot_elems[0] + pl.ws_slot_elems[1]) * q_count * (size_t)wave_images(B);
 }
 
 template <typename T>
-int fused_adrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s, bool *handled)
+int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems,
+               cudaStream_t s, bool *handled)
 {
     plan::Plan pl;
     *handled = false;
     if (n > kMaxN || !plan::make_forward_plan(n, sizeof(T), &pl)) return ADRT_B200_OK;
     *handled = true;
-    return run_plan<T, true>(pl, in, out, B, ws, ws_elems, s);
+    return run_plan<T, true>(pl, in, out, B, q_first, q_count, ws, ws_elems, s);
 }
 
 template <typename T>
-int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s, bool *handled)
+int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, T *ws, size_t ws_elems, cudaStream_t s,
+               bool *handled)
 {
     plan::Plan pl;
     *handled = false;
     if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl)) return ADRT_B200_OK;
     *handled = true;
-    return run_plan<T, false>(pl, in, out, B, ws, ws_elems, s);
+    return run_plan<T, false>(pl, in, out, B, 0, q_count, ws, ws_elems, s);
 }
 
 #define INSTANTIATE(T)                                                      \
-    template size_t fused_adrt_workspace_elems<T>(int64_t, int64_t);        \
-    template size_t fused_bdrt_workspace_elems<T>(int64_t, int64_t);        \
-    template int fused_adrt<T>(const T *, T *, int64_t, int64_t, T *, size_t, cudaStream_t, bool *); \
-    template int fused_bdrt<T>(const T *, T *, int64_t, int64_t, T *, size_t, cudaStream_t, bool *);
+    template size_t fused_adrt_workspace_elems<T>(int64_t, int64_t, int);   \
+    template size_t fused_bdrt_workspace_elems<T>(int64_t, int64_t, int);   \
+    template int fused_adrt<T>(const T *, T *, int64_t, int64_t, int, int, T *, size_t, cudaStream_t, bool *); \
+    template int fused_bdrt<T>(const T *, T *, int64_t, int64_t, int, T *, size_t, cudaStream_t, bool *);
 INSTANTIATE(float)
 INSTANTIATE(double)
 

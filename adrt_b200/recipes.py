@@ -17,22 +17,34 @@ from ._wrappers import _normalize_array
 from .core import _to_device
 
 
-def normal_operator(x, /, *, ridge: float = 0.0):
-    """``mean_q(truncate(bdrt(adrt(x)))) + ridge * x`` for CUDA tensors ``(B?, n, n)``."""
-    out = cd.truncate_mean(cd.bdrt(cd.adrt(x)), 1.0)
+def normal_operator(x, /, *, ridge: float = 0.0, dist=None):
+    """``mean_q(truncate(bdrt(adrt(x)))) + ridge * x`` for CUDA tensors ``(B?, n, n)``.
+
+    With an initialised ``torch.distributed`` module passed as `dist` (and `x`
+    replicated on the ranks) the four quadrants are computed on different GPUs
+    and exchanged with one all-gather (``_shard.sharded_normal_operator``); the
+    result is bit-identical to the single-GPU one."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        from ._shard import sharded_normal_operator
+
+        out = sharded_normal_operator(x, dist)
+    else:
+        out = cd.truncate_mean(cd.bdrt(cd.adrt(x)), 1.0)
     if ridge:
         out = out + ridge * x
     return out
 
 
 def iadrt_cg(b, /, *, ridge: float = 0.0, rtol: float = 1e-5, atol: float = 0.0, maxiter=None, x0=None,
-             return_info: bool = False):
+             return_info: bool = False, dist=None):
     """Inverse ADRT by conjugate gradients on the normal equations.
 
     ``b``: ADRT-shaped array ``(4, 2n-1, n)`` (NumPy or CUDA tensor, no batch
     dimension, like the reference recipe).  Stops when ``||r|| <= max(rtol*||A^T b||, atol)``
     (SciPy's ``cg`` criterion) or after ``maxiter`` iterations (default ``10 n^2``
     like SciPy); raises ``ValueError`` if it did not converge, as the recipe does.
+    `dist`: pass ``torch.distributed`` to shard every operator application over
+    the ranks by quadrant (`b` replicated; every rank returns the same image).
     """
     import torch
 
@@ -44,14 +56,14 @@ def iadrt_cg(b, /, *, ridge: float = 0.0, rtol: float = 1e-5, atol: float = 0.0,
     n = bt.shape[-1]
     rhs = cd.truncate_mean(cd.bdrt(bt), 1.0)
     x = torch.zeros_like(rhs) if x0 is None else (_to_device(x0) if isinstance(x0, np.ndarray) else x0).clone()
-    r = rhs - normal_operator(x, ridge=ridge) if x0 is not None else rhs.clone()
+    r = rhs - normal_operator(x, ridge=ridge, dist=dist) if x0 is not None else rhs.clone()
     p = r.clone()
     rs = torch.sum(r * r)
     tol = max(rtol * float(torch.linalg.vector_norm(rhs)), atol)
     maxiter = 10 * n * n if maxiter is None else int(maxiter)
     it, converged = 0, float(rs) ** 0.5 <= tol
     while not converged and it < maxiter:
-        ap = normal_operator(p, ridge=ridge)
+        ap = normal_operator(p, ridge=ridge, dist=dist)
         alpha = rs / torch.sum(p * ap)
         x += alpha * p
         r -= alpha * ap

@@ -77,6 +77,19 @@ size_t adrt_b200_bdrt_workspace_bytes(int64_t B, int64_t n, int dtype);
 int    adrt_b200_bdrt(const void *in, void *out, int64_t B, int64_t n, int dtype,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Plane subsets, for sharding ONE large image over several GPUs: the
+ * four quadrants of adrt are independent transforms of four orientations of the
+ * image (adrt_cdefs_adrt.hpp:124-175), and bdrt treats every (2n-1, n) plane
+ * independently.  adrt_quadrants: in (B,n,n) -> out (B,q_count,2n-1,n) holding
+ * quadrants q_first .. q_first+q_count-1;  bdrt_planes: in/out (planes,2n-1,n). */
+size_t adrt_b200_adrt_quadrants_workspace_bytes(int64_t B, int64_t n, int dtype, int q_count);
+int    adrt_b200_adrt_quadrants(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                                int q_first, int q_count, void *workspace, size_t workspace_bytes,
+                                void *stream);
+size_t adrt_b200_bdrt_planes_workspace_bytes(int64_t planes, int64_t n, int dtype);
+int    adrt_b200_bdrt_planes(const void *in, void *out, int64_t planes, int64_t n, int dtype,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 /* adrt.core.adrt_step / bdrt_step: adrt_cdefs_py.cpp:343-412, 550-619 ->
  * adrt_step (adrt_cdefs_adrt.hpp:215-258), bdrt_step (adrt_cdefs_bdrt.hpp:190-244).
  * 0 <= step < num_iters(n).  in/out (B,4,2n-1,n), must not alias. */

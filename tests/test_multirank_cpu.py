@@ -42,6 +42,60 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_quadrants(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from adrt_b200._shard import quadrant_owner_range, sharded_normal_operator, truncate_quadrant
+    from oracle import oracle as O
+
+    def oracle_fn(x, q_first, q_count):
+        # CPU stand-in for adrt_quadrants + bdrt_planes: full oracle transform, keep our quadrants
+        z = torch.from_numpy(O.bdrt(O.adrt(x.numpy())))
+        return [truncate_quadrant(z[..., q_first + i, :, :], q_first + i).contiguous() for i in range(q_count)]
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 16
+        x = torch.from_numpy(np.random.default_rng(3).standard_normal((n, n)))
+        got = sharded_normal_operator(x, dist, local_fn=oracle_fn).numpy()
+        y = O.bdrt(O.adrt(x.numpy()))
+        t = O.truncate(y)
+        want = (((t[0] + t[1]) + t[2]) + t[3]) / 4
+        q.put((rank, quadrant_owner_range(world, rank), got.tobytes() == want.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_quadrant_sharded_normal_operator():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_quadrants, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [(0, 2), (2, 2)]
+    assert all(r[2] for r in res), "sharded normal operator differs from the single-process one"
+
+
+def test_quadrant_owner_range():
+    from adrt_b200._shard import quadrant_owner_range
+
+    assert quadrant_owner_range(1, 0) == (0, 4)
+    assert [quadrant_owner_range(2, r) for r in range(2)] == [(0, 2), (2, 2)]
+    assert [quadrant_owner_range(4, r) for r in range(4)] == [(0, 1), (1, 1), (2, 1), (3, 1)]
+    assert [quadrant_owner_range(8, r)[1] for r in range(8)] == [1, 1, 1, 1, 0, 0, 0, 0]
+
+
 def test_shard_bounds():
     from adrt_b200._shard import shard_bounds
 

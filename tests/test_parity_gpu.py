@@ -266,6 +266,33 @@ def test_cg_recipe_matches_scipy_on_oracle():
         recipes.iadrt_cg(np.zeros((2, 4, 31, 16)))
 
 
+def test_quadrant_subsets_and_sharded_operator():
+    """Single-image sharding building blocks: any quadrant range of adrt equals the
+    slice of the full transform, bdrt of a plane subset equals the slice of bdrt, and
+    the quadrant-sharded normal operator (world of 1 here) equals the fused one."""
+    import torch
+
+    from adrt_b200 import _shard, recipes
+
+    for dt in (np.float32, np.float64):
+        x = make_image(21, (2, 128, 128), dt)
+        xt = torch.from_numpy(x).cuda()
+        full = adrt.adrt(xt)
+        back = adrt.bdrt(full)
+        for qf, qc in ((0, 4), (0, 1), (1, 1), (2, 2), (3, 1), (1, 3)):
+            sub = cd.adrt_quadrants(xt, qf, qc)
+            assert torch.equal(sub.view(torch.uint8), full[:, qf:qf + qc].contiguous().view(torch.uint8)), (qf, qc)
+            bsub = cd.bdrt_planes(sub)
+            assert torch.equal(bsub.view(torch.uint8), back[:, qf:qf + qc].contiguous().view(torch.uint8)), (qf, qc)
+        one = cd.adrt_quadrants(xt[0], 2, 1)
+        assert tuple(one.shape) == (1, 255, 128)
+        got = _shard.sharded_normal_operator(xt[0])
+        want = recipes.normal_operator(xt[0])
+        assert torch.equal(got.view(torch.uint8), want.view(torch.uint8))
+    with pytest.raises(ValueError, match="bad quadrant range"):
+        cd.adrt_quadrants(xt, 3, 2)
+
+
 def test_iadrt_roundtrip():
     # reference tests/test_iadrt.py:185-223
     for n in (16, 32):
