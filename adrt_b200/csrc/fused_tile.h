@@ -455,20 +455,67 @@ ADRT_HD void fwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
 // when M is odd).  Each step is two barrier-separated phases (compute, store).
 ADRT_HD constexpr int num_steps(int M) { return (M + 1) / 2; }
 
-template <typename T, int M, int STEP>
+// step starting at local stage t: radix-4 if two stages are left, else radix-2
+template <typename T, int M, int t>
 ADRT_HD void fwd_step_compute(const T *buf, int tid, T (&o)[NREG])
 {
-    constexpr int t = 2 * STEP;
     if constexpr (t + 2 <= M) fwd_radix4_compute<T, M, t>(buf, tid, o);
     else fwd_radix2_compute<T, M, t>(buf, tid, o);
 }
 
-template <typename T, int M, int STEP>
+template <typename T, int M, int t>
 ADRT_HD void fwd_step_store(T *buf, int tid, const T (&o)[NREG])
 {
-    constexpr int t = 2 * STEP;
     if constexpr (t + 2 <= M) fwd_radix4_store<T, M, t>(buf, tid, o);
     else fwd_radix2_store<T, M, t>(buf, tid, o);
+}
+
+// Loader that also performs local stage 0 (odd M on the workspace side): the two
+// input rows 2k, 2k+1 of a pair are read straight from global memory and the
+// tile receives   row 2k   = in_2k[x] + in_2k+1[x]      (even angle, shift 0)
+//                 row 2k+1 = in_2k[x] + in_2k+1[x - 1]   (odd angle, shift 1)
+// so the radix-2 step and its shared-memory round trip disappear.  Scalar,
+// coalesced accesses: the rows' different alignments do not matter here.
+template <typename T, int M, int LH>
+ADRT_HD void fwd_load_wrows_stage0(T *buf, const T *src_plane, const TileCtx &c, int tid)
+{
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int sup = c.n + c.a_g;
+    for (int k = warp; k < G / 2; k += NWARP) {
+        const int jA = 2 * k, jB = 2 * k + 1;
+        const T *rowA = src_plane + ((long long)(c.k0 * G + jA) * c.e + c.a_g) * c.in_pitch + fwd_row_skew(c.a_g, jA);
+        const T *rowB = src_plane + ((long long)(c.k0 * G + jB) * c.e + c.a_g) * c.in_pitch + fwd_row_skew(c.a_g, jB);
+        const int dA = c.d0 - LH - c.a_g * jA, dB = c.d0 - LH - c.a_g * jB;   // offsets of tile position 0
+        T *oe = buf + jA * P, *oo = buf + jB * P;
+        if (dB - 1 >= 0 && dA + XW <= sup) {   // dB < dA: the whole pair is inside [0, sup)
+            T a0[XW / 32], b0[XW / 32], b1[XW / 32];
+#pragma unroll
+            for (int i = 0; i < XW / 32; ++i) {
+                const int x = i * 32 + lane;
+                a0[i] = rowA[dA + x];
+                b0[i] = rowB[dB + x];
+                b1[i] = rowB[dB + x - 1];
+            }
+#pragma unroll
+            for (int i = 0; i < XW / 32; ++i) {
+                const int x = i * 32 + lane;
+                oe[x] = a0[i] + b0[i];
+                oo[x] = a0[i] + b1[i];
+            }
+        } else {
+#pragma unroll 2
+            for (int i = 0; i < XW / 32; ++i) {
+                const int x = i * 32 + lane;
+                const int da = dA + x, db = dB + x;
+                const T a0 = da < 0 ? T(-0.0) : (da < sup ? rowA[da] : T(0.0));
+                const T b0 = db < 0 ? T(-0.0) : (db < sup ? rowB[db] : T(0.0));
+                const T b1 = db - 1 < 0 ? T(-0.0) : (db - 1 < sup ? rowB[db - 1] : T(0.0));
+                oe[x] = a0 + b0;
+                oo[x] = a0 + b1;
+            }
+        }
+    }
 }
 
 // ---- stores -----------------------------------------------------------------------
@@ -838,26 +885,55 @@ ADRT_HD void bwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
     }
 }
 
-// Transposed steps run the forward schedule backwards: forward step i covers
-// local stages 2i (and 2i+1); transposed step i undoes forward step nsteps-1-i.
-ADRT_HD constexpr int bwd_step_t(int M, int step) { return 2 * (num_steps(M) - 1 - step); }
-// radix of the previous transposed step: 2 if that was the odd last stage
-ADRT_HD constexpr int bwd_step_rprev(int M, int step) { return step == 0 ? 0 : ((bwd_step_t(M, step) + 4 <= M) ? 4 : 2); }
-
-template <typename T, int M, bool kMask, int STEP>
+// Transposed step that produces the rows of local stage t (radix-4 if stage t+2
+// exists, else radix-2).  RPREV = radix of the step that produced its parent rows
+// (0: they were loaded).
+template <typename T, int M, bool kMask, int t, int RPREV>
 ADRT_HD void bwd_step_compute(const T *buf, int dt, int ag, int tid, T (&o)[NREG])
 {
-    constexpr int t = bwd_step_t(M, STEP);
-    if constexpr (t + 2 <= M) bwd_radix4_compute<T, M, kMask, t, bwd_step_rprev(M, STEP)>(buf, dt, ag, tid, o);
+    if constexpr (t + 2 <= M) bwd_radix4_compute<T, M, kMask, t, RPREV>(buf, dt, ag, tid, o);
     else bwd_radix2_compute<T, M, kMask, t>(buf, dt, ag, tid, o);
 }
 
-template <typename T, int M, int STEP>
+template <typename T, int M, int t, int RPREV>
 ADRT_HD void bwd_step_store(T *buf, int tid, const T (&o)[NREG])
 {
-    constexpr int t = bwd_step_t(M, STEP);
-    if constexpr (t + 2 <= M) bwd_radix4_store<T, M, t, bwd_step_rprev(M, STEP)>(buf, tid, o);
+    if constexpr (t + 2 <= M) bwd_radix4_store<T, M, t, RPREV>(buf, tid, o);
     else bwd_radix2_store<T, M, t>(buf, tid, o);
+}
+
+// Store that also performs the transposed local stage 0 (odd M on the workspace
+// side): output row j = 2k (+1) is  g0[x] + g1[x (+1)]  of the parent pair (rows 2k,
+// 2k+1 of the tile, angles 0 / 1), written to workspace row (k0*G + j)*e + a_g at
+// offset d0 + x - a_g*j.  The odd parent carries the skew (k & 3) of the radix-4
+// step that produced it (kPrevR4).  Scalar, coalesced accesses.
+template <typename T, int M, int TD, bool kMask, bool kPrevR4>
+ADRT_HD void bwd_store_wrows_stage0(const T *buf, T *dst_plane, const TileCtx &c, bool zero, int tid)
+{
+    constexpr int G = Geo<M>::G, NWARP = Geo<M>::NWARP, P = Pitch<T>::value;
+    constexpr int NS = (TD + 31) / 32;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < G; j += NWARP) {
+        const int k = j >> 1, odd = j & 1;
+        const T *g0 = buf + (2 * k) * P;
+        const T *g1 = buf + (2 * k + 1) * P + (kPrevR4 ? (k & 3) : 0) + odd;
+        const int lim_p = (c.D - c.d0) + c.a_g * (2 * k);
+        T *row = dst_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.out_pitch;
+        const int dbase = c.d0 - c.a_g * j;
+#pragma unroll 2
+        for (int i = 0; i < NS; ++i) {
+            const int xc = i * 32 + lane, d = dbase + xc;
+            if (xc < TD && d >= 0 && d < c.D) {
+                if (zero) {
+                    row[d] = T(0.0);   // tile beyond row D of the input: every surviving output is +0
+                } else {
+                    const T a = bmask<T, kMask>(g0[xc], xc, lim_p, false);
+                    const T b = bmask<T, kMask>(g1[xc], xc + odd, lim_p, true);
+                    row[d] = a + b;
+                }
+            }
+        }
+    }
 }
 
 // Output row j -> workspace row (k0*G + j)*e + a_g; tile position xc is offset
@@ -926,7 +1002,10 @@ enum TileMode { TILE_SKIP = 0, TILE_ZERO = 1, TILE_FULL = 2, TILE_FULL_MASKED = 
 template <typename T, int M, int LOADK, int STOREK>
 struct FwdProgram {
     static constexpr int G = Geo<M>::G;
-    static constexpr int kPhases = 2 + 2 * num_steps(M);
+    // odd M reading workspace rows: stage 0 is done by the loader, the rest is radix-4
+    static constexpr bool kFused0 = (M & 1) && LOADK == LOAD_WROWS;
+    static constexpr int NS = kFused0 ? (M - 1) / 2 : num_steps(M);
+    static constexpr int kPhases = 2 + 2 * NS;
     static constexpr int TD = TileTD<M, STOREK>::value;   // offsets produced per tile
     static constexpr int LH = XW - TD;                    // tile position of offset d0
 
@@ -960,11 +1039,13 @@ struct FwdProgram {
         (void)mode;
         if constexpr (PH == 0) {
             if (LOADK == LOAD_IMAGE) fwd_load_image<T, M, LH>(buf, src, c, tid);
+            else if (kFused0) fwd_load_wrows_stage0<T, M, LH>(buf, src, c, tid);
             else fwd_load_wrows<T, M, LH>(buf, src, c, tid);
-        } else if constexpr (PH <= 2 * num_steps(M)) {
+        } else if constexpr (PH <= 2 * NS) {
             constexpr int step = (PH - 1) >> 1;
-            if constexpr ((PH - 1) & 1) fwd_step_store<T, M, step>(buf, tid, regs);
-            else fwd_step_compute<T, M, step>(buf, tid, regs);
+            constexpr int t = kFused0 ? 1 + 2 * step : 2 * step;
+            if constexpr ((PH - 1) & 1) fwd_step_store<T, M, t>(buf, tid, regs);
+            else fwd_step_compute<T, M, t>(buf, tid, regs);
         } else {
             if (STOREK == STORE_QCOLS) store_qcols<T, M, TD>(buf, dst, c, LH, false, tid);
             else fwd_store_wrows<T, M, LH, TD>(buf, dst, c, false, tid);
@@ -975,8 +1056,14 @@ struct FwdProgram {
 template <typename T, int M, int LOADK, int STOREK>
 struct BwdProgram {
     static constexpr int G = Geo<M>::G;
-    static constexpr int kPhases = 2 + 2 * num_steps(M);
+    // odd M writing workspace rows: the transposed stage 0 is done by the store
+    static constexpr bool kFused0 = (M & 1) && STOREK == STORE_WROWS;
+    static constexpr int NS = kFused0 ? (M - 1) / 2 : num_steps(M);
+    static constexpr int kPhases = 2 + 2 * NS;
     static constexpr int TD = TileTD<M, STOREK>::value;
+    // stage produced by step i, and the radix of the step before it
+    static constexpr int step_t(int i) { return kFused0 ? (M - 2) - 2 * i : 2 * (NS - 1 - i); }
+    static constexpr int step_rprev(int i) { return i == 0 ? 0 : ((step_t(i - 1) + 2 <= M) ? 4 : 2); }
 
     ADRT_HD static int classify(const TileCtx &c)
     {
@@ -988,7 +1075,9 @@ struct BwdProgram {
 
     ADRT_HD static void zero_tile(T *buf, T *dst, const TileCtx &c, int tid)
     {
-        bwd_store_wrows<T, M, TD>(buf, dst, c, true, tid);
+        // same row coverage as the store of a full tile
+        if (kFused0) bwd_store_wrows_stage0<T, M, TD, false, (NS > 0)>(buf, dst, c, true, tid);
+        else bwd_store_wrows<T, M, TD>(buf, dst, c, true, tid);
     }
 
     template <int PH>
@@ -997,14 +1086,17 @@ struct BwdProgram {
         if constexpr (PH == 0) {
             if (LOADK == LOAD_QCOLS) bwd_load_qcols<T, M>(buf, src, c, tid);
             else bwd_load_wrows<T, M>(buf, src, c, tid);
-        } else if constexpr (PH <= 2 * num_steps(M)) {
+        } else if constexpr (PH <= 2 * NS) {
             constexpr int step = (PH - 1) >> 1;
-            if constexpr ((PH - 1) & 1) bwd_step_store<T, M, step>(buf, tid, regs);
-            else if (mode == TILE_FULL_MASKED) bwd_step_compute<T, M, true, step>(buf, c.D - c.d0, c.a_g, tid, regs);
-            else bwd_step_compute<T, M, false, step>(buf, c.D - c.d0, c.a_g, tid, regs);
+            constexpr int t = step_t(step), rp = step_rprev(step);
+            if constexpr ((PH - 1) & 1) bwd_step_store<T, M, t, rp>(buf, tid, regs);
+            else if (mode == TILE_FULL_MASKED) bwd_step_compute<T, M, true, t, rp>(buf, c.D - c.d0, c.a_g, tid, regs);
+            else bwd_step_compute<T, M, false, t, rp>(buf, c.D - c.d0, c.a_g, tid, regs);
         } else {
             if (STOREK == STORE_QCOLS) store_qcols<T, M, TD>(buf, dst, c, 0, false, tid);
-            else bwd_store_wrows<T, M, TD>(buf, dst, c, false, tid);
+            else if (!kFused0) bwd_store_wrows<T, M, TD>(buf, dst, c, false, tid);
+            else if (mode == TILE_FULL_MASKED) bwd_store_wrows_stage0<T, M, TD, true, (NS > 0)>(buf, dst, c, false, tid);
+            else bwd_store_wrows_stage0<T, M, TD, false, (NS > 0)>(buf, dst, c, false, tid);
         }
     }
 };
