@@ -488,20 +488,22 @@ ADRT_HD void fwd_load_wrows_stage0(T *buf, const T *src_plane, const TileCtx &c,
         const T *rowB = src_plane + ((long long)(c.k0 * G + jB) * c.e + c.a_g) * c.in_pitch + fwd_row_skew(c.a_g, jB);
         const int dA = c.d0 - LH - c.a_g * jA, dB = c.d0 - LH - c.a_g * jB;   // offsets of tile position 0
         T *oe = buf + jA * P, *oo = buf + jB * P;
-        if (dB - 1 >= 0 && dA + XW <= sup) {   // dB < dA: the whole pair is inside [0, sup)
-            T a0[XW / 32], b0[XW / 32], b1[XW / 32];
+        if (dB >= 4 && dA + XW <= sup) {   // dB < dA: the whole pair (and x - 4) is inside [0, sup)
+            // rowX + dX is 16-byte aligned (storage skew): vector loads, 4 offsets per lane
 #pragma unroll
-            for (int i = 0; i < XW / 32; ++i) {
-                const int x = i * 32 + lane;
-                a0[i] = rowA[dA + x];
-                b0[i] = rowB[dB + x];
-                b1[i] = rowB[dB + x - 1];
-            }
+            for (int cc = 0; cc < XW / (32 * V); ++cc) {
+                const int x = (cc * 32 + lane) * V;
+                T a0[V], b[V + 1];
+                load_window<T, V, 0>(rowA + dA + x, a0);
+                load_window<T, V + 1, V - 1>(rowB + dB + x - V, b);   // offsets x-1 .. x+3
+                T ve[V], vo[V];
 #pragma unroll
-            for (int i = 0; i < XW / 32; ++i) {
-                const int x = i * 32 + lane;
-                oe[x] = a0[i] + b0[i];
-                oo[x] = a0[i] + b1[i];
+                for (int i = 0; i < V; ++i) {
+                    ve[i] = a0[i] + b[i + 1];
+                    vo[i] = a0[i] + b[i];
+                }
+                store_chunk<T>(oe + x, ve);
+                store_chunk<T>(oo + x, vo);
             }
         } else {
 #pragma unroll 2
@@ -920,6 +922,15 @@ ADRT_HD void bwd_store_wrows_stage0(const T *buf, T *dst_plane, const TileCtx &c
         const int lim_p = (c.D - c.d0) + c.a_g * (2 * k);
         T *row = dst_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.out_pitch;
         const int dbase = c.d0 - c.a_g * j;
+        if (!kMask && !zero && dbase >= 0 && dbase + TD <= c.D) {
+            // whole row segment in range: immediate offsets, 2 LDS + 1 add + 1 STG per element
+            const T *p0 = g0 + lane, *p1 = g1 + lane;
+            T *r = row + dbase + lane;
+#pragma unroll
+            for (int i = 0; i < TD / 32; ++i) r[i * 32] = p0[i * 32] + p1[i * 32];
+            if ((TD % 32) != 0 && lane < TD % 32) r[(TD / 32) * 32] = p0[(TD / 32) * 32] + p1[(TD / 32) * 32];
+            continue;
+        }
 #pragma unroll 2
         for (int i = 0; i < NS; ++i) {
             const int xc = i * 32 + lane, d = dbase + xc;
