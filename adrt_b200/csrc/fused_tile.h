@@ -80,7 +80,7 @@ template <int M> struct Geo {
     // offsets consumed by M stages, rounded so that chunk boundaries stay aligned
     static constexpr int HALO = G < 4 ? 4 : G;
     static constexpr int NT = G >= 64 ? 512 : 256;   // threads per CTA: one warp per radix-4 group
-    static constexpr int MIN_CTAS = G >= 64 ? 2 : 5; // launch-bounds target (caps registers at 64)
+    static constexpr int MIN_CTAS = G >= 64 ? 2 : (G == 32 ? 5 : 3); // launch-bounds target (caps registers at 64)
     static constexpr int NWARP = NT / 32;
 };
 
