@@ -716,11 +716,13 @@ ADRT_HD T bmask(T v, int pos, int lim, bool odd)
 // `dt` = D - d0 and `ag` = global base angle give each row's logical end:
 //   parent rows (block k0 at stage t+2): dt + ag*k0*4e;  node k=1: + ag*2e.
 template <typename T, bool kMask, int JP>
-ADRT_HD void bwd_radix4_chunk(const T *ip, int a, int x, int jp, int lim_p, int lim_1, T *o)
+ADRT_HD void bwd_radix4_chunk(const T *ip, long long P, int a, int x, int jp, int lim_p, int lim_1, T *o)
 {
+    // P = distance between the four parent rows (tile pitch, or the workspace pitch
+    // when the parents are read straight from global memory)
     constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
     (void)CHUNKS;
-    constexpr int P = Pitch<T>::value, L = VecOf<T>::L;
+    constexpr int L = VecOf<T>::L;
     constexpr int Q1 = (JP * 1) % L, Q2 = (JP * 2) % L, Q3 = (JP * 3) % L;
     const int s0 = jp * 4 * a;  // skew of parent 0; parent p adds jp*p
     T g0[V], g1[V + 1], g2[V + 2], g3[V + 3];
@@ -781,7 +783,7 @@ ADRT_HD void bwd_radix4_group(const T *buf, int e, int k0, int a, int lane, int 
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int x = (lane + 32 * c) * V;
-        if (bwd_chunk_ok<T>(x, jp, a)) bwd_radix4_chunk<T, kMask, JP>(ip, a, x, jp, lim_p, lim_1, &o[c * 4 * V]);
+        if (bwd_chunk_ok<T>(x, jp, a)) bwd_radix4_chunk<T, kMask, JP>(ip, P, a, x, jp, lim_p, lim_1, &o[c * 4 * V]);
     }
 }
 
@@ -802,6 +804,26 @@ ADRT_HD void bwd_radix4_compute(const T *buf, int dt, int ag, int tid, T (&o)[NR
     case 1: bwd_radix4_group<T, kMask, 1>(buf, e, k0, a, lane, jp, dt, ag, o); break;
     case 2: bwd_radix4_group<T, kMask, 2>(buf, e, k0, a, lane, jp, dt, ag, o); break;
     default: bwd_radix4_group<T, kMask, 3>(buf, e, k0, a, lane, jp, dt, ag, o); break;
+    }
+}
+
+// First transposed step of an interior tile whose parents are workspace rows: the
+// operand windows are read straight from global memory (aligned: d0 and the pitch
+// are multiples of 4), so the tile is never staged in shared memory before step 0.
+template <typename T, int M, int t>
+ADRT_HD void bwd_radix4_compute_global(const T *src_plane, const TileCtx &c, int tid, T (&o)[NREG])
+{
+    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);
+    constexpr int G = Geo<M>::G;
+    constexpr int e = 1 << t;
+    const int gi = tid >> 5, lane = tid & 31;
+    if (gi >= G / 4) return;
+    const int k0 = gi >> t, a = gi & (e - 1);
+    const T *ip = src_plane + ((long long)c.g * G + k0 * 4 * e + 4 * a) * c.in_pitch + c.d0;
+#pragma unroll
+    for (int cc = 0; cc < CHUNKS; ++cc) {
+        const int x = (lane + 32 * cc) * V;
+        if (bwd_chunk_ok<T>(x, 0, a)) bwd_radix4_chunk<T, false, 0>(ip, c.in_pitch, a, x, 0, 0, 0, &o[cc * 4 * V]);
     }
 }
 
@@ -1075,6 +1097,9 @@ struct BwdProgram {
     // stage produced by step i, and the radix of the step before it
     static constexpr int step_t(int i) { return kFused0 ? (M - 2) - 2 * i : 2 * (NS - 1 - i); }
     static constexpr int step_rprev(int i) { return i == 0 ? 0 : ((step_t(i - 1) + 2 <= M) ? 4 : 2); }
+    // interior tiles of passes that read workspace rows and start with a radix-4 step
+    // skip the staging copy: step 0 reads its windows from global memory
+    static constexpr bool kDirect0 = LOADK == LOAD_WROWS && NS > 0 && (step_t(0) + 2 <= M);
 
     ADRT_HD static int classify(const TileCtx &c)
     {
@@ -1096,12 +1121,13 @@ struct BwdProgram {
     {
         if constexpr (PH == 0) {
             if (LOADK == LOAD_QCOLS) bwd_load_qcols<T, M>(buf, src, c, tid);
-            else bwd_load_wrows<T, M>(buf, src, c, tid);
+            else if (!(kDirect0 && mode == TILE_FULL)) bwd_load_wrows<T, M>(buf, src, c, tid);
         } else if constexpr (PH <= 2 * NS) {
             constexpr int step = (PH - 1) >> 1;
             constexpr int t = step_t(step), rp = step_rprev(step);
             if constexpr ((PH - 1) & 1) bwd_step_store<T, M, t, rp>(buf, tid, regs);
             else if (mode == TILE_FULL_MASKED) bwd_step_compute<T, M, true, t, rp>(buf, c.D - c.d0, c.a_g, tid, regs);
+            else if constexpr (kDirect0 && step == 0) bwd_radix4_compute_global<T, M, t>(src, c, tid, regs);
             else bwd_step_compute<T, M, false, t, rp>(buf, c.D - c.d0, c.a_g, tid, regs);
         } else {
             if (STOREK == STORE_QCOLS) store_qcols<T, M, TD>(buf, dst, c, 0, false, tid);
