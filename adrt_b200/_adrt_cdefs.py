@@ -431,9 +431,12 @@ def adrt_quadrants(a, q_first, q_count, /, *, out=None):
     return ret
 
 
-def bdrt_planes(a, /, *, out=None):
+def bdrt_planes(a, /, *, out=None, rows=None):
     """Back-projection of independent ``(2n-1, n)`` planes: ``(..., 2n-1, n)`` -> same
-    shape (any leading dims, e.g. a subset of quadrants).  CUDA tensors only."""
+    shape (any leading dims, e.g. a subset of quadrants).  CUDA tensors only.
+
+    ``rows``: compute only offsets ``d < rows`` of every plane (the rest of the
+    result is unspecified) -- ``rows=n`` is all that ``truncate`` reads."""
     if not (_is_torch_tensor(a) and a.is_cuda):
         raise TypeError("bdrt_planes is a device-only helper (CUDA tensors)")
     a = a.contiguous()
@@ -455,7 +458,23 @@ def bdrt_planes(a, /, *, out=None):
     with torch.cuda.device(a.device):
         nbytes = lib.adrt_b200_bdrt_planes_workspace_bytes(planes, n, code)
         ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=a.device)
-        rc = lib.adrt_b200_bdrt_planes(a.data_ptr(), ret.data_ptr(), planes, n, code, ws.data_ptr(), int(nbytes),
-                                       torch.cuda.current_stream().cuda_stream)
+        if rows is None:
+            rc = lib.adrt_b200_bdrt_planes(a.data_ptr(), ret.data_ptr(), planes, n, code, ws.data_ptr(), int(nbytes),
+                                           torch.cuda.current_stream().cuda_stream)
+        else:
+            rc = lib.adrt_b200_bdrt_rows(a.data_ptr(), ret.data_ptr(), planes, n, int(rows), code, ws.data_ptr(),
+                                         int(nbytes), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "bdrt_planes")
     return ret
+
+
+def bdrt_truncate_mean(a, divisor, /, *, out=None):
+    """``truncate_mean(bdrt(a), divisor)`` for CUDA tensors ``(B?, 4, 2n-1, n)``: the
+    back-projection computes only the offsets ``d < n`` that ``truncate`` keeps
+    (utils.py:231-242), bit-identical to the unfused composition."""
+    if not (_is_torch_tensor(a) and a.is_cuda):
+        raise TypeError("bdrt_truncate_mean is a device-only helper (CUDA tensors)")
+    shape = _array_shape(_extract_array(a), 3, 4)
+    if not _is_adrt_output_shape(shape):
+        raise ValueError("array must have a valid ADRT output shape")
+    return truncate_mean(bdrt_planes(a, rows=shape[-1]), divisor, out=out)

@@ -84,7 +84,7 @@ def _local_quadrant_backprojections(x, q_first, q_count):
     from . import _adrt_cdefs as cd
 
     y = cd.adrt_quadrants(x, q_first, q_count)
-    z = cd.bdrt_planes(y)
+    z = cd.bdrt_planes(y, rows=x.shape[-1])
     return [truncate_quadrant(z[..., i, :, :], q_first + i).contiguous() for i in range(q_count)]
 
 

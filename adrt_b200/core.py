@@ -143,7 +143,7 @@ def _fmg_step_device(a):
         m *= 2
         ret = cd.press_fmg_prolongation(ret)
         resid = cd.sub(cd.adrt(ret), stack.pop())
-        grad = cd.truncate_mean(cd.bdrt(resid), m - 1)
+        grad = cd.bdrt_truncate_mean(resid, m - 1)
         ret = cd.sub(ret, cd.press_fmg_highpass(grad), out=ret)
     return ret
 

@@ -138,7 +138,7 @@ int bdrt_impl(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_bytes,
     }
     if (g_mode.load() == 0) {
         bool handled = false;
-        int rc = fused_bdrt<T>(in, out, B, n, 4, ws, ws_bytes / sizeof(T), s, &handled);
+        int rc = fused_bdrt<T>(in, out, B, n, 4, -1, ws, ws_bytes / sizeof(T), s, &handled);
         if (rc != ADRT_B200_OK || handled) return rc;
     }
     return bdrt_by_steps<T>(in, out, B, n, ws, s);
@@ -262,7 +262,7 @@ int adrt_quadrants_impl(const T *in, T *out, int64_t B, int64_t n, int q_first, 
 }
 
 template <typename T>
-int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, T *ws, size_t ws_bytes, cudaStream_t s)
+int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, int64_t rows, T *ws, size_t ws_bytes, cudaStream_t s)
 {
     if (n == 1) {
         ADRT_CUDA_CHECK(cudaMemcpyAsync(out, in, sizeof(T) * planes, cudaMemcpyDeviceToDevice, s));
@@ -274,7 +274,7 @@ int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, T *ws, size
         return ADRT_B200_EWORKSPACE;
     }
     bool handled = false;
-    return fused_bdrt<T>(in, out, planes, n, 1, ws, ws_bytes / sizeof(T), s, &handled);
+    return fused_bdrt<T>(in, out, planes, n, 1, rows, ws, ws_bytes / sizeof(T), s, &handled);
 }
 
 #define DISPATCH(dtype, CALL_F32, CALL_F64) ((dtype) == ADRT_B200_F64 ? (CALL_F64) : (CALL_F32))
@@ -354,8 +354,19 @@ int adrt_b200_bdrt_planes(const void *in, void *out, int64_t planes, int64_t n, 
     int rc = check_image(in, out, planes, n, dtype);
     if (rc) return rc;
     return DISPATCH(dtype,
-                    bdrt_planes_impl<float>((const float *)in, (float *)out, planes, n, (float *)ws, ws_bytes, as_stream(stream)),
-                    bdrt_planes_impl<double>((const double *)in, (double *)out, planes, n, (double *)ws, ws_bytes, as_stream(stream)));
+                    bdrt_planes_impl<float>((const float *)in, (float *)out, planes, n, -1, (float *)ws, ws_bytes, as_stream(stream)),
+                    bdrt_planes_impl<double>((const double *)in, (double *)out, planes, n, -1, (double *)ws, ws_bytes, as_stream(stream)));
+}
+
+int adrt_b200_bdrt_rows(const void *in, void *out, int64_t planes, int64_t n, int64_t rows, int dtype, void *ws,
+                        size_t ws_bytes, void *stream)
+{
+    int rc = check_image(in, out, planes, n, dtype);
+    if (rc) return rc;
+    ADRT_REQUIRE(rows >= 1 && rows <= 2 * n - 1, "rows %lld out of range", (long long)rows);
+    return DISPATCH(dtype,
+                    bdrt_planes_impl<float>((const float *)in, (float *)out, planes, n, rows, (float *)ws, ws_bytes, as_stream(stream)),
+                    bdrt_planes_impl<double>((const double *)in, (double *)out, planes, n, rows, (double *)ws, ws_bytes, as_stream(stream)));
 }
 
 int adrt_b200_adrt_step(const void *in, void *out, int64_t B, int64_t n, int step, int dtype, void *stream)

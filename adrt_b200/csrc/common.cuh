@@ -75,6 +75,6 @@ template <typename T> int launch_binary(const T *a, const T *b, T *out, int64_t 
 template <typename T> size_t fused_adrt_workspace_elems(int64_t B, int64_t n, int q_count);
 template <typename T> size_t fused_bdrt_workspace_elems(int64_t B, int64_t n, int q_count);
 template <typename T> int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
-template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
+template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
 
 }  // namespace adrt_b200

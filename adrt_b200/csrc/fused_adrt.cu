@@ -14,7 +14,7 @@ namespace adrt_b200 {
 namespace {
 
 struct PassArgs {
-    int n, D, e, loge, next_g;
+    int n, D, e, loge, next_g, d_need;
     long long in_pitch, out_pitch;
     long long src_plane_stride, dst_plane_stride;  // elements between consecutive planes
     int planes;
@@ -52,6 +52,7 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
     c.a_g = c.g & (a.e - 1);
     c.d0 = blockIdx.x * Prog::TD;
     c.next_g = a.next_g;
+    c.d_need = a.d_need;
     c.in_pitch = a.in_pitch;
     c.out_pitch = a.out_pitch;
     c.q = 0;
@@ -155,7 +156,7 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
         for (int i = 0; i < pl.npass; ++i) {
             const plan::Pass &p = pl.pass[i];
             PassArgs a;
-            a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g;
+            a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g; a.d_need = p.d_need;
             a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
             a.planes = nb * q_count;
             a.q_first = q_first; a.q_count = q_count;
@@ -212,12 +213,14 @@ int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_cou
 }
 
 template <typename T>
-int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, T *ws, size_t ws_elems, cudaStream_t s,
-               bool *handled)
+int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems,
+               cudaStream_t s, bool *handled)
 {
+    // rows < 2n-1: only offsets d < rows of every output plane are computed, the rest of
+    // `out` is left as it was
     plan::Plan pl;
     *handled = false;
-    if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl)) return ADRT_B200_OK;
+    if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl, rows)) return ADRT_B200_OK;
     *handled = true;
     return run_plan<T, false>(pl, in, out, B, 0, q_count, ws, ws_elems, s);
 }
@@ -226,7 +229,7 @@ int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, T *ws, si
     template size_t fused_adrt_workspace_elems<T>(int64_t, int64_t, int);   \
     template size_t fused_bdrt_workspace_elems<T>(int64_t, int64_t, int);   \
     template int fused_adrt<T>(const T *, T *, int64_t, int64_t, int, int, T *, size_t, cudaStream_t, bool *); \
-    template int fused_bdrt<T>(const T *, T *, int64_t, int64_t, int, T *, size_t, cudaStream_t, bool *);
+    template int fused_bdrt<T>(const T *, T *, int64_t, int64_t, int, int64_t, T *, size_t, cudaStream_t, bool *);
 INSTANTIATE(float)
 INSTANTIATE(double)
 

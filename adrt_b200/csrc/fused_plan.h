@@ -26,6 +26,7 @@ struct Pass {
     int src_buf, dst_buf;           // -1 = caller's input / output, else workspace slot 0/1
     int grid_x, grid_y;             // d-tiles, groups
     int next_g;                     // forward: group size of the pass reading this pass's workspace (0: none)
+    int d_need;                     // transposed: output offsets >= d_need are not needed (tiles skipped)
 };
 
 struct Plan {
@@ -121,6 +122,7 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
         const int G = 1 << p.M;
         const int TD = tile_td(p.M, p.store);
         p.next_g = last ? 0 : (1 << ms[i + 1]);
+        p.d_need = pl->D;
         const long long extent = last ? pl->D : p.out_pitch;  // offsets that must be written
         p.grid_x = (int)((extent + TD - 1) / TD);
         p.grid_y = n / G;
@@ -134,7 +136,9 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
 }
 
 // Transposed plan: forward pass i is undone by transposed pass npass-1-i.
-inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl)
+// `rows` < D asks only for output offsets d < rows of the final result (what
+// utils.truncate keeps): every pass then skips the tiles that cannot reach them.
+inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_t rows = -1)
 {
     const int n = (int)n64;
     const int K = ilog2(n64);
@@ -157,16 +161,25 @@ inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl)
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        const int TD = tile_td(p.M, p.store);
         p.next_g = 0;
-        const long long e = 1LL << s;
-        const long long extent = pl->D + (e - 1) * (G - 1);  // tile coordinates that hold outputs
-        p.grid_x = (int)((extent + TD - 1) / TD);
         p.grid_y = n / G;
         if (!last) {
             const size_t need = (size_t)n * (size_t)round4(pl->D);
             if (need > pl->ws_slot_elems[p.dst_buf]) pl->ws_slot_elems[p.dst_buf] = need;
         }
+    }
+    // Offsets each pass must produce: an output at offset d of a pass with block height e
+    // and G rows per group reads inputs at offsets < d + (e-1)*(G-1) + G (SURVEY 8a row a5');
+    // +8 covers the 16-byte chunking of the workspace rows.
+    long long need = (rows > 0 && rows < pl->D) ? rows : pl->D;
+    for (int i = pl->npass - 1; i >= 0; --i) {
+        Pass &p = pl->pass[i];
+        p.d_need = (int)(need < pl->D ? need : pl->D);
+        const long long G = 1LL << p.M, e = 1LL << p.s;
+        need = p.d_need + (e - 1) * (G - 1) + G + 8;
+        const int TD = tile_td(p.M, p.store);
+        const long long extent = p.d_need + (e - 1) * (G - 1);  // tile coordinates that hold wanted outputs
+        p.grid_x = (int)((extent + TD - 1) / TD);
     }
     return true;
 }

@@ -94,6 +94,7 @@ struct TileCtx {
     int d0;            // forward: first valid output offset; transposed: first input offset
     long long in_pitch, out_pitch;   // elements per row of the R-layout workspaces (multiples of 4)
     int next_g;        // forward: group size (rows) of the pass that will read the workspace, 0 if none
+    int d_need;        // transposed: only output offsets < d_need are wanted (D: all of them)
 };
 
 // Valid offsets a tile produces.  Passes that store workspace rows give up 4
@@ -1103,7 +1104,8 @@ struct BwdProgram {
 
     ADRT_HD static int classify(const TileCtx &c)
     {
-        if (c.d0 >= c.D + c.a_g * (G - 1)) return TILE_SKIP;   // no output row reaches this far
+        // no wanted output row reaches this far (output row j sits at tile offset d + a_g*j)
+        if (c.d0 >= c.d_need + c.a_g * (G - 1)) return TILE_SKIP;
         if (c.d0 >= c.D) return STOREK == STORE_QCOLS ? TILE_SKIP : TILE_ZERO;
         if (c.d0 + XW + 8 > c.D) return TILE_FULL_MASKED;
         return TILE_FULL;

@@ -5,7 +5,8 @@ The reference ships these only as documentation recipes
 ``iadrt_cg``, docs/examples.tomography.md:63-70 ridge variant): a conjugate
 gradient solve of ``A^T A x = A^T b`` with ``A = adrt`` and
 ``A^T = mean_q(truncate(bdrt(.)))``.  Here every CG iteration stays on the GPU:
-one ``adrt`` + one ``bdrt`` (fused CUDA passes) + the ``truncate_mean`` kernel;
+one ``adrt`` + one ``bdrt`` restricted to the offsets ``truncate`` keeps (fused CUDA
+passes, ``adrt_b200_bdrt_rows``) + the ``truncate_mean`` kernel;
 the vector updates are elementwise torch ops on device tensors.
 """
 from __future__ import annotations
@@ -29,7 +30,7 @@ def normal_operator(x, /, *, ridge: float = 0.0, dist=None):
 
         out = sharded_normal_operator(x, dist)
     else:
-        out = cd.truncate_mean(cd.bdrt(cd.adrt(x)), 1.0)
+        out = cd.bdrt_truncate_mean(cd.adrt(x), 1.0)
     if ridge:
         out = out + ridge * x
     return out
@@ -54,7 +55,7 @@ def iadrt_cg(b, /, *, ridge: float = 0.0, rtol: float = 1e-5, atol: float = 0.0,
     as_numpy = isinstance(b, np.ndarray)
     bt = _to_device(b) if as_numpy else b
     n = bt.shape[-1]
-    rhs = cd.truncate_mean(cd.bdrt(bt), 1.0)
+    rhs = cd.bdrt_truncate_mean(bt, 1.0)
     x = torch.zeros_like(rhs) if x0 is None else (_to_device(x0) if isinstance(x0, np.ndarray) else x0).clone()
     r = rhs - normal_operator(x, ridge=ridge, dist=dist) if x0 is not None else rhs.clone()
     p = r.clone()

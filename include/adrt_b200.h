@@ -89,6 +89,13 @@ int    adrt_b200_adrt_quadrants(const void *in, void *out, int64_t B, int64_t n,
 size_t adrt_b200_bdrt_planes_workspace_bytes(int64_t planes, int64_t n, int dtype);
 int    adrt_b200_bdrt_planes(const void *in, void *out, int64_t planes, int64_t n, int dtype,
                              void *workspace, size_t workspace_bytes, void *stream);
+/* bdrt whose caller keeps only offsets d < rows of every plane -- utils.truncate keeps
+ * d < n (utils.py:231-242), which is all that the normal operator truncate(bdrt(adrt(x)))
+ * of the CG recipe (docs/examples.cginverse.md:45-52) and iadrt_fmg_step (core.py:318-331)
+ * ever read.  Rows d < rows of `out` are bit-identical to adrt_b200_bdrt_planes; the other
+ * rows of `out` are unspecified.  Workspace: adrt_b200_bdrt_planes_workspace_bytes. */
+int    adrt_b200_bdrt_rows(const void *in, void *out, int64_t planes, int64_t n, int64_t rows,
+                           int dtype, void *workspace, size_t workspace_bytes, void *stream);
 
 /* adrt.core.adrt_step / bdrt_step: adrt_cdefs_py.cpp:343-412, 550-619 ->
  * adrt_step (adrt_cdefs_adrt.hpp:215-258), bdrt_step (adrt_cdefs_bdrt.hpp:190-244).

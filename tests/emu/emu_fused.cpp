@@ -37,6 +37,7 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
                 c.n = n; c.D = D; c.e = e; c.g = by; c.k0 = by / e; c.a_g = by % e;
                 c.d0 = bx * Prog::TD;
                 c.next_g = p.next_g;
+                c.d_need = p.d_need;
                 c.in_pitch = p.in_pitch; c.out_pitch = p.out_pitch;
                 c.q = 0;
                 const int mode = Prog::classify(c);
@@ -76,10 +77,10 @@ void run_kinds(const plan::Pass &p, const T *src, T *dst, int n, int D, int plan
 }
 
 template <typename T, bool kForward>
-int run(const T *in, T *out, int64_t B, int64_t n64)
+int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1)
 {
     plan::Plan pl;
-    const bool ok = kForward ? plan::make_forward_plan(n64, sizeof(T), &pl) : plan::make_transposed_plan(n64, sizeof(T), &pl);
+    const bool ok = kForward ? plan::make_forward_plan(n64, sizeof(T), &pl) : plan::make_transposed_plan(n64, sizeof(T), &pl, rows);
     if (!ok) return 1;
     const int n = pl.n, D = pl.D, planes = (int)B * 4;
     // workspaces start as NaN so that any read of a never-written element shows up
@@ -115,4 +116,7 @@ int emu_adrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run
 int emu_adrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run<double, true>(in, out, B, n); }
 int emu_bdrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, false>(in, out, B, n); }
 int emu_bdrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run<double, false>(in, out, B, n); }
+// only offsets d < rows of every output plane are produced
+int emu_bdrt_rows_f32(const float *in, float *out, int64_t B, int64_t n, int64_t rows) { return run<float, false>(in, out, B, n, rows); }
+int emu_bdrt_rows_f64(const double *in, double *out, int64_t B, int64_t n, int64_t rows) { return run<double, false>(in, out, B, n, rows); }
 }

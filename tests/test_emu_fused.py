@@ -105,3 +105,27 @@ def test_skewed_rows_near_tile_boundary(emu):
 def test_medium_default(emu):
     # K = 9: two passes (5, 4); several d-tiles per group, masked boundary tiles
     _check(emu, 512, 1, np.float32)
+
+
+@pytest.mark.parametrize("n,rows,split", [
+    (64, 64, None), (128, 128, None), (256, 256, None), (256, 256, "3,5"), (256, 100, "5,3"),
+    (512, 512, None), (512, 512, "3,3,3"), (512, 1, None), (1024, 1024, None),
+])
+def test_bdrt_rows(emu, n, rows, split):
+    # row-limited back-projection (adrt_b200_bdrt_rows): offsets d < rows must be
+    # bit-identical to the full transform although whole tiles of every pass are skipped
+    os.environ.pop("ADRT_B200_SPLIT_BDRT", None)
+    if split:
+        os.environ["ADRT_B200_SPLIT_BDRT"] = split
+    try:
+        s = make_sino(17 + n, (1, 4, 2 * n - 1, n), np.float32)
+        out = np.full(s.shape, np.nan, dtype=s.dtype)
+        rc = emu.emu_bdrt_rows_f32(ctypes.c_void_p(s.ctypes.data), ctypes.c_void_p(out.ctypes.data),
+                                   ctypes.c_int64(1), ctypes.c_int64(n), ctypes.c_int64(rows))
+        assert rc == 0
+        want = O.bdrt(s)
+        assert bytes_equal(out[:, :, :rows], want[:, :, :rows]), first_diff(out[:, :, :rows], want[:, :, :rows])
+        if rows <= n // 2:
+            assert np.isnan(out[:, :, -1]).all()   # the far rows were really skipped
+    finally:
+        os.environ.pop("ADRT_B200_SPLIT_BDRT", None)

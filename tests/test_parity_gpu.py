@@ -293,6 +293,31 @@ def test_quadrant_subsets_and_sharded_operator():
         cd.adrt_quadrants(xt, 3, 2)
 
 
+@pytest.mark.parametrize("dn", list(DTYPES))
+@pytest.mark.parametrize("n,B", [(2, 3), (16, 2), (64, 2), (256, 2), (1024, 1), (2048, 2), (8192, 1)])
+def test_bdrt_rows_and_truncate_mean(dn, n, B):
+    """adrt_b200_bdrt_rows: offsets d < rows are bit-identical to the full bdrt, and the
+    fused normal-operator tail equals truncate_mean(bdrt(.)) (utils.py:231-242,
+    core.py:329)."""
+    import torch
+
+    dt = DTYPES[dn]
+    s = torch.from_numpy(make_sino(31 + n, (B, 4, 2 * n - 1, n), dt)).cuda()
+    full = adrt.bdrt(s)
+    for rows in sorted({1, n // 2 + 1, n, 2 * n - 1}):
+        part = cd.bdrt_planes(s, rows=rows)
+        assert torch.equal(part[:, :, :rows].contiguous().view(torch.uint8),
+                           full[:, :, :rows].contiguous().view(torch.uint8)), rows
+    got = cd.bdrt_truncate_mean(s, n - 1 if n > 1 else 1)
+    want = cd.truncate_mean(full, n - 1 if n > 1 else 1)
+    assert torch.equal(got.view(torch.uint8), want.view(torch.uint8))
+    if n <= 1024:
+        ref = np.mean(O.truncate(O.bdrt(s.cpu().numpy())) / dt(n - 1 if n > 1 else 1), axis=-3)
+        _eq(got.cpu().numpy(), ref.astype(dt), "bdrt_truncate_mean vs oracle")
+    with pytest.raises(_lib.ADRTB200Error, match="rows"):
+        cd.bdrt_planes(s, rows=2 * n)
+
+
 def test_iadrt_roundtrip():
     # reference tests/test_iadrt.py:185-223
     for n in (16, 32):
