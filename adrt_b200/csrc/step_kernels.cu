@@ -178,53 +178,86 @@ iadrt_stage_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes
 }
 
 // ---- Press FMG operators: adrt_cdefs_fmg.hpp ----------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
+// Grids: x over (vectors of) columns, y over rows, z over planes (y and z looped when
+// they exceed the grid limits), so no thread ever divides.
+constexpr int kRowThreads = 128;
+
+template <typename T, int kVec> struct alignas(sizeof(T) * kVec) InVec { T v[kVec]; };
+
+inline dim3 row_grid(int64_t col_items, int64_t rows, int64_t planes)
+{
+    return dim3((unsigned)((col_items + kRowThreads - 1) / kRowThreads), (unsigned)(rows < 65535 ? rows : 65535),
+                (unsigned)(planes < 65535 ? planes : 65535));
+}
+
+// out[r,c] = (in[2r,2c] + in[2r+1,2c]) / 4  (fmg.hpp:53-73).  kVec = 2: two output
+// columns per thread from two 4-element row vectors (n % 4 == 0).
+template <typename T, int kVec>
+__global__ void __launch_bounds__(kRowThreads)
 fmg_restriction_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n)
 {
     const int64_t D = 2 * (int64_t)n - 1, R = n - 1, C = n / 2;
-    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= R * C) return;
-    const int64_t r = idx / C, c = idx - r * C;
-    for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
-        const T *I = in + p * D * n;
-        const T va = I[(2 * r) * n + 2 * c];
-        const T vb = I[(2 * r + 1) * n + 2 * c];
-        out[p * R * C + idx] = (va + vb) / T(4);
-    }
+    const int c = (blockIdx.x * kRowThreads + threadIdx.x) * kVec;
+    if (c >= C) return;
+    for (int64_t p = blockIdx.z; p < planes; p += gridDim.z)
+        for (int64_t r = blockIdx.y; r < R; r += gridDim.y) {
+            const T *I = in + p * D * n + (2 * r) * n + 2 * c;
+            T *O = out + p * R * C + r * C + c;
+            if (kVec == 2) {
+                const InVec<T, 4> va = *reinterpret_cast<const InVec<T, 4> *>(I);
+                const InVec<T, 4> vb = *reinterpret_cast<const InVec<T, 4> *>(I + n);
+                const T v[2] = {(va.v[0] + vb.v[0]) / T(4), (va.v[2] + vb.v[2]) / T(4)};
+                store_outvec<T, 2>(O, v);
+            } else {
+                O[0] = (I[0] + I[n]) / T(4);
+            }
+        }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
+// out[2r+{0,1}, 2c+{0,1}] = in[r,c]  (fmg.hpp:75-95).  kVec = 2: two input columns per
+// thread, written as one 4-element vector to each of the two output rows (w even).
+template <typename T, int kVec>
+__global__ void __launch_bounds__(kRowThreads)
 fmg_prolongation_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int64_t h, int64_t w)
 {
-    const int64_t W2 = 2 * w, H2 = 2 * h;
-    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= H2 * W2) return;
-    const int64_t r = idx / W2, c = idx - r * W2;
-    for (int64_t b = blockIdx.y; b < B; b += gridDim.y)
-        out[b * H2 * W2 + idx] = in[b * h * w + (r >> 1) * w + (c >> 1)];
+    const int64_t W2 = 2 * w;
+    const int64_t c = ((int64_t)blockIdx.x * kRowThreads + threadIdx.x) * kVec;
+    if (c >= w) return;
+    for (int64_t b = blockIdx.z; b < B; b += gridDim.z)
+        for (int64_t r = blockIdx.y; r < h; r += gridDim.y) {
+            const T *I = in + (b * h + r) * w + c;
+            T *O = out + (b * 2 * h + 2 * r) * W2 + 2 * c;
+            if (kVec == 2) {
+                const InVec<T, 2> x = *reinterpret_cast<const InVec<T, 2> *>(I);
+                const T v[4] = {x.v[0], x.v[0], x.v[1], x.v[1]};
+                store_outvec<T, 4>(O, v);
+                store_outvec<T, 4>(O + W2, v);
+            } else {
+                const T x = I[0];
+                O[0] = x; O[1] = x; O[W2] = x; O[W2 + 1] = x;
+            }
+        }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kRowThreads)
 fmg_highpass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int64_t h, int64_t w)
 {
     const T ca = T(-0.0625), cb = T(-0.125), cc = T(0.75);
-    const int64_t idx = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= h * w) return;
-    const int64_t r = idx / w, c = idx - r * w;
-    const int64_t pr = (r == 0 ? 1 : r - 1), nr = (r == h - 1 ? r - 1 : r + 1);
+    const int64_t c = (int64_t)blockIdx.x * kRowThreads + threadIdx.x;
+    if (c >= w) return;
     const int64_t pc = (c == 0 ? 1 : c - 1), nc = (c == w - 1 ? c - 1 : c + 1);
-    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
-        const T *I = in + b * h * w;
-        // every product is rounded on its own (no FMA), then summed column by
-        // column exactly like fmg.hpp:129,150,167
-        const T v11 = ca * I[pr * w + pc], v12 = cb * I[pr * w + c], v13 = ca * I[pr * w + nc];
-        const T v21 = cb * I[r * w + pc], v22 = cc * I[r * w + c], v23 = cb * I[r * w + nc];
-        const T v31 = ca * I[nr * w + pc], v32 = cb * I[nr * w + c], v33 = ca * I[nr * w + nc];
-        out[b * h * w + idx] = ((v11 + v21) + v31) + ((v12 + v22) + v32) + ((v13 + v23) + v33);
-    }
+    for (int64_t b = blockIdx.z; b < B; b += gridDim.z)
+        for (int64_t r = blockIdx.y; r < h; r += gridDim.y) {
+            const int64_t pr = (r == 0 ? 1 : r - 1), nr = (r == h - 1 ? r - 1 : r + 1);
+            const T *I = in + b * h * w;
+            // every product is rounded on its own (no FMA), then summed column by
+            // column exactly like fmg.hpp:129,150,167
+            const T v11 = ca * I[pr * w + pc], v12 = cb * I[pr * w + c], v13 = ca * I[pr * w + nc];
+            const T v21 = cb * I[r * w + pc], v22 = cc * I[r * w + c], v23 = cb * I[r * w + nc];
+            const T v31 = ca * I[nr * w + pc], v32 = cb * I[nr * w + c], v33 = ca * I[nr * w + nc];
+            out[(b * h + r) * w + c] = ((v11 + v21) + v31) + ((v12 + v22) + v32) + ((v13 + v23) + v33);
+        }
 }
 
 // ---- interp_to_cart: adrt_cdefs_interp_adrtcart.hpp:61-114 --------------------
@@ -309,6 +342,39 @@ truncate_mean_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, i
     }
 }
 
+// n >= 32: 32 x 32 output tiles; the two transposed quadrants (0 and 3) go through
+// shared memory so that every global access runs along the contiguous axis.
+template <typename T>
+__global__ void __launch_bounds__(256)
+truncate_mean_tiled_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int n, T divisor)
+{
+    __shared__ T s0[32][33], s3[32][33];
+    const int64_t D = 2 * (int64_t)n - 1;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
+        const T *I = in + b * 4 * D * n;
+        // s0[i][j] = a0[n-1-(c0+i), r0+j] = T0[r0+j, c0+i];  s3[i][j] = a3[n-1-(c0+i), n-1-(r0+j)] = T3[r0+j, c0+i]
+#pragma unroll
+        for (int i = ty; i < 32; i += 8) {
+            const int64_t d = n - 1 - (c0 + i);
+            s0[i][tx] = I[(0 * D + d) * n + (r0 + tx)];
+            s3[i][tx] = I[(3 * D + d) * n + (n - 1 - (r0 + tx))];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = ty; j < 32; j += 8) {
+            const int r = r0 + j, c = c0 + tx;
+            const T t0 = s0[tx][j] / divisor;
+            const T t1 = I[(1 * D + (n - 1 - r)) * n + c] / divisor;
+            const T t2 = I[(2 * D + r) * n + c] / divisor;
+            const T t3 = s3[tx][j] / divisor;
+            out[b * n * n + (int64_t)r * n + c] = (((t0 + t1) + t2) + t3) / T(4);
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T, int kOp>
 __global__ void __launch_bounds__(kThreads)
 binary_kernel(const T *a, const T *b, T *out, int64_t count)  // out may alias a or b
@@ -317,9 +383,28 @@ binary_kernel(const T *a, const T *b, T *out, int64_t count)  // out may alias a
         out[i] = kOp == 0 ? a[i] - b[i] : a[i] + b[i];
 }
 
+// 16-byte vectors (count and the three pointers are multiples of the vector size)
+template <typename T, int kOp>
+__global__ void __launch_bounds__(kThreads)
+binary_vec_kernel(const T *a, const T *b, T *out, int64_t vectors)
+{
+    constexpr int L = 16 / sizeof(T);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < vectors; i += (int64_t)gridDim.x * kThreads) {
+        const InVec<T, L> x = reinterpret_cast<const InVec<T, L> *>(a)[i];
+        const InVec<T, L> y = reinterpret_cast<const InVec<T, L> *>(b)[i];
+        T v[L];
+#pragma unroll
+        for (int k = 0; k < L; ++k) v[k] = kOp == 0 ? x.v[k] - y.v[k] : x.v[k] + y.v[k];
+        store_outvec<T, L>(out + i * L, v);
+    }
+}
+
 }  // namespace
 
 // ---- launchers ------------------------------------------------------------------
+// vector paths need the base pointers aligned to the vector size
+inline bool aligned_to(const void *p, size_t bytes) { return reinterpret_cast<uintptr_t>(p) % bytes == 0; }
+
 template <typename T>
 int launch_adrt_init(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s)
 {
@@ -333,7 +418,7 @@ template <typename T>
 int launch_adrt_step(const T *in, T *out, int64_t B, int64_t n, int step, cudaStream_t s)
 {
     const int64_t D = 2 * n - 1;
-    if (n % 4 == 0)
+    if (n % 4 == 0 && aligned_to(out, 4 * sizeof(T)))
         adrt_step_kernel<T, 4><<<plane_grid(D * n / 4, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), step);
     else
         adrt_step_kernel<T, 1><<<plane_grid(D * n, B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), step);
@@ -346,7 +431,7 @@ int launch_bdrt_step(const T *in, T *out, int64_t B, int64_t n, int step, bool c
 {
     const int64_t D = 2 * n - 1;
     const int adrt_iter = num_iters(n) - 1 - step;
-    const bool vec = n % 4 == 0;
+    const bool vec = n % 4 == 0 && aligned_to(out, 4 * sizeof(T));
     const dim3 grid = plane_grid(vec ? D * n / 4 : D * n, B * 4);
     if (core_semantics && vec) bdrt_step_kernel<T, true, 4><<<grid, kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
     else if (core_semantics) bdrt_step_kernel<T, true, 1><<<grid, kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
@@ -369,7 +454,8 @@ int launch_iadrt_stage(const T *in, T *out, int64_t B, int64_t n, int stage, cud
 template <typename T>
 int launch_fmg_restriction(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s)
 {
-    fmg_restriction_kernel<T><<<plane_grid((n - 1) * (n / 2), B * 4), kThreads, 0, s>>>(in, out, B * 4, (int)n);
+    if (n % 4 == 0 && aligned_to(in, 4 * sizeof(T)) && aligned_to(out, 2 * sizeof(T))) fmg_restriction_kernel<T, 2><<<row_grid(n / 4, n - 1, B * 4), kRowThreads, 0, s>>>(in, out, B * 4, (int)n);
+    else fmg_restriction_kernel<T, 1><<<row_grid(n / 2, n - 1, B * 4), kRowThreads, 0, s>>>(in, out, B * 4, (int)n);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }
@@ -377,7 +463,8 @@ int launch_fmg_restriction(const T *in, T *out, int64_t B, int64_t n, cudaStream
 template <typename T>
 int launch_fmg_prolongation(const T *in, T *out, int64_t B, int64_t h, int64_t w, cudaStream_t s)
 {
-    fmg_prolongation_kernel<T><<<plane_grid(4 * h * w, B), kThreads, 0, s>>>(in, out, B, h, w);
+    if (w % 2 == 0 && aligned_to(in, 2 * sizeof(T)) && aligned_to(out, 4 * sizeof(T))) fmg_prolongation_kernel<T, 2><<<row_grid(w / 2, h, B), kRowThreads, 0, s>>>(in, out, B, h, w);
+    else fmg_prolongation_kernel<T, 1><<<row_grid(w, h, B), kRowThreads, 0, s>>>(in, out, B, h, w);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }
@@ -385,7 +472,7 @@ int launch_fmg_prolongation(const T *in, T *out, int64_t B, int64_t h, int64_t w
 template <typename T>
 int launch_fmg_highpass(const T *in, T *out, int64_t B, int64_t h, int64_t w, cudaStream_t s)
 {
-    fmg_highpass_kernel<T><<<plane_grid(h * w, B), kThreads, 0, s>>>(in, out, B, h, w);
+    fmg_highpass_kernel<T><<<row_grid(w, h, B), kRowThreads, 0, s>>>(in, out, B, h, w);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }
@@ -411,7 +498,12 @@ int launch_truncate(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s)
 template <typename T>
 int launch_truncate_mean(const T *in, T *out, int64_t B, int64_t n, T divisor, cudaStream_t s)
 {
-    truncate_mean_kernel<T><<<plane_grid(n * n, B), kThreads, 0, s>>>(in, out, B, (int)n, ilog2(n), divisor);
+    if (n >= 32) {
+        dim3 grid((unsigned)(n / 32), (unsigned)(n / 32), (unsigned)(B < 65535 ? B : 65535));
+        truncate_mean_tiled_kernel<T><<<grid, 256, 0, s>>>(in, out, B, (int)n, divisor);
+    } else {
+        truncate_mean_kernel<T><<<plane_grid(n * n, B), kThreads, 0, s>>>(in, out, B, (int)n, ilog2(n), divisor);
+    }
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }
@@ -419,10 +511,17 @@ int launch_truncate_mean(const T *in, T *out, int64_t B, int64_t n, T divisor, c
 template <typename T>
 int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStream_t s)
 {
-    int64_t blocks = (count + kThreads - 1) / kThreads;
+    constexpr int L = 16 / sizeof(T);
+    const bool vec = count % L == 0 && aligned_to(a, 16) && aligned_to(b, 16) && aligned_to(out, 16);
+    const int64_t items = vec ? count / L : count;
+    int64_t blocks = (items + kThreads - 1) / kThreads;
     if (blocks > 148 * 64) blocks = 148 * 64;
     if (blocks < 1) blocks = 1;
-    if (op == 0)
+    if (vec && op == 0)
+        binary_vec_kernel<T, 0><<<(unsigned)blocks, kThreads, 0, s>>>(a, b, out, items);
+    else if (vec)
+        binary_vec_kernel<T, 1><<<(unsigned)blocks, kThreads, 0, s>>>(a, b, out, items);
+    else if (op == 0)
         binary_kernel<T, 0><<<(unsigned)blocks, kThreads, 0, s>>>(a, b, out, count);
     else
         binary_kernel<T, 1><<<(unsigned)blocks, kThreads, 0, s>>>(a, b, out, count);

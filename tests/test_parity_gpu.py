@@ -318,6 +318,44 @@ def test_bdrt_rows_and_truncate_mean(dn, n, B):
         cd.bdrt_planes(s, rows=2 * n)
 
 
+@pytest.mark.parametrize("dn", list(DTYPES))
+def test_fmg_operators_shapes_and_alignment(dn):
+    """Press FMG operators on odd / non-square / large shapes (scalar and vector kernel
+    variants) and on tensors whose storage is not 16-byte aligned."""
+    import torch
+
+    dt = DTYPES[dn]
+    for shape in ((3, 5, 7), (2, 6, 10), (1, 33, 64), (2, 2, 2), (1, 1024, 2048), (5, 64, 3)):
+        x = make_image(41 + shape[-1], shape, dt)
+        _eq(cd.press_fmg_prolongation(x), O.press_fmg_prolongation(x), f"prolongation {shape}")
+        if shape[-1] >= 2 and shape[-2] >= 2:
+            _eq(cd.press_fmg_highpass(x), O.press_fmg_highpass(x), f"highpass {shape}")
+    for n, B in ((2, 3), (4, 2), (8, 1), (64, 2), (1024, 1)):
+        s = make_sino(43 + n, (B, 4, 2 * n - 1, n), dt)
+        _eq(cd.press_fmg_restriction(s), O.press_fmg_restriction(s), f"restriction n={n}")
+    # misaligned storage: views starting one element into a larger buffer
+    n = 64
+    s = make_sino(47, (2, 4, 2 * n - 1, n), dt)
+    x = make_image(48, (2, n, n), dt)
+    for arr, fn, ofn in ((s, cd.press_fmg_restriction, O.press_fmg_restriction),
+                         (x, cd.press_fmg_prolongation, O.press_fmg_prolongation),
+                         (x, cd.press_fmg_highpass, O.press_fmg_highpass),
+                         (s, lambda t, **kw: cd.adrt_step(t, 2, **kw), lambda a: O.adrt_step(a, 2)),
+                         (s, lambda t, **kw: cd.bdrt_step(t, 2, **kw), lambda a: O.bdrt_step(a, 2))):
+        buf = torch.zeros(arr.size + 1, dtype=torch.from_numpy(arr).dtype, device="cuda")
+        view = buf[1:].view(arr.shape)
+        view.copy_(torch.from_numpy(arr))
+        want = ofn(arr)
+        obuf = torch.zeros(want.size + 1, dtype=view.dtype, device="cuda")
+        oview = obuf[1:].view(want.shape)
+        got = fn(view, out=oview)
+        _eq(got.cpu().numpy(), want, "misaligned in/out")
+        a2 = torch.from_numpy(arr).cuda()
+        d = cd.sub(view, a2, out=oview) if want.shape == arr.shape else None
+        if d is not None:
+            assert not d.any()
+
+
 def test_iadrt_roundtrip():
     # reference tests/test_iadrt.py:185-223
     for n in (16, 32):
