@@ -239,6 +239,62 @@ fmg_prolongation_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B
         }
 }
 
+// Four consecutive columns per thread, walking down a strip of kStrip rows with the three
+// live rows in registers: one vector + two scalar loads per row instead of nine per output.
+// w % 4 == 0 and 16-byte aligned planes.
+constexpr int kStrip = 8;
+
+template <typename T> struct HpRow { T l, v[4], r; };
+
+template <typename T>
+__device__ __forceinline__ HpRow<T> hp_load(const T *__restrict__ row, int c, int w)
+{
+    HpRow<T> o;
+    const InVec<T, 4> x = *reinterpret_cast<const InVec<T, 4> *>(row + c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.v[i] = x.v[i];
+    o.l = c == 0 ? x.v[1] : row[c - 1];             // reflect-101 (fmg.hpp:108-118)
+    o.r = c + 4 == w ? x.v[2] : row[c + 4];
+    return o;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads)
+fmg_highpass_vec_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int h, int w)
+{
+    const T ca = T(-0.0625), cb = T(-0.125), cc = T(0.75);
+    const int c = (blockIdx.x * kRowThreads + threadIdx.x) * 4;
+    if (c >= w) return;
+    for (int64_t b = blockIdx.z; b < B; b += gridDim.z)
+        for (int r0 = blockIdx.y * kStrip; r0 < h; r0 += gridDim.y * kStrip) {
+            const T *I = in + b * h * w;
+            T *O = out + b * h * w;
+            HpRow<T> P = hp_load(I + (int64_t)(r0 == 0 ? 1 : r0 - 1) * w, c, w);
+            HpRow<T> C = hp_load(I + (int64_t)r0 * w, c, w);
+#pragma unroll
+            for (int i = 0; i < kStrip; ++i) {
+                const int r = r0 + i;
+                if (r >= h) break;
+                const HpRow<T> N = (r == h - 1) ? P : hp_load(I + (int64_t)(r + 1) * w, c, w);
+                const T p[6] = {P.l, P.v[0], P.v[1], P.v[2], P.v[3], P.r};
+                const T m[6] = {C.l, C.v[0], C.v[1], C.v[2], C.v[3], C.r};
+                const T q[6] = {N.l, N.v[0], N.v[1], N.v[2], N.v[3], N.r};
+                T v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // products rounded one by one, summed column by column (fmg.hpp:129,150,167)
+                    const T v11 = ca * p[k], v12 = cb * p[k + 1], v13 = ca * p[k + 2];
+                    const T v21 = cb * m[k], v22 = cc * m[k + 1], v23 = cb * m[k + 2];
+                    const T v31 = ca * q[k], v32 = cb * q[k + 1], v33 = ca * q[k + 2];
+                    v[k] = ((v11 + v21) + v31) + ((v12 + v22) + v32) + ((v13 + v23) + v33);
+                }
+                store_outvec<T, 4>(O + (int64_t)r * w + c, v);
+                P = C;
+                C = N;
+            }
+        }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads)
 fmg_highpass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int64_t h, int64_t w)
@@ -285,6 +341,8 @@ interp_kernel(const T *__restrict__ in, T *__restrict__ out, const float *__rest
     const bool ok = hi >= 0.0f && hi < (float)D;
     const int64_t src = ok ? (int64_t)base[ang] + (int64_t)hi * n : 0;
     const T f = factor[ang];
+    // the index computation above is shared by all images: each thread serves B / gridDim.y of them
+#pragma unroll 4
     for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
         T v = T(0);
         if (ok) v = f * in[b * 4 * D * n + src];
@@ -355,21 +413,32 @@ truncate_mean_tiled_kernel(const T *__restrict__ in, T *__restrict__ out, int64_
     for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
         const T *I = in + b * 4 * D * n;
         // s0[i][j] = a0[n-1-(c0+i), r0+j] = T0[r0+j, c0+i];  s3[i][j] = a3[n-1-(c0+i), n-1-(r0+j)] = T3[r0+j, c0+i]
+        // all sixteen loads of a thread are issued before anything waits on them
+        T a0[4], a3[4], a1[4], a2[4];
 #pragma unroll
-        for (int i = ty; i < 32; i += 8) {
+        for (int m = 0; m < 4; ++m) {
+            const int i = ty + 8 * m;
             const int64_t d = n - 1 - (c0 + i);
-            s0[i][tx] = I[(0 * D + d) * n + (r0 + tx)];
-            s3[i][tx] = I[(3 * D + d) * n + (n - 1 - (r0 + tx))];
+            a0[m] = I[(0 * D + d) * n + (r0 + tx)];
+            a3[m] = I[(3 * D + d) * n + (n - 1 - (r0 + tx))];
+            const int r = r0 + i;
+            a1[m] = I[(1 * D + (n - 1 - r)) * n + c0 + tx];
+            a2[m] = I[(2 * D + r) * n + c0 + tx];
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            s0[ty + 8 * m][tx] = a0[m];
+            s3[ty + 8 * m][tx] = a3[m];
         }
         __syncthreads();
 #pragma unroll
-        for (int j = ty; j < 32; j += 8) {
-            const int r = r0 + j, c = c0 + tx;
+        for (int m = 0; m < 4; ++m) {
+            const int j = ty + 8 * m;
             const T t0 = s0[tx][j] / divisor;
-            const T t1 = I[(1 * D + (n - 1 - r)) * n + c] / divisor;
-            const T t2 = I[(2 * D + r) * n + c] / divisor;
+            const T t1 = a1[m] / divisor;
+            const T t2 = a2[m] / divisor;
             const T t3 = s3[tx][j] / divisor;
-            out[b * n * n + (int64_t)r * n + c] = (((t0 + t1) + t2) + t3) / T(4);
+            out[b * n * n + (int64_t)(r0 + j) * n + c0 + tx] = (((t0 + t1) + t2) + t3) / T(4);
         }
         __syncthreads();
     }
@@ -472,7 +541,10 @@ int launch_fmg_prolongation(const T *in, T *out, int64_t B, int64_t h, int64_t w
 template <typename T>
 int launch_fmg_highpass(const T *in, T *out, int64_t B, int64_t h, int64_t w, cudaStream_t s)
 {
-    fmg_highpass_kernel<T><<<row_grid(w, h, B), kRowThreads, 0, s>>>(in, out, B, h, w);
+    if (w % 4 == 0 && w >= 4 && h < (1 << 30) && w < (1 << 30) && aligned_to(in, 4 * sizeof(T)) && aligned_to(out, 4 * sizeof(T)))
+        fmg_highpass_vec_kernel<T><<<row_grid(w / 4, (h + kStrip - 1) / kStrip, B), kRowThreads, 0, s>>>(in, out, B, (int)h, (int)w);
+    else
+        fmg_highpass_kernel<T><<<row_grid(w, h, B), kRowThreads, 0, s>>>(in, out, B, h, w);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }
@@ -482,7 +554,10 @@ int launch_interp_to_cart(const T *in, T *out, const float *t, const int32_t *ba
                           const float *cosv, const int32_t *sgn, const T *factor, int64_t B, int64_t n,
                           cudaStream_t s)
 {
-    interp_kernel<T><<<plane_grid(4 * n * n, B), kThreads, 0, s>>>(in, out, t, base, h_base, cosv, sgn, factor, B, (int)n, ilog2(n));
+    dim3 grid = plane_grid(4 * n * n, B);
+    // enough threads to fill the GPU with one or two images: share the index math over the batch
+    if (4 * n * n >= (int64_t)148 * 2048 * 4) grid.y = (unsigned)((B + 7) / 8);
+    interp_kernel<T><<<grid, kThreads, 0, s>>>(in, out, t, base, h_base, cosv, sgn, factor, B, (int)n, ilog2(n));
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }

@@ -325,7 +325,7 @@ def test_fmg_operators_shapes_and_alignment(dn):
     import torch
 
     dt = DTYPES[dn]
-    for shape in ((3, 5, 7), (2, 6, 10), (1, 33, 64), (2, 2, 2), (1, 1024, 2048), (5, 64, 3)):
+    for shape in ((3, 5, 7), (2, 6, 10), (1, 33, 64), (2, 2, 2), (1, 1024, 2048), (5, 64, 3), (3, 9, 4), (2, 17, 8), (2, 2, 12)):
         x = make_image(41 + shape[-1], shape, dt)
         _eq(cd.press_fmg_prolongation(x), O.press_fmg_prolongation(x), f"prolongation {shape}")
         if shape[-1] >= 2 and shape[-2] >= 2:
