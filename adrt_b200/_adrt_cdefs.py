@@ -350,6 +350,31 @@ def truncate_mean(a, divisor, /, *, out=None):
     return ret
 
 
+def fmg_step(a, /, *, out=None):
+    """core.iadrt_fmg_step (core.py:265-331) for CUDA tensors ``(B?, 4, 2n-1, n)`` ->
+    ``(B?, n, n)``: all multigrid levels in one native call."""
+    arr = _extract_array(a)
+    if not arr.is_torch:
+        raise TypeError("fmg_step is a device-only helper (CUDA tensors)")
+    shape = _array_shape(arr, 3, 4)
+    if not _is_adrt_output_shape(shape):
+        raise ValueError("array must have a valid ADRT output shape")
+    b, _, _, n = shape
+    res = _result_shape(arr, (b, n, n), drop=1)
+    lib = _lib.load()
+    code = _dtype_code(arr)
+    ret = _empty_like(arr, res, out)
+    import torch
+
+    with torch.cuda.device(arr.obj.device):
+        nbytes = int(lib.adrt_b200_fmg_step_workspace_bytes(b, n, code))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=arr.obj.device)
+        rc = lib.adrt_b200_fmg_step(arr.obj.data_ptr(), ret.data_ptr(), b, n, code, ws.data_ptr(), nbytes,
+                                    torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "fmg_step")
+    return ret
+
+
 def truncate(a, /, *, out=None):
     """Device version of utils.truncate (utils.py:231-242); CUDA tensors only."""
     arr = _extract_array(a)

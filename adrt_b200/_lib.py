@@ -48,6 +48,8 @@ SIGNATURES = {
     "adrt_b200_fmg_restriction": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
     "adrt_b200_fmg_prolongation": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp]),
     "adrt_b200_fmg_highpass": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp]),
+    "adrt_b200_fmg_step_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int]),
+    "adrt_b200_fmg_step": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp, _c_sz, _c_vp]),
     "adrt_b200_interp_to_cart": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
     "adrt_b200_truncate": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
     "adrt_b200_truncate_mean": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_double, _c_int, _c_vp]),

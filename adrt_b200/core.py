@@ -128,24 +128,13 @@ def _to_device(a):
 def _fmg_step_device(a):
     """One FMG pass on a CUDA tensor ``(B?, 4, 2n-1, n)`` -> ``(B?, n, n)``.
 
-    Same operator sequence as core.py:318-331; ``np.mean(x / (m-1), axis=-3)``
-    is the fused ``truncate_mean`` kernel, which divides each quadrant first
-    and then sums ``((q0+q1)+q2)+q3`` before the ``/4`` exactly as NumPy does.
+    Same operator sequence as core.py:318-331, run level by level inside one
+    native call (``adrt_b200_fmg_step``): ``np.mean(x / (m-1), axis=-3)`` is the
+    ``truncate_mean`` kernel, which divides each quadrant first and then sums
+    ``((q0+q1)+q2)+q3`` before the ``/4`` exactly as NumPy does, and the
+    back-projection only computes the offsets ``truncate`` keeps.
     """
-    cd = _adrt_cdefs
-    stack = []
-    for _ in range(num_iters(a.shape[-1])):
-        stack.append(a)
-        a = cd.press_fmg_restriction(a)
-    ret = a[..., 0, :, :].contiguous()
-    m = 1
-    while stack:
-        m *= 2
-        ret = cd.press_fmg_prolongation(ret)
-        resid = cd.sub(cd.adrt(ret), stack.pop())
-        grad = cd.bdrt_truncate_mean(resid, m - 1)
-        ret = cd.sub(ret, cd.press_fmg_highpass(grad), out=ret)
-    return ret
+    return _adrt_cdefs.fmg_step(a)
 
 
 def iadrt_fmg_step(a, /):

@@ -277,6 +277,85 @@ int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, int64_t row
     return fused_bdrt<T>(in, out, planes, n, 1, rows, ws, ws_bytes / sizeof(T), s, &handled);
 }
 
+// ---- one full-multigrid pass, all levels, no host round trips --------------------
+// core.py:318-331 (iadrt_fmg_step): restrict the sinogram down to 1 x 1, then per level
+//   ret = prolongation(ret); ret -= highpass(mean_q(truncate(bdrt(adrt(ret) - a_level)) / (m - 1)))
+// with the reference's operator order, so the result is bit-identical to composing the
+// public operators.  Workspace segments are padded to 64 elements.
+inline size_t pad64(size_t v) { return (v + 63) & ~size_t(63); }
+
+template <typename T>
+size_t fmg_transform_ws_elems(int64_t B, int64_t n)
+{
+    size_t a = adrt_ws_elems<T>(B, n), b = bdrt_ws_elems<T>(B, n);
+    if (g_mode.load() == 0 && n >= 2) {
+        const size_t c = fused_bdrt_workspace_elems<T>(B * 4, n, 1);
+        if (c != (size_t)-1 && c > b) b = c;
+    }
+    return a > b ? a : b;
+}
+
+template <typename T>
+size_t fmg_step_ws_elems(int64_t B, int64_t n)
+{
+    size_t total = 0;
+    for (int64_t m = n / 2; m >= 1; m /= 2) total += pad64((size_t)sino_elems(B, m));
+    total += 2 * pad64((size_t)sino_elems(B, n)) + 4 * pad64((size_t)(B * n * n));
+    return total + pad64(fmg_transform_ws_elems<T>(B, n));
+}
+
+template <typename T>
+int fmg_step_impl(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_bytes, cudaStream_t s)
+{
+    const size_t need = fmg_step_ws_elems<T>(B, n) * sizeof(T);
+    if (!ws || ws_bytes < need) {
+        set_error("fmg_step workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return ADRT_B200_EWORKSPACE;
+    }
+    const int K = num_iters(n);
+    // restricted sinograms: level[0] = caller's input, level[k] has side n >> k
+    std::vector<const T *> level(K + 1);
+    level[0] = in;
+    T *p = ws;
+    int rc = ADRT_B200_OK;
+    for (int k = 1; k <= K && rc == ADRT_B200_OK; ++k) {
+        rc = launch_fmg_restriction<T>(level[k - 1], p, B, n >> (k - 1), s);
+        level[k] = p;
+        p += pad64((size_t)sino_elems(B, n >> k));
+    }
+    if (rc != ADRT_B200_OK) return rc;
+    T *sino_a = p; p += pad64((size_t)sino_elems(B, n));
+    T *sino_b = p; p += pad64((size_t)sino_elems(B, n));
+    T *img[2] = {p, p + pad64((size_t)(B * n * n))};
+    p += 2 * pad64((size_t)(B * n * n));
+    T *grad = p; p += pad64((size_t)(B * n * n));
+    T *hp = p; p += pad64((size_t)(B * n * n));
+    T *tws = p;
+    const size_t tws_bytes = ws_bytes - (size_t)(tws - ws) * sizeof(T);
+
+    // ret = a_K[..., 0, :, :]: element 0 of every image's (4, 1, 1) block
+    T *cur = K == 0 ? out : img[0];
+    ADRT_CUDA_CHECK(cudaMemcpy2DAsync(cur, sizeof(T), level[K], 4 * sizeof(T), sizeof(T), (size_t)B,
+                                      cudaMemcpyDeviceToDevice, s));
+    int which = 0;
+    for (int k = K - 1; k >= 0; --k) {
+        const int64_t m = n >> k;
+        T *pro = img[which ^ 1];
+        if ((rc = launch_fmg_prolongation<T>(cur, pro, B, m / 2, m / 2, s))) return rc;
+        if ((rc = adrt_impl<T>(pro, sino_a, B, m, tws, tws_bytes, s))) return rc;
+        if ((rc = launch_binary<T>(sino_a, level[k], sino_a, sino_elems(B, m), 0, s))) return rc;
+        if (g_mode.load() == 0) rc = bdrt_planes_impl<T>(sino_a, sino_b, B * 4, m, m, tws, tws_bytes, s);
+        else rc = bdrt_impl<T>(sino_a, sino_b, B, m, tws, tws_bytes, s);
+        if (rc) return rc;
+        if ((rc = launch_truncate_mean<T>(sino_b, grad, B, m, (T)(m - 1), s))) return rc;
+        if ((rc = launch_fmg_highpass<T>(grad, hp, B, m, m, s))) return rc;
+        if ((rc = launch_binary<T>(pro, hp, k == 0 ? out : pro, B * m * m, 0, s))) return rc;
+        cur = pro;
+        which ^= 1;
+    }
+    return ADRT_B200_OK;
+}
+
 #define DISPATCH(dtype, CALL_F32, CALL_F64) ((dtype) == ADRT_B200_F64 ? (CALL_F64) : (CALL_F32))
 
 extern "C" {
@@ -444,6 +523,22 @@ int adrt_b200_fmg_highpass(const void *in, void *out, int64_t B, int64_t h, int6
     return DISPATCH(dtype,
                     launch_fmg_highpass<float>((const float *)in, (float *)out, B, h, w, as_stream(stream)),
                     launch_fmg_highpass<double>((const double *)in, (double *)out, B, h, w, as_stream(stream)));
+}
+
+size_t adrt_b200_fmg_step_workspace_bytes(int64_t B, int64_t n, int dtype)
+{
+    if (B <= 0 || !is_pow2(n) || n > kMaxN || !dtype_ok(dtype)) return 0;
+    return DISPATCH(dtype, fmg_step_ws_elems<float>(B, n) * 4, fmg_step_ws_elems<double>(B, n) * 8);
+}
+
+int adrt_b200_fmg_step(const void *in, void *out, int64_t B, int64_t n, int dtype, void *ws, size_t ws_bytes,
+                       void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    return DISPATCH(dtype,
+                    fmg_step_impl<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes, as_stream(stream)),
+                    fmg_step_impl<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes, as_stream(stream)));
 }
 
 int adrt_b200_interp_to_cart(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream)

@@ -125,6 +125,14 @@ int    adrt_b200_fmg_prolongation(const void *in, void *out, int64_t B, int64_t 
 int    adrt_b200_fmg_highpass(const void *in, void *out, int64_t B, int64_t h, int64_t w,
                               int dtype, void *stream);
 
+/* adrt.core.iadrt_fmg_step (core.py:265-331; pure Python over the operators above in
+ * the reference): one full-multigrid pass, every level on the device in one call.
+ * in (B,4,2n-1,n) -> out (B,n,n); bit-identical to composing restriction /
+ * prolongation / adrt / bdrt / truncate / mean / highpass as core.py:318-331 does. */
+size_t adrt_b200_fmg_step_workspace_bytes(int64_t B, int64_t n, int dtype);
+int    adrt_b200_fmg_step(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
 /* adrt.utils.interp_to_cart: adrt_cdefs_py.cpp:621-682 -> interp_adrtcart
  * (adrt_cdefs_interp_adrtcart.hpp:61-114).  The (quadrant, height, slope,
  * factor) table depends only on (n, dtype); it is computed on the host with

@@ -356,6 +356,34 @@ def test_fmg_operators_shapes_and_alignment(dn):
             assert not d.any()
 
 
+@pytest.mark.parametrize("dn", list(DTYPES))
+@pytest.mark.parametrize("n,B", [(1, 2), (2, 3), (8, 2), (64, 3), (512, 2), (2048, 1)])
+def test_native_fmg_step_equals_composed_operators(mode, dn, n, B):
+    """adrt_b200_fmg_step (all levels in one native call) against the same sequence written
+    with the public operators as in core.py:318-331."""
+    import torch
+
+    dt = DTYPES[dn]
+    a = torch.from_numpy(make_sino(51 + n, (B, 4, 2 * n - 1, n), dt)).cuda()
+    got = cd.fmg_step(a)
+    stack, cur = [], a
+    for _ in range(O.num_iters(n)):
+        stack.append(cur)
+        cur = cd.press_fmg_restriction(cur)
+    ret = cur[..., 0, :, :].contiguous()
+    m = 1
+    while stack:
+        m *= 2
+        ret = cd.press_fmg_prolongation(ret)
+        resid = cd.sub(cd.adrt(ret), stack.pop())
+        grad = cd.truncate_mean(cd.bdrt(resid), m - 1)
+        ret = cd.sub(ret, cd.press_fmg_highpass(grad))
+    assert tuple(got.shape) == (B, n, n)
+    assert torch.equal(got.view(torch.uint8), ret.view(torch.uint8))
+    if n <= 64:
+        _eq(got.cpu().numpy(), O.iadrt_fmg_step(a.cpu().numpy()), "fmg_step vs oracle")
+
+
 def test_iadrt_roundtrip():
     # reference tests/test_iadrt.py:185-223
     for n in (16, 32):
