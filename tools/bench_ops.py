@@ -51,3 +51,11 @@ for (B, n, dt) in ((16, 2048, torch.float32), (4, 4096, torch.float32), (8, 2048
     print(json.dumps(r), flush=True)
     del x, y
     torch.cuda.empty_cache()
+
+# BASELINE config 4: iadrt_fmg workload, 16 images of 4096^2 fp32 -- one FMG pass, device resident
+x = torch.rand((16, 4096, 4096), device="cuda")
+y = adrt.adrt(x)
+del x
+t = timeit(lambda: adrt.core.iadrt_fmg_step(y), reps=3)
+print(json.dumps({"B": 16, "n": 4096, "dtype": "torch.float32", "fmg_step_ms": round(t, 3),
+                  "Gpx/s": round(16 * 4096 * 4096 / (t * 1e-3) / 1e9, 2)}), flush=True)
