@@ -117,3 +117,31 @@ def sharded_normal_operator(x, dist=None, *, local_fn=_local_quadrant_backprojec
             parts += [gathered[r][i] for i in range(qc)]
     t0, t1, t2, t3 = parts
     return (((t0 + t1) + t2) + t3) / 4
+
+
+def bind_host_to_device(index: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to CUDA device
+    `index` (its NUMA node), so that pinned host buffers allocated afterwards and
+    the staging threads of the host API sit next to the GPU's PCIe root.  One
+    process per GPU should call this before allocating host memory.  Returns
+    False (and changes nothing) when NVML or the affinity call is unavailable."""
+    import os
+
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(index)
+        bus_id = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {i * 64 + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False

@@ -224,6 +224,9 @@ def ours(args, np_dtype):
         args.gpus = world
     torch.cuda.set_device(local_rank)
     adrt.set_device(local_rank)
+    # one process per GPU: sit on the GPU's NUMA node before any host buffer exists
+    from adrt_b200._shard import bind_host_to_device
+    numa_bound = bind_host_to_device(local_rank) if world > 1 else False
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
@@ -305,6 +308,7 @@ def ours(args, np_dtype):
                 "d2h_bytes_per_step": int(ny.nbytes + nz.nbytes),
                 "ms_per_step": dt_step * 1e3, "steps": e2e_steps,
                 "api": "adrt_b200.adrt / adrt_b200.bdrt on pinned numpy.ndarray (adrt_b200_host_adrt / _bdrt)",
+                "numa_bound": bool(numa_bound),
             }
             # end-to-end result check on one image against the device-resident result
             assert np.array_equal(ny[0], y[0].cpu().numpy()), "host path and device path disagree"
