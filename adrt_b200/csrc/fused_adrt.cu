@@ -4,8 +4,7 @@
 // algorithms are in fused_tile.h, the pass planning in fused_plan.h.  HBM
 // traffic per transform drops from 2*K sinogram sweeps (per-stage kernels) to
 // one sweep per pass (2 passes up to n = 4096 in fp32).
-#include "common.cuh"
-#include "fused_plan.h"
+#include "pass_args.h"
 
 #include <type_traits>
 
@@ -13,13 +12,6 @@ namespace adrt_b200 {
 
 namespace {
 
-struct PassArgs {
-    int n, D, e, loge, next_g, d_need;
-    long long in_pitch, out_pitch;
-    long long src_plane_stride, dst_plane_stride;  // elements between consecutive planes
-    int planes;
-    int q_first, q_count;   // image loader: plane -> (image = plane / q_count, quadrant = q_first + plane % q_count)
-};
 
 // The phases of a full tile, unrolled at compile time with a barrier after each.
 template <typename Prog, typename T, int PH>
@@ -112,6 +104,11 @@ int dispatch_kinds(int load, int store, const T *src, T *dst, const PassArgs &a,
 template <typename T, bool kForward>
 int dispatch_pass(const plan::Pass &p, const T *src, T *dst, const PassArgs &a, cudaStream_t s)
 {
+    if (p.stream) {
+        if constexpr (std::is_same<T, float>::value) return launch_stream_pass(p, kForward, src, dst, a, s);
+        set_error("internal: streaming passes are fp32 only");
+        return ADRT_B200_EINVAL;
+    }
     switch (p.M) {
     case 1: return dispatch_kinds<T, 1, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);
     case 2: return dispatch_kinds<T, 2, kForward>(p.load, p.store, src, dst, a, p.grid_x, p.grid_y, s);

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "fused_tile.h"
+#include "stream_tile.h"
 
 namespace adrt_b200 {
 namespace plan {
@@ -27,6 +28,7 @@ struct Pass {
     int grid_x, grid_y;             // d-tiles, groups
     int next_g;                     // forward: group size of the pass reading this pass's workspace (0: none)
     int d_need;                     // transposed: output offsets >= d_need are not needed (tiles skipped)
+    bool stream;                    // run by the streaming kernels (stream_tile.h) instead of fused_tile.h
 };
 
 struct Plan {
@@ -92,10 +94,22 @@ inline long long fwd_pitch(int n, int s)
     return round4((p < D ? p : D) + 3);
 }
 
-inline int tile_td(int M, int store)
+inline int tile_td(int M, int store, bool stream = false)
 {
+    if (stream) return M == 6 ? stile::STileTD<6, 0>::value + (store == tile::STORE_WROWS ? 0 : 4)
+                              : stile::STileTD<5, 0>::value + (store == tile::STORE_WROWS ? 0 : 4);
     const int G = 1 << M;
     return tile::XW - (G < 4 ? 4 : G) - (store == tile::STORE_WROWS ? 4 : 0);
+}
+
+// Which passes the streaming kernels take: fp32, 5 or 6 stages.  ADRT_B200_STREAM=0
+// turns them off (A/B measurements, tests of the fused_tile.h path).
+inline bool use_stream(int M, size_t elem_size, bool forward)
+{
+    if (elem_size != 4 || (M != 5 && M != 6)) return false;
+    if (!forward) return false;
+    if (const char *e = getenv("ADRT_B200_STREAM")) return atoi(e) != 0;
+    return true;
 }
 
 inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
@@ -120,7 +134,8 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        const int TD = tile_td(p.M, p.store);
+        p.stream = use_stream(p.M, elem_size, true);
+        const int TD = tile_td(p.M, p.store, p.stream);
         p.next_g = last ? 0 : (1 << ms[i + 1]);
         p.d_need = pl->D;
         const long long extent = last ? pl->D : p.out_pitch;  // offsets that must be written
@@ -161,6 +176,7 @@ inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
+        p.stream = use_stream(p.M, elem_size, false);
         p.next_g = 0;
         p.grid_y = n / G;
         if (!last) {
@@ -177,7 +193,7 @@ inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_
         p.d_need = (int)(need < pl->D ? need : pl->D);
         const long long G = 1LL << p.M, e = 1LL << p.s;
         need = p.d_need + (e - 1) * (G - 1) + G + 8;
-        const int TD = tile_td(p.M, p.store);
+        const int TD = tile_td(p.M, p.store, p.stream);
         const long long extent = p.d_need + (e - 1) * (G - 1);  // tile coordinates that hold wanted outputs
         p.grid_x = (int)((extent + TD - 1) / TD);
     }

@@ -1,0 +1,21 @@
+// Kernel arguments of one fused pass, shared by fused_adrt.cu (fused_tile.h kernels) and
+// stream_adrt.cu (stream_tile.h kernels).
+#pragma once
+
+#include "common.cuh"
+#include "fused_plan.h"
+
+namespace adrt_b200 {
+
+struct PassArgs {
+    int n, D, e, loge, next_g, d_need;
+    long long in_pitch, out_pitch;
+    long long src_plane_stride, dst_plane_stride;  // elements between consecutive planes
+    int planes;
+    int q_first, q_count;   // image loader: plane -> (image = plane / q_count, quadrant = q_first + plane % q_count)
+};
+
+// fp32 streaming passes (plan::Pass::stream); defined in stream_adrt.cu
+int launch_stream_pass(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a, cudaStream_t s);
+
+}  // namespace adrt_b200

@@ -1,0 +1,104 @@
+// Streaming fused passes for sm_100a (fp32, 5 or 6 stages per pass): the CUDA
+// kernels around the tile programs of stream_tile.h.  One CTA = one tile of one
+// group of one (image, quadrant) plane, 128 threads; the butterfly steps keep a
+// radix-8 butterfly and its history in registers (few, fat threads: the tile, not
+// the register file, limits occupancy).
+#include "pass_args.h"
+
+namespace adrt_b200 {
+
+namespace {
+
+// the barrier-separated phases of a full tile, unrolled at compile time
+template <typename Prog, int PH>
+__device__ __forceinline__ void run_phases(float *buf, typename Prog::State &st, const float *sp, float *dp,
+                                           const tile::TileCtx &c, int tid)
+{
+    if constexpr (PH < Prog::kPhases) {
+        Prog::template phase_ct<PH>(buf, st, sp, dp, c, tid);
+        if (Prog::barrier_after(PH)) __syncthreads();
+        run_phases<Prog, PH + 1>(buf, st, sp, dp, c, tid);
+    }
+}
+
+template <typename Prog>
+__global__ void __launch_bounds__(Prog::NT, Prog::MIN_CTAS)
+stream_kernel(const float *__restrict__ src, float *__restrict__ dst, PassArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *buf = reinterpret_cast<float *>(smem_raw);
+
+    tile::TileCtx c;
+    c.n = a.n;
+    c.D = a.D;
+    c.e = a.e;
+    c.g = blockIdx.y;
+    c.k0 = c.g >> a.loge;
+    c.a_g = c.g & (a.e - 1);
+    c.d0 = blockIdx.x * Prog::TD;
+    c.next_g = a.next_g;
+    c.d_need = a.d_need;
+    c.in_pitch = a.in_pitch;
+    c.out_pitch = a.out_pitch;
+    c.q = 0;
+    const int mode = Prog::classify(c);
+    if (mode == tile::TILE_SKIP) return;
+    const int tid = threadIdx.x;
+    __shared__ unsigned long long bulk_bar;
+    typename Prog::State st;
+    if (mode != tile::TILE_ZERO) stile::bulk_init(st.bar, &bulk_bar, Prog::NT, tid);
+
+    for (int plane = blockIdx.z; plane < a.planes; plane += gridDim.z) {
+        const float *sp;
+        if (Prog::kImage) {
+            c.q = a.q_first + plane % a.q_count;
+            sp = src + (long long)(plane / a.q_count) * a.src_plane_stride;
+        } else {
+            sp = src + (long long)plane * a.src_plane_stride;
+        }
+        float *dp = dst + (long long)plane * a.dst_plane_stride;
+        if (mode == tile::TILE_ZERO) {
+            Prog::zero_tile(buf, dp, c, tid);
+        } else {
+            run_phases<Prog, 0>(buf, st, sp, dp, c, tid);
+        }
+    }
+}
+
+template <typename Prog>
+int launch(const float *src, float *dst, const PassArgs &a, int grid_x, int grid_y, cudaStream_t s)
+{
+    auto kern = stream_kernel<Prog>;
+    const size_t smem = (size_t)Prog::G * stile::P * sizeof(float);
+    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)grid_x, (unsigned)grid_y, (unsigned)(a.planes < 65535 ? a.planes : 65535));
+    kern<<<grid, Prog::NT, smem, s>>>(src, dst, a);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <int M>
+int dispatch_fwd(const plan::Pass &p, const float *src, float *dst, const PassArgs &a, cudaStream_t s)
+{
+    using namespace tile;
+    if (p.load == LOAD_IMAGE && p.store == STORE_WROWS) return launch<stile::FwdStream<M, LOAD_IMAGE, STORE_WROWS>>(src, dst, a, p.grid_x, p.grid_y, s);
+    if (p.load == LOAD_IMAGE && p.store == STORE_QCOLS) return launch<stile::FwdStream<M, LOAD_IMAGE, STORE_QCOLS>>(src, dst, a, p.grid_x, p.grid_y, s);
+    if (p.load == LOAD_WROWS && p.store == STORE_WROWS) return launch<stile::FwdStream<M, LOAD_WROWS, STORE_WROWS>>(src, dst, a, p.grid_x, p.grid_y, s);
+    if (p.load == LOAD_WROWS && p.store == STORE_QCOLS) return launch<stile::FwdStream<M, LOAD_WROWS, STORE_QCOLS>>(src, dst, a, p.grid_x, p.grid_y, s);
+    set_error("internal: bad streaming pass kinds %d/%d", p.load, p.store);
+    return ADRT_B200_EINVAL;
+}
+
+}  // namespace
+
+int launch_stream_pass(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a, cudaStream_t s)
+{
+    if (forward) {
+        if (p.M == 6) return dispatch_fwd<6>(p, src, dst, a, s);
+        if (p.M == 5) return dispatch_fwd<5>(p, src, dst, a, s);
+    }
+    set_error("internal: no streaming kernel for M=%d forward=%d", p.M, (int)forward);
+    return ADRT_B200_EINVAL;
+}
+
+}  // namespace adrt_b200

@@ -59,6 +59,74 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
             }
 }
 
+// thread order inside a phase: 0 = ascending tid, 1 = descending (a result that depends on
+// the order means two threads race on a tile cell within one phase)
+int g_order = 0;
+long long g_stream_tiles = 0;   // full tiles run by the streaming programs
+
+// Streaming passes (stream_tile.h): fp32, M = 5 or 6.
+template <typename Prog>
+void run_stream_pass(const plan::Pass &p, const float *src, float *dst, int n, int D, int planes, long long sps, long long dps,
+                     bool image_loader)
+{
+    const size_t cells = (size_t)Prog::G * stile::P + 64;
+    std::vector<tile::Pack<float>> storeA(cells / 4 + 1);
+    float *buf = reinterpret_cast<float *>(storeA.data());
+    std::vector<typename Prog::State> states(Prog::NT);
+    const int e = 1 << p.s;
+    for (int plane = 0; plane < planes; ++plane)
+        for (int by = 0; by < p.grid_y; ++by)
+            for (int bx = 0; bx < p.grid_x; ++bx) {
+                tile::TileCtx c;
+                c.n = n; c.D = D; c.e = e; c.g = by; c.k0 = by / e; c.a_g = by % e;
+                c.d0 = bx * Prog::TD;
+                c.next_g = p.next_g;
+                c.d_need = p.d_need;
+                c.in_pitch = p.in_pitch; c.out_pitch = p.out_pitch;
+                c.q = 0;
+                const int mode = Prog::classify(c);
+                if (mode == tile::TILE_SKIP) continue;
+                const float *sp;
+                if (image_loader) { c.q = plane & 3; sp = src + (long long)(plane >> 2) * sps; }
+                else sp = src + (long long)plane * sps;
+                float *dp = dst + (long long)plane * dps;
+                for (size_t i = 0; i < cells; ++i) buf[i] = 1e30f;
+                if (mode == tile::TILE_ZERO) {
+                    for (int tid = 0; tid < Prog::NT; ++tid) Prog::zero_tile(buf, dp, c, tid);
+                    continue;
+                }
+                ++g_stream_tiles;
+                unsigned long long fake_bar = 0;
+                for (int tid = 0; tid < Prog::NT; ++tid) stile::bulk_init(states[tid].bar, &fake_bar, Prog::NT, tid);
+                for (int ph = 0; ph < Prog::kPhases; ++ph)
+                    for (int i = 0; i < Prog::NT; ++i) {
+                        const int tid = g_order ? Prog::NT - 1 - i : i;
+                        stile::run_phase<Prog>(ph, buf, states[tid], sp, dp, c, tid);
+                    }
+            }
+}
+
+template <int M, bool kForward>
+void run_stream_kinds(const plan::Pass &p, const float *src, float *dst, int n, int D, int planes, long long sps, long long dps)
+{
+    using namespace tile;
+    if (kForward) {
+        if (p.load == LOAD_IMAGE && p.store == STORE_WROWS) run_stream_pass<stile::FwdStream<M, LOAD_IMAGE, STORE_WROWS>>(p, src, dst, n, D, planes, sps, dps, true);
+        else if (p.load == LOAD_IMAGE && p.store == STORE_QCOLS) run_stream_pass<stile::FwdStream<M, LOAD_IMAGE, STORE_QCOLS>>(p, src, dst, n, D, planes, sps, dps, true);
+        else if (p.load == LOAD_WROWS && p.store == STORE_WROWS) run_stream_pass<stile::FwdStream<M, LOAD_WROWS, STORE_WROWS>>(p, src, dst, n, D, planes, sps, dps, false);
+        else run_stream_pass<stile::FwdStream<M, LOAD_WROWS, STORE_QCOLS>>(p, src, dst, n, D, planes, sps, dps, false);
+    }
+}
+
+template <typename T, bool kForward>
+void run_stream(const plan::Pass &p, const T *src, T *dst, int n, int D, int planes, long long sps, long long dps)
+{
+    if constexpr (std::is_same<T, float>::value) {
+        if (p.M == 6) run_stream_kinds<6, kForward>(p, src, dst, n, D, planes, sps, dps);
+        else run_stream_kinds<5, kForward>(p, src, dst, n, D, planes, sps, dps);
+    }
+}
+
 template <typename T, int M, bool kForward>
 void run_kinds(const plan::Pass &p, const T *src, T *dst, int n, int D, int planes, long long sps, long long dps)
 {
@@ -96,6 +164,10 @@ int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1)
         else { src = slot[p.src_buf]; sps = (long long)n * p.in_pitch; }
         if (p.dst_buf < 0) { dst = out; dps = sino; }
         else { dst = slot[p.dst_buf]; dps = (long long)n * p.out_pitch; }
+        if (p.stream) {
+            run_stream<T, kForward>(p, src, dst, n, D, planes, sps, dps);
+            continue;
+        }
         switch (p.M) {
         case 1: run_kinds<T, 1, kForward>(p, src, dst, n, D, planes, sps, dps); break;
         case 2: run_kinds<T, 2, kForward>(p, src, dst, n, D, planes, sps, dps); break;
@@ -112,6 +184,8 @@ int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1)
 }  // namespace
 
 extern "C" {
+void emu_set_order(int order) { g_order = order; }
+long long emu_stream_tiles(void) { return g_stream_tiles; }
 int emu_adrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, true>(in, out, B, n); }
 int emu_adrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run<double, true>(in, out, B, n); }
 int emu_bdrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, false>(in, out, B, n); }
