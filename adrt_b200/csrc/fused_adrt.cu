@@ -156,6 +156,7 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
             a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g; a.d_need = p.d_need;
             a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
             a.planes = nb * q_count;
+            a.x_off = 0;
             a.q_first = q_first; a.q_count = q_count;
             const T *src;
             T *dst;

@@ -107,8 +107,7 @@ inline int tile_td(int M, int store, bool stream = false)
 inline bool use_stream(int M, size_t elem_size, bool forward)
 {
     if (elem_size != 4 || (M != 5 && M != 6)) return false;
-    if (!forward) return false;
-    if (const char *e = getenv("ADRT_B200_STREAM")) return atoi(e) != 0;
+    if (const char *e = getenv(forward ? "ADRT_B200_STREAM" : "ADRT_B200_STREAM_BDRT")) return atoi(e) != 0;
     return true;
 }
 

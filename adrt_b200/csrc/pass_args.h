@@ -12,6 +12,7 @@ struct PassArgs {
     long long in_pitch, out_pitch;
     long long src_plane_stride, dst_plane_stride;  // elements between consecutive planes
     int planes;
+    int x_off;              // first d-tile of this launch (streaming passes launch interior and boundary tiles separately)
     int q_first, q_count;   // image loader: plane -> (image = plane / q_count, quadrant = q_first + plane % q_count)
 };
 

@@ -11,13 +11,13 @@ namespace {
 
 // the barrier-separated phases of a full tile, unrolled at compile time
 template <typename Prog, int PH>
-__device__ __forceinline__ void run_phases(float *buf, typename Prog::State &st, const float *sp, float *dp,
+__device__ __forceinline__ void run_phases(int mode, float *buf, typename Prog::State &st, const float *sp, float *dp,
                                            const tile::TileCtx &c, int tid)
 {
     if constexpr (PH < Prog::kPhases) {
-        Prog::template phase_ct<PH>(buf, st, sp, dp, c, tid);
+        Prog::template phase_ct<PH>(mode, buf, st, sp, dp, c, tid);
         if (Prog::barrier_after(PH)) __syncthreads();
-        run_phases<Prog, PH + 1>(buf, st, sp, dp, c, tid);
+        run_phases<Prog, PH + 1>(mode, buf, st, sp, dp, c, tid);
     }
 }
 
@@ -35,14 +35,14 @@ stream_kernel(const float *__restrict__ src, float *__restrict__ dst, PassArgs a
     c.g = blockIdx.y;
     c.k0 = c.g >> a.loge;
     c.a_g = c.g & (a.e - 1);
-    c.d0 = blockIdx.x * Prog::TD;
+    c.d0 = (blockIdx.x + a.x_off) * Prog::TD;
     c.next_g = a.next_g;
     c.d_need = a.d_need;
     c.in_pitch = a.in_pitch;
     c.out_pitch = a.out_pitch;
     c.q = 0;
     const int mode = Prog::classify(c);
-    if (mode == tile::TILE_SKIP) return;
+    if (!Prog::runs(mode)) return;
     const int tid = threadIdx.x;
     __shared__ unsigned long long bulk_bar;
     typename Prog::State st;
@@ -60,16 +60,20 @@ stream_kernel(const float *__restrict__ src, float *__restrict__ dst, PassArgs a
         if (mode == tile::TILE_ZERO) {
             Prog::zero_tile(buf, dp, c, tid);
         } else {
-            run_phases<Prog, 0>(buf, st, sp, dp, c, tid);
+            run_phases<Prog, 0>(mode, buf, st, sp, dp, c, tid);
         }
     }
 }
 
 template <typename Prog>
-int launch(const float *src, float *dst, const PassArgs &a, int grid_x, int grid_y, cudaStream_t s)
+int launch(const float *src, float *dst, PassArgs a, int x_first, int grid_x, int grid_y, cudaStream_t s)
 {
+    // d-tiles x_first .. x_first + grid_x - 1
+    if (grid_x <= 0) return ADRT_B200_OK;
+    a.x_off = x_first;
     auto kern = stream_kernel<Prog>;
-    const size_t smem = (size_t)Prog::G * stile::P * sizeof(float);
+    // + 32 bytes: the top segment of a transposed step reads a few cells past the last row
+    const size_t smem = (size_t)Prog::G * stile::P * sizeof(float) + 32;
     ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)grid_x, (unsigned)grid_y, (unsigned)(a.planes < 65535 ? a.planes : 65535));
     kern<<<grid, Prog::NT, smem, s>>>(src, dst, a);
@@ -81,10 +85,33 @@ template <int M>
 int dispatch_fwd(const plan::Pass &p, const float *src, float *dst, const PassArgs &a, cudaStream_t s)
 {
     using namespace tile;
-    if (p.load == LOAD_IMAGE && p.store == STORE_WROWS) return launch<stile::FwdStream<M, LOAD_IMAGE, STORE_WROWS>>(src, dst, a, p.grid_x, p.grid_y, s);
-    if (p.load == LOAD_IMAGE && p.store == STORE_QCOLS) return launch<stile::FwdStream<M, LOAD_IMAGE, STORE_QCOLS>>(src, dst, a, p.grid_x, p.grid_y, s);
-    if (p.load == LOAD_WROWS && p.store == STORE_WROWS) return launch<stile::FwdStream<M, LOAD_WROWS, STORE_WROWS>>(src, dst, a, p.grid_x, p.grid_y, s);
-    if (p.load == LOAD_WROWS && p.store == STORE_QCOLS) return launch<stile::FwdStream<M, LOAD_WROWS, STORE_QCOLS>>(src, dst, a, p.grid_x, p.grid_y, s);
+    if (p.load == LOAD_IMAGE && p.store == STORE_WROWS) return launch<stile::FwdStream<M, LOAD_IMAGE, STORE_WROWS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
+    if (p.load == LOAD_IMAGE && p.store == STORE_QCOLS) return launch<stile::FwdStream<M, LOAD_IMAGE, STORE_QCOLS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
+    if (p.load == LOAD_WROWS && p.store == STORE_WROWS) return launch<stile::FwdStream<M, LOAD_WROWS, STORE_WROWS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
+    if (p.load == LOAD_WROWS && p.store == STORE_QCOLS) return launch<stile::FwdStream<M, LOAD_WROWS, STORE_QCOLS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
+    set_error("internal: bad streaming pass kinds %d/%d", p.load, p.store);
+    return ADRT_B200_EINVAL;
+}
+
+// interior tiles and the tiles that reach offset D run as two launches (see BwdStream::phase_ct)
+template <int M, int LOADK, int STOREK>
+int launch_bwd(const plan::Pass &p, const float *src, float *dst, const PassArgs &a, cudaStream_t s)
+{
+    int xm = stile::BwdStream<M, LOADK, STOREK, false>::first_masked_tile(a.D);
+    if (xm > p.grid_x) xm = p.grid_x;
+    int rc = launch<stile::BwdStream<M, LOADK, STOREK, false>>(src, dst, a, 0, xm, p.grid_y, s);
+    if (rc != ADRT_B200_OK) return rc;
+    return launch<stile::BwdStream<M, LOADK, STOREK, true>>(src, dst, a, xm, p.grid_x - xm, p.grid_y, s);
+}
+
+template <int M>
+int dispatch_bwd(const plan::Pass &p, const float *src, float *dst, const PassArgs &a, cudaStream_t s)
+{
+    using namespace tile;
+    if (p.load == LOAD_QCOLS && p.store == STORE_WROWS) return launch_bwd<M, LOAD_QCOLS, STORE_WROWS>(p, src, dst, a, s);
+    if (p.load == LOAD_QCOLS && p.store == STORE_QCOLS) return launch_bwd<M, LOAD_QCOLS, STORE_QCOLS>(p, src, dst, a, s);
+    if (p.load == LOAD_WROWS && p.store == STORE_WROWS) return launch_bwd<M, LOAD_WROWS, STORE_WROWS>(p, src, dst, a, s);
+    if (p.load == LOAD_WROWS && p.store == STORE_QCOLS) return launch_bwd<M, LOAD_WROWS, STORE_QCOLS>(p, src, dst, a, s);
     set_error("internal: bad streaming pass kinds %d/%d", p.load, p.store);
     return ADRT_B200_EINVAL;
 }
@@ -96,6 +123,10 @@ int launch_stream_pass(const plan::Pass &p, bool forward, const float *src, floa
     if (forward) {
         if (p.M == 6) return dispatch_fwd<6>(p, src, dst, a, s);
         if (p.M == 5) return dispatch_fwd<5>(p, src, dst, a, s);
+    }
+    if (!forward) {
+        if (p.M == 6) return dispatch_bwd<6>(p, src, dst, a, s);
+        if (p.M == 5) return dispatch_bwd<5>(p, src, dst, a, s);
     }
     set_error("internal: no streaming kernel for M=%d forward=%d", p.M, (int)forward);
     return ADRT_B200_EINVAL;

@@ -59,6 +59,14 @@ using tile::STORE_WROWS;
 using tile::STORE_QCOLS;
 using tile::fwd_row_skew;
 
+// iterations of a step's main loop unrolled together: the per-thread history lives in registers, so
+// the loop must be unrolled enough for the compiler to rename it instead of moving it, but the whole
+// kernel should stay inside the instruction cache (several CTAs in different phases share an SM)
+#ifndef ADRT_STREAM_UNROLL
+#define ADRT_STREAM_UNROLL 3
+#endif
+constexpr int kStreamUnroll = ADRT_STREAM_UNROLL;
+
 constexpr int V = 4;
 constexpr int XW = 288;          // offsets per tile row
 constexpr int P = 292;           // row pitch (floats): 4 mod 32
@@ -145,6 +153,17 @@ ADRT_HD void bulk_arrive_wait(BulkBar &b, int my_bytes)
 #endif
 }
 
+// one 32-byte sector (8 consecutive columns of the public layout)
+ADRT_HD void store8(float *p, const float (&v)[8])
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+#else
+    for (int i = 0; i < 8; ++i) p[i] = v[i];
+#endif
+}
+
 ADRT_HD void copy4_async(float *dst_smem, const float *src)
 {
 #ifdef __CUDA_ARCH__
@@ -161,11 +180,15 @@ ADRT_HD void copy_async_wait()
 #endif
 }
 
-template <int M> struct SGeo {
+// The radix-8 step is the one next to the public layout (last forward step, last transposed step):
+// its 8 outputs are 8 consecutive columns = one 32-byte sector per offset, written straight from
+// registers.  Forward: step 1 radix 2^(M-3), step 2 radix 8.  Transposed: step A (the transpose of
+// step 2) radix 2^(M-3), step B (the transpose of step 1) radix 8.
+template <int M, bool kFwd> struct SGeo {
     static_assert(M == 5 || M == 6, "streaming passes fuse 5 or 6 stages");
     static constexpr int G = 1 << M;
-    static constexpr int LOGR1 = 3, R1 = 8;
-    static constexpr int LOGR2 = M - 3, R2 = 1 << LOGR2;
+    static constexpr int LOGR1 = kFwd ? M - 3 : 3, R1 = 1 << LOGR1;
+    static constexpr int LOGR2 = kFwd ? 3 : M - 3, R2 = 1 << LOGR2;
     // step 1 covers the whole row, step 2 the offsets [X2, XW)
     static constexpr int SEG1 = 36, NSEG1 = 8;
     static constexpr int SEG2 = (M == 6) ? 28 : 36, NSEG2 = (M == 6) ? 8 : 7;
@@ -173,14 +196,14 @@ template <int M> struct SGeo {
 };
 
 template <int M, int STOREK> struct STileTD {
-    static constexpr int value = XW - SGeo<M>::X2 - (STOREK == STORE_WROWS ? 4 : 0);
+    static constexpr int value = XW - SGeo<M, true>::X2 - (STOREK == STORE_WROWS ? 4 : 0);
 };
 
 // Row order.  kRev = false: leaf j sits in tile row j and output angle A ends in
 // row (A % R2) * R1 + A / R2.  kRev = true: leaf j = k0*R1 + jj sits in row
 // jj*R2 + k0 and output angle A ends in row A.
-template <int M, bool kRev> struct RowMap {
-    static constexpr int R1 = SGeo<M>::R1, R2 = SGeo<M>::R2;
+template <int M, bool kRev, bool kFwd> struct RowMap {
+    static constexpr int R1 = SGeo<M, kFwd>::R1, R2 = SGeo<M, kFwd>::R2;
     ADRT_HD static int leaf_row(int j) { return kRev ? (j % R1) * R2 + j / R1 : j; }
     ADRT_HD static int out_row(int A) { return kRev ? A : (A % R2) * R1 + A / R2; }
     // storage skew of output angle A (multiple of 4)
@@ -264,8 +287,8 @@ template <int LOGR> struct FwdStepState {
 
 // state of the two steps of a pass (only one of them is live at any time)
 template <int M> struct FwdState {
-    FwdStepState<SGeo<M>::LOGR1> s1;
-    FwdStepState<SGeo<M>::LOGR2> s2;
+    FwdStepState<SGeo<M, true>::LOGR1> s1;
+    FwdStepState<SGeo<M, true>::LOGR2> s2;
     BulkBar bar;
 };
 
@@ -314,7 +337,7 @@ template <int LOGR, bool kShift, int NIT>
 ADRT_HD void fwd_step_main(float *buf, int base, int stride, int p, int c0, FwdStepState<LOGR> &st)
 {
     constexpr int R = 1 << LOGR;
-#pragma unroll
+#pragma unroll kStreamUnroll
     for (int it = 0; it < NIT; ++it) {
         float cur[R][4], out[R][4];
 #pragma unroll
@@ -344,7 +367,7 @@ ADRT_HD void fwd_step_main_direct(const float *buf, int base, int stride, int p,
                                   float *o, long long n1, int dmax)
 {
     constexpr int R = 1 << LOGR;
-#pragma unroll
+#pragma unroll kStreamUnroll
     for (int it = 0; it < NIT; ++it) {
         float cur[R][4], out[R][4];
 #pragma unroll
@@ -356,13 +379,11 @@ ADRT_HD void fwd_step_main_direct(const float *buf, int base, int stride, int p,
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (4 * it + i < dmax) {
+                static_assert(R == 8, "direct stores write 8 columns");
+                float v[8];
 #pragma unroll
-                for (int h = 0; h < R / 4; ++h) {
-                    F4 v;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v.v[k] = out[4 * h + k][i];
-                    *reinterpret_cast<F4 *>(o + (long long)(4 * it + i) * n1 + 4 * h) = v;
-                }
+                for (int k = 0; k < 8; ++k) v[k] = out[k][i];
+                store8(o + (long long)(4 * it + i) * n1, v);
             }
         }
     }
@@ -372,10 +393,10 @@ ADRT_HD void fwd_step_main_direct(const float *buf, int base, int stride, int p,
 template <int M, bool kRev>
 ADRT_HD bool fwd_s1_map(int tid, int &base, int &c0, bool &warm)
 {
-    typedef SGeo<M> Geo;
+    typedef SGeo<M, true> Geo;
     const int grp = tid >> 3, seg = tid & 7;
     if (grp >= Geo::G / Geo::R1) return false;
-    base = RowMap<M, kRev>::s1_base(grp);
+    base = RowMap<M, kRev, true>::s1_base(grp);
     c0 = seg * Geo::SEG1;
     warm = seg > 0;
     return true;
@@ -384,11 +405,11 @@ ADRT_HD bool fwd_s1_map(int tid, int &base, int &c0, bool &warm)
 template <int M, bool kRev>
 ADRT_HD bool fwd_s2_map(int tid, int &base, int &p, int &c0)
 {
-    typedef SGeo<M> Geo;
+    typedef SGeo<M, true> Geo;
     const int grp = tid >> 3, seg = tid & 7;
     if (grp >= Geo::G / Geo::R2 || seg >= Geo::NSEG2) return false;
     p = grp;    // one block group per tile: the butterfly's base angle is its index
-    base = RowMap<M, kRev>::s2_base(p);
+    base = RowMap<M, kRev, true>::s2_base(p);
     c0 = Geo::X2 + seg * Geo::SEG2;
     return true;
 }
@@ -405,7 +426,7 @@ ADRT_HD bool fwd_s2_map(int tid, int &base, int &p, int &c0)
 template <int M, bool kRev, int LH, int NT>
 ADRT_HD void fwd_load_wrows(float *buf, const float *src_plane, const TileCtx &c, int tid, BulkBar &bar)
 {
-    constexpr int G = SGeo<M>::G;
+    constexpr int G = SGeo<M, true>::G;
     static_assert(G <= NT, "one row per thread");
     const int pitch = (int)c.in_pitch;
     int my_bytes = 0;
@@ -416,7 +437,7 @@ ADRT_HD void fwd_load_wrows(float *buf, const float *src_plane, const TileCtx &c
         const float *row = src_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.in_pitch;
         const int dbase = c.d0 - LH - c.a_g * j;
         const int gbase = dbase + fwd_row_skew(c.a_g, j);
-        float *dst = buf + RowMap<M, kRev>::leaf_row(j) * P;
+        float *dst = buf + RowMap<M, kRev, true>::leaf_row(j) * P;
         int xlo = gbase < 0 ? -gbase : 0;            // first tile column whose position exists
         int xhi = pitch - gbase;                      // first tile column beyond the pitch
         if (xlo > XW) xlo = XW;
@@ -441,7 +462,7 @@ ADRT_HD void fwd_load_wrows(float *buf, const float *src_plane, const TileCtx &c
 template <int M, bool kRev, int LH, int NWARP>
 ADRT_HD void fwd_load_image(float *buf, const float *img, const TileCtx &c, int tid)
 {
-    constexpr int G = SGeo<M>::G;
+    constexpr int G = SGeo<M, true>::G;
     const int warp = tid >> 5, lane = tid & 31;
     const int n = c.n;
     const int dbase = c.d0 - LH;        // multiple of 4, like n: a 4-chunk lies inside [0, n) or outside
@@ -463,7 +484,7 @@ ADRT_HD void fwd_load_image(float *buf, const float *img, const TileCtx &c, int 
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                float *dst = buf + RowMap<M, kRev>::leaf_row(j0 + u) * P;
+                float *dst = buf + RowMap<M, kRev, true>::leaf_row(j0 + u) * P;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int d = dbase + (k * 32 + lane) * V;
@@ -514,7 +535,7 @@ ADRT_HD void fwd_load_image(float *buf, const float *img, const TileCtx &c, int 
                         F4 w;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) w.v[i] = in ? v[u][i].v[t] : fill;
-                        *reinterpret_cast<F4 *>(buf + RowMap<M, kRev>::leaf_row(4 * rg + t) * P + 4 * ch) = w;
+                        *reinterpret_cast<F4 *>(buf + RowMap<M, kRev, true>::leaf_row(4 * rg + t) * P + 4 * ch) = w;
                     }
                 }
             }
@@ -580,7 +601,7 @@ ADRT_HD void fwd_store_row_skewed(const float *b, float *row, const TileCtx &c, 
 template <int M, bool kRev, int LH, int TD, int NWARP>
 ADRT_HD void fwd_store_wrows(const float *buf, float *dst_plane, const TileCtx &c, bool zero, int tid)
 {
-    constexpr int G = SGeo<M>::G;
+    constexpr int G = SGeo<M, true>::G;
     const int warp = tid >> 5, lane = tid & 31;
     for (int p = warp; p < G; p += NWARP) {
         float *row = dst_plane + ((long long)c.g * G + p) * c.out_pitch;
@@ -588,7 +609,7 @@ ADRT_HD void fwd_store_wrows(const float *buf, float *dst_plane, const TileCtx &
         int lim = c.n + ang;
         if (lim > c.D) lim = c.D;
         const int s = c.next_g ? fwd_row_skew(ang, c.k0 & (c.next_g - 1)) : 0;
-        const float *b = buf + RowMap<M, kRev>::out_row(p) * P - RowMap<M, kRev>::out_skew(p);
+        const float *b = buf + RowMap<M, kRev, true>::out_row(p) * P - RowMap<M, kRev, true>::out_skew(p);
         switch (s) {
         case 0: fwd_store_row_aligned<LH, TD>(b, row, c, lim, zero, lane); break;
         case 1: fwd_store_row_skewed<LH, TD, 1>(b, row, c, lim, zero, lane); break;
@@ -602,7 +623,7 @@ ADRT_HD void fwd_store_wrows(const float *buf, float *dst_plane, const TileCtx &
 template <int M, bool kRev, int TD, int NWARP>
 ADRT_HD void store_qcols(const float *buf, float *dst_plane, const TileCtx &c, int xoff, bool zero, int tid)
 {
-    constexpr int G = SGeo<M>::G;
+    constexpr int G = SGeo<M, true>::G;
     constexpr int NIT = (TD + NWARP * V - 1) / (NWARP * V);
     const int warp = tid >> 5, lane = tid & 31;
     const int cols = G < c.n ? G : c.n;
@@ -610,7 +631,7 @@ ADRT_HD void store_qcols(const float *buf, float *dst_plane, const TileCtx &c, i
     const long long n1 = c.n;
     for (int p = lane; p < cols; p += 32) {
         float *o = dst_plane + (long long)(c.d0 + warp * V) * n1 + c.g * G + p;
-        const float *b = buf + RowMap<M, kRev>::out_row(p) * P - RowMap<M, kRev>::out_skew(p) + xoff + warp * V;
+        const float *b = buf + RowMap<M, kRev, true>::out_row(p) * P - RowMap<M, kRev, true>::out_skew(p) + xoff + warp * V;
         const long long ostep = (long long)NWARP * V * n1;
 #pragma unroll 3
         for (int it = 0; it < NIT; ++it, o += ostep, b += NWARP * V) {
@@ -644,10 +665,11 @@ ADRT_HD void store_qcols(const float *buf, float *dst_plane, const TileCtx &c, i
 // with a CTA barrier after each.
 template <int M, int LOADK, int STOREK>
 struct FwdStream {
-    typedef SGeo<M> Geo;
+    typedef SGeo<M, true> Geo;
     static constexpr int G = Geo::G;
     static constexpr bool kRev = (STOREK == STORE_QCOLS);
     static constexpr bool kImage = (LOADK == LOAD_IMAGE);
+    ADRT_HD static constexpr bool runs(int mode) { return mode != tile::TILE_SKIP; }   // forward tiles are never masked
     // passes that store the public layout write it from the registers of step 2 (no store phase)
     static constexpr bool kDirect = (STOREK == STORE_QCOLS);
     static constexpr int kPhases = kDirect ? 5 : 6;
@@ -683,9 +705,10 @@ struct FwdStream {
     }
 
     template <int PH>
-    ADRT_HD static void phase_ct(float *buf, State &st, const float *src, float *dst, const TileCtx &c, int tid)
+    ADRT_HD static void phase_ct(int mode, float *buf, State &st, const float *src, float *dst, const TileCtx &c, int tid)
     {
-        typedef RowMap<M, kRev> RM;
+        (void)mode;
+        typedef RowMap<M, kRev, true> RM;
         if constexpr (PH == 0) {
             if (LOADK == LOAD_IMAGE) fwd_load_image<M, kRev, LH, NWARP>(buf, src, c, tid);
             else fwd_load_wrows<M, kRev, LH, NT>(buf, src, c, tid, st.bar);
@@ -715,12 +738,455 @@ struct FwdStream {
     }
 };
 
+// ===========================================================================
+// transposed (bdrt) butterfly: exact transpose of FwdBfly
+// ===========================================================================
+//   g(L, 2k,   a)[x] = g(L+1, k, 2a)[x]     + g(L+1, k, 2a+1)[x]
+//   g(L, 2k+1, a)[x] = g(L+1, k, 2a)[x + a] + g(L+1, k, 2a+1)[x + a + 1]
+// (first operand = even parent angle, adrt_cdefs_bdrt.hpp:216-237).  The shifts look AHEAD,
+// so the segment is walked downwards and the history is the previous, higher 4-vector.
+// Masked instantiation (tiles that reach offset D): an operand read at a position at or beyond
+// the end `thr` of its node is absent and acts as +0.0 (first operand) / -0.0 (second operand),
+// the copy-vs-add rule of adrt_cdefs_bdrt.hpp:96-109.
+template <int LOGR> struct BwdBfly {
+    static constexpr int R = 1 << LOGR;
+    float hist[LOGR][R][4];   // hist[L]: higher 4-vector of the level-(L+1) nodes; only the first a+b entries are live
+
+    ADRT_HD void clear()
+    {
+#pragma unroll
+        for (int l = 0; l < LOGR; ++l)
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hist[l][k][i] = 0.0f;
+    }
+
+    // thr0 + k * thrk = end (in the coordinates of x0) of node k of level L+1
+    template <int L, bool kMask>
+    ADRT_HD void level(const float (&cur)[R][4], float (&nxt)[R][4], int x0, int thr0, int thrk)
+    {
+        constexpr int nodes1 = R >> (L + 1), angles = 1 << L, angles1 = 2 << L;
+#pragma unroll
+        for (int k = 0; k < nodes1; ++k) {
+            const int thr = kMask ? thr0 + k * thrk : 0;
+#pragma unroll
+            for (int a = 0; a < angles; ++a) {
+                const int iA = k * angles1 + 2 * a, iB = iA + 1;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float vA = cur[iA][i], vB = cur[iB][i];
+                    if (kMask && x0 + i >= thr) { vA = 0.0f; vB = -0.0f; }
+                    nxt[(2 * k) * angles + a][i] = vA + vB;
+                    const int jA = i + a, jB = i + a + 1;
+                    float wA = jA < 4 ? cur[iA][jA] : hist[L][iA][jA - 4];
+                    float wB = jB < 4 ? cur[iB][jB] : hist[L][iB][jB - 4];
+                    if (kMask && x0 + jA >= thr) wA = 0.0f;
+                    if (kMask && x0 + jB >= thr) wB = -0.0f;
+                    nxt[(2 * k + 1) * angles + a][i] = wA + wB;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hist[L][k][i] = cur[k][i];
+    }
+
+    // par[q] = the 4 offsets [x0, x0+4) of parent angle q; out[jj] = the same offsets of child jj
+    // (each in its own frame).  thr_top = end of the parents; a node k of level L ends at
+    // thr_top + k * 2^L * thr_leaf.
+    template <bool kMask>
+    ADRT_HD void iterate(const float (&par)[R][4], float (&out)[R][4], int x0, int thr_top, int thr_leaf)
+    {
+        if constexpr (LOGR == 1) {
+            level<0, kMask>(par, out, x0, thr_top, 2 * thr_leaf);
+        } else if constexpr (LOGR == 2) {
+            float t[R][4];
+            level<1, kMask>(par, t, x0, thr_top, 4 * thr_leaf);
+            level<0, kMask>(t, out, x0, thr_top, 2 * thr_leaf);
+        } else {
+            float t[R][4], u[R][4];
+            level<2, kMask>(par, t, x0, thr_top, 8 * thr_leaf);
+            level<1, kMask>(t, u, x0, thr_top, 4 * thr_leaf);
+            level<0, kMask>(u, out, x0, thr_top, 2 * thr_leaf);
+        }
+    }
+};
+
+template <int LOGR> struct BwdStepState {
+    BwdBfly<LOGR> b;
+    float nxt[1 << LOGR][4];
+};
+
+template <int M> struct BwdState {
+    BwdStepState<SGeo<M, false>::LOGR2> sa;   // first transposed step: radix 2^(M-3), local stages M-1 .. 3
+    BwdStepState<SGeo<M, false>::LOGR1> sb;   // second: radix 8, local stages 2 .. 0
+    BulkBar bar;
+};
+
+// Storage conventions of the transposed tile (mirror image of the forward ones):
+//   parents of step A      : logical column x at x (as loaded)
+//   children of step A     : child (block jj, angle p), logical column c = x - p*jj, at c + floor4(p*jj)
+//                            = x - ((p*jj) & 3): mixed-width stores (128 / 64 / 32 bit by jj), never
+//                            above the position its row was read from and at most 3 below it
+//   step B reads parent q of block k0 at c + floor4(q*k0) (aligned) and writes leaf jj of block k0 at
+//   c + floor4(jj*k0) (aligned, the very positions it read from row jj)
+template <int R, bool kB>
+ADRT_HD void bwd_load_parents(const float *buf, int base, int stride, int k0, int x, float (&par)[R][4])
+{
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        const float *rp = buf + (base + q * stride) * P + x + (kB ? ((q * k0) & ~3) : 0);
+        const F4 v = *reinterpret_cast<const F4 *>(rp);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) par[q][i] = v.v[i];
+    }
+}
+
+template <int R, bool kB>
+ADRT_HD void bwd_store_children(float *buf, int base, int stride, int pk, int x, const float (&out)[R][4])
+{
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+        float *rp = buf + (base + jj * stride) * P;
+        if (kB) {
+            F4 v;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v.v[i] = out[jj][i];
+            *reinterpret_cast<F4 *>(rp + x + ((jj * pk) & ~3)) = v;
+        } else {
+            const int col = x - ((pk * jj) & 3);     // may be negative only for x = 0: those columns are nobody's
+            if ((jj & 3) == 0) {
+                F4 v;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v.v[i] = out[jj][i];
+                *reinterpret_cast<F4 *>(rp + col) = v;
+            } else if ((jj & 1) == 0) {
+                F2 v0, v1;
+                v0.v[0] = out[jj][0]; v0.v[1] = out[jj][1]; v1.v[0] = out[jj][2]; v1.v[1] = out[jj][3];
+                if (col >= 0) *reinterpret_cast<F2 *>(rp + col) = v0;
+                *reinterpret_cast<F2 *>(rp + col + 2) = v1;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i == 3 || col + i >= 0) rp[col + i] = out[jj][i];
+            }
+        }
+    }
+}
+
+// Transposed step for the segment [c0, c0 + 4*NIT) of one butterfly, walked downwards.
+//   kB = false: step A (group base angle pk = p);  kB = true: step B (pk = k0, block index)
+//   warm: the 8 columns above the segment exist (false for the segment that ends the row)
+template <int LOGR, bool kB, int NIT>
+ADRT_HD void bwd_step_prologue(const float *buf, int base, int stride, int pk, int c0, bool warm, BwdStepState<LOGR> &st)
+{
+    constexpr int R = 1 << LOGR;
+    st.b.clear();
+    const int top = c0 + 4 * NIT;
+    if (warm) {
+        float par[R][4], out[R][4];
+#pragma unroll
+        for (int w = 1; w >= 0; --w) {
+            bwd_load_parents<R, kB>(buf, base, stride, pk, top + 4 * w, par);
+            st.b.template iterate<false>(par, out, 0, 0, 0);
+        }
+    }
+    bwd_load_parents<R, kB>(buf, base, stride, pk, top - 4, st.nxt);
+}
+
+template <int LOGR, bool kB, bool kMask, int NIT>
+ADRT_HD void bwd_step_main(float *buf, int base, int stride, int pk, int c0, BwdStepState<LOGR> &st, int thr_top, int thr_leaf)
+{
+    constexpr int R = 1 << LOGR;
+#pragma unroll kStreamUnroll
+    for (int it = NIT - 1; it >= 0; --it) {
+        float cur[R][4], out[R][4];
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[q][i] = st.nxt[q][i];
+        if (it > 0) bwd_load_parents<R, kB>(buf, base, stride, pk, c0 + 4 * (it - 1), st.nxt);
+        st.b.template iterate<kMask>(cur, out, c0 + 4 * it, thr_top, thr_leaf);
+        bwd_store_children<R, kB>(buf, base, stride, pk, c0 + 4 * it, out);
+    }
+}
+
+// Step B of a pass that stores the public layout: the 8 leaves of a butterfly are 8 consecutive
+// columns; `o` points at (offset of tile column c0, first column), dmax = offsets from there to D.
+template <int LOGR, bool kMask, int NIT>
+ADRT_HD void bwd_step_main_direct(const float *buf, int base, int stride, int pk, int c0, BwdStepState<LOGR> &st,
+                                  int thr_top, int thr_leaf, float *o, long long n1, int dmax)
+{
+    constexpr int R = 1 << LOGR;
+#pragma unroll kStreamUnroll
+    for (int it = NIT - 1; it >= 0; --it) {
+        float cur[R][4], out[R][4];
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[q][i] = st.nxt[q][i];
+        if (it > 0) bwd_load_parents<R, true>(buf, base, stride, pk, c0 + 4 * (it - 1), st.nxt);
+        st.b.template iterate<kMask>(cur, out, c0 + 4 * it, thr_top, thr_leaf);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (4 * it + i < dmax) {
+                static_assert(R == 8, "direct stores write 8 columns");
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = out[k][i];
+                store8(o + (long long)(4 * it + i) * n1, v);
+            }
+        }
+    }
+}
+
+// ---- transposed loaders ---------------------------------------------------------------
+// Public layout: tile row of parent angle A <- column g*G + A, tile column x <- offset d0 + x
+// (zero from offset D on).  4 x 4 register transposes as in fwd_load_image.
+template <int M, bool kRev, int NWARP>
+ADRT_HD void bwd_load_qcols(float *buf, const float *src_plane, const TileCtx &c, int tid)
+{
+    constexpr int G = SGeo<M, false>::G;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int n = c.n;
+    const int cols = G < n ? G : n;
+    const int rg_lo = (lane & 1) | (((lane >> 3) & 3) << 1), ch_lo = (lane >> 1) & 3;
+    const int nblk = (cols / 32) * (NVEC / 4);
+    const float *ib = src_plane + (long long)c.d0 * n + c.g * G;
+    for (int blk0 = warp; blk0 < nblk; blk0 += 3 * NWARP) {
+        F4 v[3][4];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int blk = blk0 + u * NWARP;
+            const int rg = (blk / (NVEC / 4)) * 8 + rg_lo, ch = (blk % (NVEC / 4)) * 4 + ch_lo;
+            if (blk < nblk) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (c.d0 + 4 * ch + i < c.D) {
+                        v[u][i] = *reinterpret_cast<const F4 *>(ib + (long long)(4 * ch + i) * n + 4 * rg);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) v[u][i].v[t] = 0.0f;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int blk = blk0 + u * NWARP;
+            if (blk < nblk) {
+                const int rg = (blk / (NVEC / 4)) * 8 + rg_lo, ch = (blk % (NVEC / 4)) * 4 + ch_lo;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    F4 w;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w.v[i] = v[u][i].v[t];
+                    *reinterpret_cast<F4 *>(buf + RowMap<M, kRev, false>::out_row(4 * rg + t) * P + 4 * ch) = w;
+                }
+            }
+        }
+    }
+}
+
+// Workspace rows (dense, pitch round4(D), offsets >= D never written): parent A <- row g*G + A,
+// columns [d0, d0 + XW): one bulk copy of the whole chunks below D, scalar tail, zeros above.
+template <int M, bool kRev, int NT>
+ADRT_HD void bwd_load_wrows(float *buf, const float *src_plane, const TileCtx &c, int tid, BulkBar &bar)
+{
+    constexpr int G = SGeo<M, false>::G;
+    static_assert(G <= NT, "one row per thread");
+    int my_bytes = 0;
+    bulk_fence();
+    if (tid < G) {
+        const int A = tid;
+        const float *row = src_plane + ((long long)c.g * G + A) * c.in_pitch + c.d0;
+        float *dst = buf + RowMap<M, kRev, false>::out_row(A) * P;
+        int xv = c.D - c.d0;             // columns that exist
+        if (xv > XW) xv = XW;
+        if (xv < 0) xv = 0;
+        const int xb = xv & ~3;          // whole chunks
+        if (xb > 0) {
+            bulk_load(bar, dst, row, xb * 4);
+            my_bytes = xb * 4;
+        }
+        if (xb < XW) {
+            for (int x = xb; x < XW; ++x) dst[x] = x < xv ? row[x] : 0.0f;
+        }
+    }
+    bulk_arrive_wait(bar, my_bytes);
+}
+
+// ---- transposed stores ----------------------------------------------------------------
+// Workspace row of leaf j: (k0*G + j)*e + a_g; tile column xc is offset d0 - a_g*j + xc.  The tile owns
+// the aligned chunks [ceil4(dbase), ceil4(dbase) + TD) of the row; Q = (a_g*j) & 3 is the residue of the
+// tile-side window (see fused_tile.h bwd_store_row).  `b` already includes the leaf's storage skew.
+template <int TD, int Q>
+ADRT_HD void bwd_store_row(const float *b, float *row, const TileCtx &c, int dbase, bool zero, int lane)
+{
+#pragma unroll
+    for (int k = 0; k < (TD / V + 31) / 32; ++k) {
+        const int xa = (k * 32 + lane) * V;
+        const int gp = dbase + Q + xa;
+        if (xa < TD && gp + V > 0 && gp < c.D) {
+            float v[V];
+            if (zero) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = 0.0f;
+            } else {
+                tile::load_window<float, V, Q>(b + xa, v);
+            }
+            if (gp >= 0 && gp + V <= c.D) {
+                tile::store_chunk<float>(row + gp, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    if (gp + i >= 0 && gp + i < c.D) row[gp + i] = v[i];
+            }
+        }
+    }
+}
+
+template <int M, bool kRev, int TD, int NWARP>
+ADRT_HD void bwd_store_wrows(const float *buf, float *dst_plane, const TileCtx &c, bool zero, int tid)
+{
+    constexpr int G = SGeo<M, false>::G, R1 = SGeo<M, false>::R1;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < G; j += NWARP) {
+        float *row = dst_plane + ((long long)(c.k0 * G + j) * c.e + c.a_g) * c.out_pitch;
+        const int dbase = c.d0 - c.a_g * j;
+        const int k0 = j / R1, jj = j % R1;
+        const float *b = buf + RowMap<M, kRev, false>::leaf_row(j) * P + ((jj * k0) & ~3);
+        switch ((c.a_g * j) & 3) {
+        case 0: bwd_store_row<TD, 0>(b, row, c, dbase, zero, lane); break;
+        case 1: bwd_store_row<TD, 1>(b, row, c, dbase, zero, lane); break;
+        case 2: bwd_store_row<TD, 2>(b, row, c, dbase, zero, lane); break;
+        default: bwd_store_row<TD, 3>(b, row, c, dbase, zero, lane); break;
+        }
+    }
+}
+
+// thread -> (butterfly, segment)
+template <int M, bool kRev>
+ADRT_HD bool bwd_sa_map(int tid, int &base, int &p, int &c0, bool &warm)
+{
+    typedef SGeo<M, false> Geo;
+    const int grp = tid >> 3, seg = tid & 7;
+    if (grp >= Geo::G / Geo::R2) return false;
+    p = grp;
+    base = RowMap<M, kRev, false>::s2_base(p);
+    c0 = seg * Geo::SEG1;        // step A walks the whole row: 8 segments of 36
+    warm = seg < 7;
+    return true;
+}
+
+template <int M, bool kRev>
+ADRT_HD bool bwd_sb_map(int tid, int &base, int &k0, int &c0)
+{
+    typedef SGeo<M, false> Geo;
+    const int grp = tid >> 3, seg = tid & 7;
+    if (grp >= Geo::G / Geo::R1 || seg >= Geo::NSEG2) return false;
+    k0 = grp;
+    base = RowMap<M, kRev, false>::s1_base(k0);
+    c0 = seg * Geo::SEG2;        // step B produces the columns [0, TD): NSEG2 segments of SEG2
+    return true;
+}
+
+// ===========================================================================
+// tile program (transposed)
+// ===========================================================================
+// Phases: 0 load | 1 step-A prologue | 2 step-A main | 3 step-B prologue | 4 step-B main | 5 store
+template <int M, int LOADK, int STOREK, bool kMaskTiles>
+struct BwdStream {
+    typedef SGeo<M, false> Geo;
+    static constexpr int G = Geo::G;
+    // parents arrive in natural row order from the public layout (transposing load); workspace rows may
+    // be placed anywhere, and then the leaves come out in natural order for the public-layout store
+    static constexpr bool kRev = (LOADK == LOAD_QCOLS);
+    static constexpr bool kImage = false;
+    // the masked program also writes the all-zero tiles beyond offset D
+    ADRT_HD static constexpr bool runs(int mode) { return kMaskTiles ? (mode == tile::TILE_FULL_MASKED || mode == tile::TILE_ZERO) : mode == tile::TILE_FULL; }
+    static constexpr bool kDirect = (STOREK == STORE_QCOLS);
+    static constexpr int kPhases = kDirect ? 5 : 6;
+    static constexpr int TD = STileTD<M, STOREK>::value;
+    static constexpr int TDB = XW - Geo::X2;            // columns step B produces (TD, or TD + 4 for workspace stores)
+    static constexpr int NT = (LOADK == LOAD_QCOLS) ? 128 : 64;
+    static constexpr int NWARP = NT / 32;
+    static constexpr int MIN_CTAS = (M == 6 || LOADK == LOAD_QCOLS) ? 3 : 6;
+    typedef BwdState<M> State;
+    ADRT_HD static constexpr bool barrier_after(int ph) { return !(kDirect && ph == 3); }
+
+    ADRT_HD static int classify(const TileCtx &c)
+    {
+        if (c.d0 >= c.d_need + c.a_g * (G - 1)) return tile::TILE_SKIP;
+        if (c.d0 >= c.D) return STOREK == STORE_QCOLS ? tile::TILE_SKIP : tile::TILE_ZERO;
+        if (c.d0 + XW + 8 > c.D) return tile::TILE_FULL_MASKED;
+        return tile::TILE_FULL;
+    }
+
+    ADRT_HD static void zero_tile(float *buf, float *dst, const TileCtx &c, int tid)
+    {
+        bwd_store_wrows<M, kRev, TD, NWARP>(buf, dst, c, true, tid);
+    }
+
+    template <int PH, bool kMask>
+    ADRT_HD static void phase_m(float *buf, State &st, const float *src, float *dst, const TileCtx &c, int tid)
+    {
+        typedef RowMap<M, kRev, false> RM;
+        const int dt = c.D - c.d0;
+        if constexpr (PH == 0) {
+            if (LOADK == LOAD_QCOLS) bwd_load_qcols<M, kRev, NWARP>(buf, src, c, tid);
+            else bwd_load_wrows<M, kRev, NT>(buf, src, c, tid, st.bar);
+        } else if constexpr (PH == 1 || PH == 2) {
+            int base, p, c0;
+            bool warm;
+            if (!bwd_sa_map<M, kRev>(tid, base, p, c0, warm)) return;
+            // node k of a level whose nodes span 2^L step leaves ends at dt + a_g*(8*2^L*k) + p*(2^L*k):
+            // per step leaf (= a block of 8 tile leaves) a_g*8 + p
+            if constexpr (PH == 1) bwd_step_prologue<Geo::LOGR2, false, Geo::SEG1 / V>(buf, base, RM::s2_stride, p, c0, warm, st.sa);
+            else bwd_step_main<Geo::LOGR2, false, kMask, Geo::SEG1 / V>(buf, base, RM::s2_stride, p, c0, st.sa, dt, c.a_g * Geo::R1 + p);
+        } else if constexpr (PH == 3 || PH == 4) {
+            int base, k0, c0;
+            if (!bwd_sb_map<M, kRev>(tid, base, k0, c0)) return;
+            // block k0 lives in the frame of its first leaf 8*k0: its nodes end at dt + a_g*(8*k0 + 2^L*k)
+            const int thr_top = dt + c.a_g * (Geo::R1 * k0);
+            if constexpr (PH == 3) {
+                bwd_step_prologue<Geo::LOGR1, true, Geo::SEG2 / V>(buf, base, RM::s1_stride, k0, c0, true, st.sb);
+            } else if constexpr (kDirect) {
+                float *o = dst + (long long)(c.d0 + c0) * c.n + c.g * G + k0 * Geo::R1;
+                bwd_step_main_direct<Geo::LOGR1, kMask, Geo::SEG2 / V>(buf, base, RM::s1_stride, k0, c0, st.sb, thr_top, c.a_g,
+                                                                       o, c.n, dt - c0);
+            } else {
+                bwd_step_main<Geo::LOGR1, true, kMask, Geo::SEG2 / V>(buf, base, RM::s1_stride, k0, c0, st.sb, thr_top, c.a_g);
+            }
+        } else {
+            bwd_store_wrows<M, kRev, TD, NWARP>(buf, dst, c, false, tid);
+        }
+    }
+
+    // kMaskTiles programs run the tiles that reach offset D (TILE_FULL_MASKED), the others the interior
+    // tiles: two launches, so that neither kernel carries both copies of the unrolled steps
+    template <int PH>
+    ADRT_HD static void phase_ct(int mode, float *buf, State &st, const float *src, float *dst, const TileCtx &c, int tid)
+    {
+        (void)mode;
+        phase_m<PH, kMaskTiles>(buf, st, src, dst, c, tid);
+    }
+    // first d-tile that must run masked
+    ADRT_HD static int first_masked_tile(int D)
+    {
+        const int lim = D - XW - 8;
+        return lim < 0 ? 0 : lim / TD + 1;
+    }
+};
+
 template <typename Prog, int PH = 0>
-ADRT_HD void run_phase(int ph, float *buf, typename Prog::State &st, const float *src, float *dst, const TileCtx &c, int tid)
+ADRT_HD void run_phase(int ph, int mode, float *buf, typename Prog::State &st, const float *src, float *dst, const TileCtx &c, int tid)
 {
     if constexpr (PH < Prog::kPhases) {
-        if (ph == PH) Prog::template phase_ct<PH>(buf, st, src, dst, c, tid);
-        else run_phase<Prog, PH + 1>(ph, buf, st, src, dst, c, tid);
+        if (ph == PH) Prog::template phase_ct<PH>(mode, buf, st, src, dst, c, tid);
+        else run_phase<Prog, PH + 1>(ph, mode, buf, st, src, dst, c, tid);
     }
 }
 

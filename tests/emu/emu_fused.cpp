@@ -69,7 +69,7 @@ template <typename Prog>
 void run_stream_pass(const plan::Pass &p, const float *src, float *dst, int n, int D, int planes, long long sps, long long dps,
                      bool image_loader)
 {
-    const size_t cells = (size_t)Prog::G * stile::P + 64;
+    const size_t cells = (size_t)Prog::G * stile::P + 64;   // + slack: the top segment of a transposed step reads a few cells past the last row
     std::vector<tile::Pack<float>> storeA(cells / 4 + 1);
     float *buf = reinterpret_cast<float *>(storeA.data());
     std::vector<typename Prog::State> states(Prog::NT);
@@ -86,6 +86,7 @@ void run_stream_pass(const plan::Pass &p, const float *src, float *dst, int n, i
                 c.q = 0;
                 const int mode = Prog::classify(c);
                 if (mode == tile::TILE_SKIP) continue;
+                if (!Prog::runs(mode)) continue;
                 const float *sp;
                 if (image_loader) { c.q = plane & 3; sp = src + (long long)(plane >> 2) * sps; }
                 else sp = src + (long long)plane * sps;
@@ -101,7 +102,7 @@ void run_stream_pass(const plan::Pass &p, const float *src, float *dst, int n, i
                 for (int ph = 0; ph < Prog::kPhases; ++ph)
                     for (int i = 0; i < Prog::NT; ++i) {
                         const int tid = g_order ? Prog::NT - 1 - i : i;
-                        stile::run_phase<Prog>(ph, buf, states[tid], sp, dp, c, tid);
+                        stile::run_phase<Prog>(ph, mode, buf, states[tid], sp, dp, c, tid);
                     }
             }
 }
@@ -115,6 +116,11 @@ void run_stream_kinds(const plan::Pass &p, const float *src, float *dst, int n, 
         else if (p.load == LOAD_IMAGE && p.store == STORE_QCOLS) run_stream_pass<stile::FwdStream<M, LOAD_IMAGE, STORE_QCOLS>>(p, src, dst, n, D, planes, sps, dps, true);
         else if (p.load == LOAD_WROWS && p.store == STORE_WROWS) run_stream_pass<stile::FwdStream<M, LOAD_WROWS, STORE_WROWS>>(p, src, dst, n, D, planes, sps, dps, false);
         else run_stream_pass<stile::FwdStream<M, LOAD_WROWS, STORE_QCOLS>>(p, src, dst, n, D, planes, sps, dps, false);
+    } else {
+        if (p.load == LOAD_QCOLS && p.store == STORE_WROWS) { run_stream_pass<stile::BwdStream<M, LOAD_QCOLS, STORE_WROWS, false>>(p, src, dst, n, D, planes, sps, dps, false); run_stream_pass<stile::BwdStream<M, LOAD_QCOLS, STORE_WROWS, true>>(p, src, dst, n, D, planes, sps, dps, false); }
+        else if (p.load == LOAD_QCOLS && p.store == STORE_QCOLS) { run_stream_pass<stile::BwdStream<M, LOAD_QCOLS, STORE_QCOLS, false>>(p, src, dst, n, D, planes, sps, dps, false); run_stream_pass<stile::BwdStream<M, LOAD_QCOLS, STORE_QCOLS, true>>(p, src, dst, n, D, planes, sps, dps, false); }
+        else if (p.load == LOAD_WROWS && p.store == STORE_WROWS) { run_stream_pass<stile::BwdStream<M, LOAD_WROWS, STORE_WROWS, false>>(p, src, dst, n, D, planes, sps, dps, false); run_stream_pass<stile::BwdStream<M, LOAD_WROWS, STORE_WROWS, true>>(p, src, dst, n, D, planes, sps, dps, false); }
+        else { run_stream_pass<stile::BwdStream<M, LOAD_WROWS, STORE_QCOLS, false>>(p, src, dst, n, D, planes, sps, dps, false); run_stream_pass<stile::BwdStream<M, LOAD_WROWS, STORE_QCOLS, true>>(p, src, dst, n, D, planes, sps, dps, false); }
     }
 }
 
