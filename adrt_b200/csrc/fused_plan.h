@@ -102,13 +102,18 @@ inline int tile_td(int M, int store, bool stream = false)
     return tile::XW - (G < 4 ? 4 : G) - (store == tile::STORE_WROWS ? 4 : 0);
 }
 
-// Which passes the streaming kernels take: fp32, 5 or 6 stages.  ADRT_B200_STREAM=0
-// turns them off (A/B measurements, tests of the fused_tile.h path).
-inline bool use_stream(int M, size_t elem_size, bool forward)
+// Which passes the streaming kernels (stream_tile.h) take: fp32, 5 or 6 stages, and only the pass
+// kinds where they beat the fused_tile.h kernels (profiles/): a kind is named <f|b><M><p|w> --
+// forward / transposed, stages, loading from the public side (image / sinogram) or from workspace
+// rows.  ADRT_B200_STREAM_SET="f6p,f5w,..." overrides the default set ("" = none, "all" = every kind).
+inline bool use_stream(int M, size_t elem_size, bool forward, int load)
 {
     if (elem_size != 4 || (M != 5 && M != 6)) return false;
-    if (const char *e = getenv(forward ? "ADRT_B200_STREAM" : "ADRT_B200_STREAM_BDRT")) return atoi(e) != 0;
-    return true;
+    char key[4] = {forward ? 'f' : 'b', (char)('0' + M), load == tile::LOAD_WROWS ? 'w' : 'p', 0};
+    const char *set = getenv("ADRT_B200_STREAM_SET");
+    if (!set) set = "f6p,f6w,f5w,b6w,b5w,b6p";
+    if (!strcmp(set, "all")) return true;
+    return strstr(set, key) != nullptr;
 }
 
 inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
@@ -133,7 +138,7 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        p.stream = use_stream(p.M, elem_size, true);
+        p.stream = use_stream(p.M, elem_size, true, p.load);
         const int TD = tile_td(p.M, p.store, p.stream);
         p.next_g = last ? 0 : (1 << ms[i + 1]);
         p.d_need = pl->D;
@@ -175,7 +180,7 @@ inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        p.stream = use_stream(p.M, elem_size, false);
+        p.stream = use_stream(p.M, elem_size, false, p.load);
         p.next_g = 0;
         p.grid_y = n / G;
         if (!last) {

@@ -66,6 +66,9 @@ using tile::fwd_row_skew;
 #define ADRT_STREAM_UNROLL 3
 #endif
 constexpr int kStreamUnroll = ADRT_STREAM_UNROLL;
+// 4 x 4 blocks a thread of a transposing loader keeps in flight (UB * 4 vector loads); the 5-stage
+// kernels run 6 CTAs per SM and have 168 registers
+template <int M> struct LoadBatch { static constexpr int value = (M == 6) ? 6 : 3; };
 
 constexpr int V = 4;
 constexpr int XW = 288;          // offsets per tile row
@@ -150,6 +153,52 @@ ADRT_HD void bulk_arrive_wait(BulkBar &b, int my_bytes)
     b.phase ^= 1;
 #else
     (void)b; (void)my_bytes;
+#endif
+}
+
+// 16-byte shared-memory load the compiler may not narrow (narrowed window loads turn into 4-byte
+// loads with a 16-byte lane stride: 4-way bank conflicts)
+ADRT_HD F4 lds128(const float *p)
+{
+#ifdef __CUDA_ARCH__
+    F4 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.v[0]), "=f"(v.v[1]), "=f"(v.v[2]), "=f"(v.v[3]) : "r"(a));
+    return v;
+#else
+    return *reinterpret_cast<const F4 *>(p);
+#endif
+}
+
+// N consecutive elements starting Q after the 16-byte aligned p, from whole 16-byte loads
+template <int N, int Q>
+ADRT_HD void load_window_wide(const float *p, float (&dst)[N])
+{
+    constexpr int NV = (Q + N + 3) / 4;
+    F4 tmp[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) tmp[v] = lds128(p + 4 * v);
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = tmp[(Q + i) / 4].v[(Q + i) % 4];
+}
+
+// Sources of the constant fills of a tile row (+0.0 above the data, -0.0 "copy" sentinels below
+// offset 0), so that fills are bulk copies too instead of shared-memory stores.
+#define ADRT_R8(x) x, x, x, x, x, x, x, x
+#define ADRT_R32(x) ADRT_R8(x), ADRT_R8(x), ADRT_R8(x), ADRT_R8(x)
+#define ADRT_R288(x) ADRT_R32(x), ADRT_R32(x), ADRT_R32(x), ADRT_R32(x), ADRT_R32(x), ADRT_R32(x), ADRT_R32(x), ADRT_R32(x), ADRT_R32(x)
+#ifdef __CUDACC__
+__device__ __align__(16) const float g_fill_pos[288] = {ADRT_R288(0.0f)};
+__device__ __align__(16) const float g_fill_neg[288] = {ADRT_R288(-0.0f)};
+#endif
+static const float h_fill_pos[288] = {ADRT_R288(0.0f)};
+static const float h_fill_neg[288] = {ADRT_R288(-0.0f)};
+ADRT_HD const float *fill_src(bool neg)
+{
+#ifdef __CUDA_ARCH__
+    return neg ? g_fill_neg : g_fill_pos;
+#else
+    return neg ? h_fill_neg : h_fill_pos;
 #endif
 }
 
@@ -443,17 +492,10 @@ ADRT_HD void fwd_load_wrows(float *buf, const float *src_plane, const TileCtx &c
         if (xlo > XW) xlo = XW;
         if (xhi > XW) xhi = XW;
         if (xhi < xlo) xhi = xlo;
-        if (xhi > xlo) {
-            bulk_load(bar, dst + xlo, row + gbase + xlo, (xhi - xlo) * 4);
-            my_bytes = (xhi - xlo) * 4;
-        }
-        if (xlo > 0 || xhi < XW) {
-            F4 neg, pos;
-#pragma unroll
-            for (int i = 0; i < V; ++i) { neg.v[i] = -0.0f; pos.v[i] = 0.0f; }
-            for (int x = 0; x < xlo; x += V) *reinterpret_cast<F4 *>(dst + x) = neg;
-            for (int x = xhi; x < XW; x += V) *reinterpret_cast<F4 *>(dst + x) = pos;
-        }
+        if (xlo > 0) bulk_load(bar, dst, fill_src(true), xlo * 4);
+        if (xhi > xlo) bulk_load(bar, dst + xlo, row + gbase + xlo, (xhi - xlo) * 4);
+        if (xhi < XW) bulk_load(bar, dst + xhi, fill_src(false), (XW - xhi) * 4);
+        my_bytes = XW * 4;
     }
     bulk_arrive_wait(bar, my_bytes);
 }
@@ -505,14 +547,15 @@ ADRT_HD void fwd_load_image(float *buf, const float *img, const TileCtx &c, int 
         // transposes them in registers and stores four tile-row vectors.  Lane bits: b0, b3, b4 ->
         // row group (8 groups = 128 contiguous bytes per image row), b1, b2 -> offset chunk; the 8
         // lanes of a quarter warp then write 8 distinct 16-byte bank groups.
+        constexpr int UB = LoadBatch<M>::value;
         const int rg_lo = (lane & 1) | (((lane >> 3) & 3) << 1), ch_lo = (lane >> 1) & 3;
         const int nblk = (rows / 32) * (NVEC / 4);
         const long long step = (c.q == 1) ? -(long long)n : (long long)n;
         const float *ib = (c.q == 1) ? img + (long long)(n - 1 - dbase) * n + c.g * G : img + (long long)dbase * n + c.g * G;
-        for (int blk0 = warp; blk0 < nblk; blk0 += 3 * NWARP) {
-            F4 v[3][4];
+        for (int blk0 = warp; blk0 < nblk; blk0 += UB * NWARP) {
+            F4 v[UB][4];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
+            for (int u = 0; u < UB; ++u) {
                 const int blk = blk0 + u * NWARP;
                 const int rg = (blk / (NVEC / 4)) * 8 + rg_lo, ch = (blk % (NVEC / 4)) * 4 + ch_lo;
                 const int d = dbase + 4 * ch;
@@ -523,7 +566,7 @@ ADRT_HD void fwd_load_image(float *buf, const float *img, const TileCtx &c, int 
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
+            for (int u = 0; u < UB; ++u) {
                 const int blk = blk0 + u * NWARP;
                 if (blk < nblk) {
                     const int rg = (blk / (NVEC / 4)) * 8 + rg_lo, ch = (blk % (NVEC / 4)) * 4 + ch_lo;
@@ -588,7 +631,7 @@ ADRT_HD void fwd_store_row_skewed(const float *b, float *row, const TileCtx &c, 
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = 0.0f;
             } else {
-                tile::load_window<float, V, Q>(b + (LH + xc - S - Q), v);
+                load_window_wide<V, Q>(b + (LH + xc - S - Q), v);
 #pragma unroll
                 for (int i = 0; i < V; ++i)
                     if (gp - S + i >= lim) v[i] = 0.0f;
@@ -677,9 +720,11 @@ struct FwdStream {
     static constexpr int LH = XW - TD;
     // image loads go through registers (more threads = more loads in flight); workspace rows are
     // copied asynchronously, so those passes only need the 64 threads of the butterfly steps
-    static constexpr int NT = kImage ? 128 : 64;
+    // 64 threads: the butterfly steps want ~200 registers, and a scheduler's 16K registers are shared by
+    // the warps resident on it (3 CTAs x 2 warps = at most 2 warps per scheduler)
+    static constexpr int NT = 64;
     static constexpr int NWARP = NT / 32;
-    static constexpr int MIN_CTAS = (M == 6 || kImage) ? 3 : 6;
+    static constexpr int MIN_CTAS = (M == 6) ? 3 : 6;
     typedef FwdState<M> State;
     // a direct step 2 writes nothing to the tile: its prologue and main loop need no barrier between them
     ADRT_HD static constexpr bool barrier_after(int ph) { return !(kDirect && ph == 3); }
@@ -945,27 +990,29 @@ ADRT_HD void bwd_step_main_direct(const float *buf, int base, int stride, int pk
 // ---- transposed loaders ---------------------------------------------------------------
 // Public layout: tile row of parent angle A <- column g*G + A, tile column x <- offset d0 + x
 // (zero from offset D on).  4 x 4 register transposes as in fwd_load_image.
-template <int M, bool kRev, int NWARP>
+template <int M, bool kRev, int NWARP, bool kEdge>
 ADRT_HD void bwd_load_qcols(float *buf, const float *src_plane, const TileCtx &c, int tid)
 {
     constexpr int G = SGeo<M, false>::G;
     const int warp = tid >> 5, lane = tid & 31;
     const int n = c.n;
     const int cols = G < n ? G : n;
+    constexpr int UB = LoadBatch<M>::value;
     const int rg_lo = (lane & 1) | (((lane >> 3) & 3) << 1), ch_lo = (lane >> 1) & 3;
     const int nblk = (cols / 32) * (NVEC / 4);
-    const float *ib = src_plane + (long long)c.d0 * n + c.g * G;
-    for (int blk0 = warp; blk0 < nblk; blk0 += 3 * NWARP) {
-        F4 v[3][4];
+    const float *ib = src_plane + (long long)c.d0 * n + c.g * G + 4 * rg_lo + 4 * ch_lo * n;   // in-plane offsets fit 32 bits
+    const int dt = c.D - c.d0;
+    for (int blk0 = warp; blk0 < nblk; blk0 += UB * NWARP) {
+        F4 v[UB][4];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < UB; ++u) {
             const int blk = blk0 + u * NWARP;
-            const int rg = (blk / (NVEC / 4)) * 8 + rg_lo, ch = (blk % (NVEC / 4)) * 4 + ch_lo;
+            const int rb = blk / (NVEC / 4), cb = blk % (NVEC / 4);   // 8 row groups x 4 chunks per block
             if (blk < nblk) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (c.d0 + 4 * ch + i < c.D) {
-                        v[u][i] = *reinterpret_cast<const F4 *>(ib + (long long)(4 * ch + i) * n + 4 * rg);
+                    if (!kEdge || 16 * cb + 4 * ch_lo + i < dt) {
+                        v[u][i] = *reinterpret_cast<const F4 *>(ib + (16 * cb + i) * n + 32 * rb);
                     } else {
 #pragma unroll
                         for (int t = 0; t < 4; ++t) v[u][i].v[t] = 0.0f;
@@ -974,7 +1021,7 @@ ADRT_HD void bwd_load_qcols(float *buf, const float *src_plane, const TileCtx &c
             }
         }
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < UB; ++u) {
             const int blk = blk0 + u * NWARP;
             if (blk < nblk) {
                 const int rg = (blk / (NVEC / 4)) * 8 + rg_lo, ch = (blk % (NVEC / 4)) * 4 + ch_lo;
@@ -1012,7 +1059,13 @@ ADRT_HD void bwd_load_wrows(float *buf, const float *src_plane, const TileCtx &c
             my_bytes = xb * 4;
         }
         if (xb < XW) {
-            for (int x = xb; x < XW; ++x) dst[x] = x < xv ? row[x] : 0.0f;
+            // the chunk that straddles D by hand, whole chunks above it from the zero source
+            const int xz = xb + 4 < XW ? xb + 4 : XW;
+            for (int x = xb; x < xz; ++x) dst[x] = x < xv ? row[x] : 0.0f;
+            if (xz < XW) {
+                bulk_load(bar, dst + xz, fill_src(false), (XW - xz) * 4);
+                my_bytes += (XW - xz) * 4;
+            }
         }
     }
     bulk_arrive_wait(bar, my_bytes);
@@ -1025,6 +1078,20 @@ ADRT_HD void bwd_load_wrows(float *buf, const float *src_plane, const TileCtx &c
 template <int TD, int Q>
 ADRT_HD void bwd_store_row(const float *b, float *row, const TileCtx &c, int dbase, bool zero, int lane)
 {
+    if (!zero && dbase + Q >= 0 && dbase + Q + TD <= c.D) {
+        // the whole segment lies inside the row
+        float *o = row + dbase + Q;
+#pragma unroll
+        for (int k = 0; k < (TD / V + 31) / 32; ++k) {
+            const int xa = (k * 32 + lane) * V;
+            if (xa < TD) {
+                float v[V];
+                load_window_wide<V, Q>(b + xa, v);
+                tile::store_chunk<float>(o + xa, v);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < (TD / V + 31) / 32; ++k) {
         const int xa = (k * 32 + lane) * V;
@@ -1035,7 +1102,7 @@ ADRT_HD void bwd_store_row(const float *b, float *row, const TileCtx &c, int dba
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = 0.0f;
             } else {
-                tile::load_window<float, V, Q>(b + xa, v);
+                load_window_wide<V, Q>(b + xa, v);
             }
             if (gp >= 0 && gp + V <= c.D) {
                 tile::store_chunk<float>(row + gp, v);
@@ -1111,9 +1178,9 @@ struct BwdStream {
     static constexpr int kPhases = kDirect ? 5 : 6;
     static constexpr int TD = STileTD<M, STOREK>::value;
     static constexpr int TDB = XW - Geo::X2;            // columns step B produces (TD, or TD + 4 for workspace stores)
-    static constexpr int NT = (LOADK == LOAD_QCOLS) ? 128 : 64;
+    static constexpr int NT = 64;
     static constexpr int NWARP = NT / 32;
-    static constexpr int MIN_CTAS = (M == 6 || LOADK == LOAD_QCOLS) ? 3 : 6;
+    static constexpr int MIN_CTAS = (M == 6) ? 3 : 6;
     typedef BwdState<M> State;
     ADRT_HD static constexpr bool barrier_after(int ph) { return !(kDirect && ph == 3); }
 
@@ -1136,7 +1203,7 @@ struct BwdStream {
         typedef RowMap<M, kRev, false> RM;
         const int dt = c.D - c.d0;
         if constexpr (PH == 0) {
-            if (LOADK == LOAD_QCOLS) bwd_load_qcols<M, kRev, NWARP>(buf, src, c, tid);
+            if (LOADK == LOAD_QCOLS) bwd_load_qcols<M, kRev, NWARP, kMask>(buf, src, c, tid);
             else bwd_load_wrows<M, kRev, NT>(buf, src, c, tid, st.bar);
         } else if constexpr (PH == 1 || PH == 2) {
             int base, p, c0;
