@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "fused_tile.h"
@@ -55,7 +56,7 @@ inline int max_stages_per_pass(size_t elem_size)
 }
 
 // Split K stages into passes.  ADRT_B200_SPLIT="6,5" overrides (testing/tuning).
-inline std::vector<int> split_stages(int K, size_t elem_size, const char *env_name)
+inline std::vector<int> split_stages(int K, size_t elem_size, const char *env_name, bool small_first = false)
 {
     std::vector<int> out;
     if (const char *e = getenv(env_name)) {
@@ -80,6 +81,7 @@ inline std::vector<int> split_stages(int K, size_t elem_size, const char *env_na
         out.push_back(m);
         left -= m;
     }
+    if (small_first) std::reverse(out.begin(), out.end());
     return out;
 }
 
@@ -122,7 +124,9 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
     const int K = ilog2(n64);
     if (K < 1) return false;
     pl->n = n; pl->K = K; pl->D = 2 * n - 1;
-    const std::vector<int> ms = split_stages(K, elem_size, "ADRT_B200_SPLIT");
+    // fp32: the pass next to the public layout is the long one in both directions (it is a streaming
+    // pass, stream_tile.h, and the fastest kernel per stage) -- measured 4.7 vs 5.05 ms at 64 x 2048^2
+    const std::vector<int> ms = split_stages(K, elem_size, "ADRT_B200_SPLIT", elem_size == 4);
     pl->npass = (int)ms.size();
     pl->ws_slot_elems[0] = pl->ws_slot_elems[1] = 0;
     int s = 0;

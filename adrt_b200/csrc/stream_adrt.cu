@@ -5,6 +5,8 @@
 // the register file, limits occupancy).
 #include "pass_args.h"
 
+#include <mutex>
+
 namespace adrt_b200 {
 
 namespace {
@@ -93,15 +95,51 @@ int dispatch_fwd(const plan::Pass &p, const float *src, float *dst, const PassAr
     return ADRT_B200_EINVAL;
 }
 
+// A per-device helper stream: the few, slow boundary tiles run beside the interior tiles
+// instead of after them (fork / join with events around the two launches).
+cudaStream_t side_stream()
+{
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+    return streams[dev];
+}
+
 // interior tiles and the tiles that reach offset D run as two launches (see BwdStream::phase_ct)
 template <int M, int LOADK, int STOREK>
 int launch_bwd(const plan::Pass &p, const float *src, float *dst, const PassArgs &a, cudaStream_t s)
 {
     int xm = stile::BwdStream<M, LOADK, STOREK, false>::first_masked_tile(a.D);
     if (xm > p.grid_x) xm = p.grid_x;
-    int rc = launch<stile::BwdStream<M, LOADK, STOREK, false>>(src, dst, a, 0, xm, p.grid_y, s);
+    const int nmask = p.grid_x - xm;
+    cudaStream_t side = (xm > 0 && nmask > 0) ? side_stream() : nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    if (side) {
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) {
+            if (fork) cudaEventDestroy(fork);
+            side = nullptr;
+            (void)cudaGetLastError();
+        }
+    }
+    int rc;
+    if (side) {
+        ADRT_CUDA_CHECK(cudaEventRecord(fork, s));
+        ADRT_CUDA_CHECK(cudaStreamWaitEvent(side, fork, 0));
+        rc = launch<stile::BwdStream<M, LOADK, STOREK, true>>(src, dst, a, xm, nmask, p.grid_y, side);
+        if (rc == ADRT_B200_OK) rc = launch<stile::BwdStream<M, LOADK, STOREK, false>>(src, dst, a, 0, xm, p.grid_y, s);
+        cudaEventRecord(join, side);
+        cudaStreamWaitEvent(s, join, 0);
+        cudaEventDestroy(fork);
+        cudaEventDestroy(join);
+        return rc;
+    }
+    rc = launch<stile::BwdStream<M, LOADK, STOREK, false>>(src, dst, a, 0, xm, p.grid_y, s);
     if (rc != ADRT_B200_OK) return rc;
-    return launch<stile::BwdStream<M, LOADK, STOREK, true>>(src, dst, a, xm, p.grid_x - xm, p.grid_y, s);
+    return launch<stile::BwdStream<M, LOADK, STOREK, true>>(src, dst, a, xm, nmask, p.grid_y, s);
 }
 
 template <int M>

@@ -20,7 +20,7 @@ SO = os.path.join(HERE, "emu", "_build", "libemu.so")
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [SRC] + [os.path.join(HERE, "..", "adrt_b200", "csrc", f) for f in ("fused_tile.h", "fused_plan.h")]
+    deps = [SRC] + [os.path.join(HERE, "..", "adrt_b200", "csrc", f) for f in ("fused_tile.h", "fused_plan.h", "stream_tile.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
@@ -129,3 +129,66 @@ def test_bdrt_rows(emu, n, rows, split):
             assert np.isnan(out[:, :, -1]).all()   # the far rows were really skipped
     finally:
         os.environ.pop("ADRT_B200_SPLIT_BDRT", None)
+
+
+# ---------------------------------------------------------------------------------------------
+# Streaming passes (adrt_b200/csrc/stream_tile.h: fp32, 5 or 6 stages, butterflies with register
+# history, in-place tiles).  ADRT_B200_STREAM_SET=all forces every pass kind through them; each case
+# runs twice, with the threads of a phase emulated in ascending and in descending order -- a result
+# that depended on the order would mean two threads race on a tile cell inside a phase.
+def _check_stream(emu, n, split, rows=None):
+    emu.emu_stream_tiles.restype = ctypes.c_longlong
+    keys = ("ADRT_B200_SPLIT", "ADRT_B200_SPLIT_BDRT", "ADRT_B200_STREAM_SET")
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ["ADRT_B200_STREAM_SET"] = "all"
+    if split:
+        os.environ["ADRT_B200_SPLIT"] = split
+        os.environ["ADRT_B200_SPLIT_BDRT"] = split
+    try:
+        x = make_image(11 + n, (1, n, n), np.float32)
+        want = O.adrt(x)
+        s = make_sino(13 + n, want.shape, np.float32)
+        wz = O.bdrt(s)
+        x0, s0 = np.full_like(x, -0.0), np.full_like(s, -0.0)
+        wy0, wz0 = O.adrt(x0), O.bdrt(s0)
+        for order in (0, 1):
+            emu.emu_set_order(order)
+            t0 = emu.emu_stream_tiles()
+            y = _run(emu, "emu_adrt", x, want.shape)
+            assert emu.emu_stream_tiles() > t0, "no streaming tile ran"
+            assert bytes_equal(y, want), f"adrt n={n} split={split} order={order}: {first_diff(y, want)}"
+            assert bytes_equal(_run(emu, "emu_adrt", x0, want.shape), wy0), f"adrt(-0) n={n} split={split} order={order}"
+            t0 = emu.emu_stream_tiles()
+            z = _run(emu, "emu_bdrt", s, s.shape)
+            assert emu.emu_stream_tiles() > t0, "no streaming tile ran"
+            assert bytes_equal(z, wz), f"bdrt n={n} split={split} order={order}: {first_diff(z, wz)}"
+            assert bytes_equal(_run(emu, "emu_bdrt", s0, s.shape), wz0), f"bdrt(-0) n={n} split={split} order={order}"
+            if rows:
+                out = np.full(s.shape, np.nan, dtype=s.dtype)
+                rc = emu.emu_bdrt_rows_f32(ctypes.c_void_p(s.ctypes.data), ctypes.c_void_p(out.ctypes.data),
+                                           ctypes.c_int64(1), ctypes.c_int64(n), ctypes.c_int64(rows))
+                assert rc == 0
+                assert bytes_equal(out[:, :, :rows], wz[:, :, :rows]), first_diff(out[:, :, :rows], wz[:, :, :rows])
+    finally:
+        emu.emu_set_order(0)
+        for k in keys:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("n,split,rows", [
+    (32, None, None), (64, None, 20),                 # one pass: image / sinogram on both sides, every tile masked
+    (128, "5,2", None), (128, "2,5", 128),            # 5 stages next to the image / next to the public layout
+    (256, "6,2", None), (256, "2,6", 100),            # 6 stages likewise
+    (512, "6,3", 512), (512, "3,6", None),            # several d-tiles per group: interior and boundary tiles
+    (1024, None, 1024), (1024, "5,5", None),          # default plan (5 + 5), both orders of the split
+])
+def test_streaming_passes(emu, n, split, rows):
+    _check_stream(emu, n, split, rows)
+
+
+def test_streaming_two_six_stage_passes(emu):
+    # K = 12 = 6 + 6 (the 4096^2 plan) at the smallest size that has it is too slow to emulate;
+    # 6 + 5 and 5 + 6 (the 2048^2 plans) are covered through 11-stage splits of n = 2048 on the GPU.
+    _check_stream(emu, 512, "6,3")
+    _check_stream(emu, 512, "4,5")
