@@ -54,8 +54,9 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
     for (int plane = blockIdx.z; plane < a.planes; plane += gridDim.z) {
         const T *sp;
         if (LOADK == tile::LOAD_IMAGE) {
-            c.q = a.q_first + plane % a.q_count;
-            sp = src + (long long)(plane / a.q_count) * a.src_plane_stride;
+            const int gp = plane + a.plane0;
+            c.q = a.q_first + gp % a.q_count;
+            sp = src + (long long)(gp / a.q_count) * a.src_plane_stride;
         } else {
             sp = src + (long long)plane * a.src_plane_stride;
         }
@@ -121,15 +122,52 @@ int dispatch_pass(const plan::Pass &p, const T *src, T *dst, const PassArgs &a, 
     return ADRT_B200_EINVAL;
 }
 
-// Images per wave: the batch is processed in waves so that the R-layout
-// workspace of a wave can stay resident in the 126 MB L2 between the pass
-// that writes it and the pass that reads it.  0 = whole batch at once.
-int wave_images(int64_t B)
+// Waves: the planes of a batch are processed in waves of `planes` planes, every pass of a
+// wave before the next wave starts, so that the R-layout workspace a pass writes is still
+// in the 126 MB L2 when the next pass reads it (one fp32 2048^2 plane: 17 MB forward, 34 MB
+// transposed).  With two lanes, odd waves run on a helper stream with their own workspace:
+// the tail of one wave's kernel overlaps the head of the other's.
+// ADRT_B200_WAVE_PLANES / ADRT_B200_WAVE (images) / ADRT_B200_WAVE_LANES override; 0 planes =
+// the whole batch at once.
+struct WaveCfg {
+    int planes;  // planes per wave
+    int lanes;   // 1 or 2 concurrent waves
+};
+
+WaveCfg wave_config(int64_t total_planes, int q_count, size_t plane_ws_bytes)
 {
-    const char *e = getenv("ADRT_B200_WAVE");  // read per call: tunable at run time
-    const int w = e ? atoi(e) : 0;
-    if (w <= 0 || w > B) return (int)B;
+    WaveCfg w;
+    w.planes = (int)total_planes;
+    w.lanes = 1;
+    long long want = 0;
+    if (const char *e = getenv("ADRT_B200_WAVE_PLANES")) want = atoll(e);  // read per call: tunable at run time
+    else if (const char *e2 = getenv("ADRT_B200_WAVE")) want = atoll(e2) * q_count;
+    (void)plane_ws_bytes;
+    if (want > 0 && want < total_planes) w.planes = (int)want;
+    if (const char *e = getenv("ADRT_B200_WAVE_LANES")) w.lanes = atoi(e) >= 2 ? 2 : 1;
+    if ((long long)w.planes * w.lanes > total_planes) w.lanes = 1;
     return w;
+}
+
+// Experiment: keep the workspace resident in L2 (persisting access-policy window on the
+// streams the waves run on).  ADRT_B200_L2_PERSIST_MB = size of the persisting carve-out.
+void set_persist_window(cudaStream_t s, void *base, size_t bytes)
+{
+    const char *e = getenv("ADRT_B200_L2_PERSIST_MB");
+    if (!e) return;
+    const size_t carve = (size_t)atoi(e) << 20;
+    int dev = 0, max_win = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    cudaStreamAttrValue v = {};
+    v.accessPolicyWindow.base_ptr = carve ? base : nullptr;
+    v.accessPolicyWindow.num_bytes = carve ? std::min(bytes, (size_t)max_win) : 0;
+    v.accessPolicyWindow.hitRatio = carve ? std::min(1.0f, (float)carve / (float)std::max<size_t>(bytes, 1)) : 0.f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
+    (void)cudaGetLastError();
 }
 
 template <typename T, bool kForward>
@@ -139,46 +177,86 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
     // B images of q_count planes each (forward: quadrants q_first .. q_first+q_count-1 of
     // every image; transposed: any plane count, the quadrant identity does not matter)
     const int n = pl.n, D = pl.D;
-    const int wave = wave_images(B);
-    const size_t slot0 = pl.ws_slot_elems[0] * q_count * (size_t)wave;
-    const size_t slot1 = pl.ws_slot_elems[1] * q_count * (size_t)wave;
-    if (slot0 + slot1 > ws_elems) {
-        set_error("fused workspace too small: need %zu elements, got %zu", slot0 + slot1, ws_elems);
+    const int64_t total = B * q_count;
+    const size_t plane_ws = pl.ws_slot_elems[0] + pl.ws_slot_elems[1];
+    const WaveCfg wc = wave_config(total, q_count, plane_ws * sizeof(T));
+    const size_t slot0 = pl.ws_slot_elems[0] * (size_t)wc.planes;
+    const size_t lane_elems = plane_ws * (size_t)wc.planes;
+    if (lane_elems * wc.lanes > ws_elems) {
+        set_error("fused workspace too small: need %zu elements, got %zu", lane_elems * wc.lanes, ws_elems);
         return ADRT_B200_EWORKSPACE;
     }
-    T *slot[2] = {ws, ws + slot0};
+    // lane 1 = helper stream, forked from / joined to the caller's stream by events
+    cudaStream_t lane_stream[2] = {s, nullptr};
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int lanes = wc.lanes;
+    if (lanes == 2) {
+        lane_stream[1] = aux_stream(1);
+        if (!lane_stream[1] || cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) {
+            if (fork) cudaEventDestroy(fork);
+            fork = nullptr;
+            lanes = 1;
+            (void)cudaGetLastError();
+        }
+    }
+    if (lanes == 2) {
+        ADRT_CUDA_CHECK(cudaEventRecord(fork, s));
+        ADRT_CUDA_CHECK(cudaStreamWaitEvent(lane_stream[1], fork, 0));
+    }
+    for (int l = 0; l < lanes; ++l) set_persist_window(lane_stream[l], ws, lane_elems * lanes * sizeof(T));
     const long long img_elems = (long long)n * n, sino_plane = (long long)D * n;
-    for (int64_t b0 = 0; b0 < B; b0 += wave) {
-        const int nb = (int)((B - b0) < wave ? (B - b0) : wave);
-        for (int i = 0; i < pl.npass; ++i) {
+    int rc = ADRT_B200_OK;
+    int64_t wave = 0;
+    for (int64_t p0 = 0; p0 < total && rc == ADRT_B200_OK; p0 += wc.planes, ++wave) {
+        const int lane = (int)(wave % lanes);
+        T *lane_ws = ws + lane_elems * lane;
+        T *slot[2] = {lane_ws, lane_ws + slot0};
+        const int np = (int)((total - p0) < wc.planes ? (total - p0) : wc.planes);
+        for (int i = 0; i < pl.npass && rc == ADRT_B200_OK; ++i) {
             const plan::Pass &p = pl.pass[i];
             PassArgs a;
             a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g; a.d_need = p.d_need;
             a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
-            a.planes = nb * q_count;
+            a.planes = np;
             a.x_off = 0;
             a.q_first = q_first; a.q_count = q_count;
+            a.plane0 = 0;
+            a.side_idx = lane == 0 ? 0 : 2;
             const T *src;
             T *dst;
             if (p.src_buf < 0) {
-                if (kForward) { src = in + b0 * img_elems; a.src_plane_stride = img_elems; }
-                else { src = in + b0 * q_count * sino_plane; a.src_plane_stride = sino_plane; }
+                if (kForward) { src = in; a.plane0 = (int)p0; a.src_plane_stride = img_elems; }
+                else { src = in + p0 * sino_plane; a.src_plane_stride = sino_plane; }
             } else {
                 src = slot[p.src_buf];
                 a.src_plane_stride = (long long)n * p.in_pitch;
             }
             if (p.dst_buf < 0) {
-                dst = out + b0 * q_count * sino_plane;
+                dst = out + p0 * sino_plane;
                 a.dst_plane_stride = sino_plane;
             } else {
                 dst = slot[p.dst_buf];
                 a.dst_plane_stride = (long long)n * p.out_pitch;
             }
-            int rc = dispatch_pass<T, kForward>(p, src, dst, a, s);
-            if (rc != ADRT_B200_OK) return rc;
+            rc = dispatch_pass<T, kForward>(p, src, dst, a, lane_stream[lane]);
         }
     }
-    return ADRT_B200_OK;
+    if (lanes == 2) {
+        cudaEventRecord(join, lane_stream[1]);
+        cudaStreamWaitEvent(s, join, 0);
+        cudaEventDestroy(fork);
+        cudaEventDestroy(join);
+    }
+    return rc;
+}
+
+template <typename T, bool kForward>
+size_t plan_workspace_elems(const plan::Plan &pl, int64_t B, int q_count)
+{
+    const size_t plane_ws = pl.ws_slot_elems[0] + pl.ws_slot_elems[1];
+    const WaveCfg wc = wave_config(B * q_count, q_count, plane_ws * sizeof(T));
+    return plane_ws * (size_t)wc.planes * wc.lanes;
 }
 
 }  // namespace
@@ -188,7 +266,7 @@ size_t fused_adrt_workspace_elems(int64_t B, int64_t n, int q_count)
 {
     plan::Plan pl;
     if (n > kMaxN || !plan::make_forward_plan(n, sizeof(T), &pl)) return (size_t)-1;
-    return (pl.ws_slot_elems[0] + pl.ws_slot_elems[1]) * q_count * (size_t)wave_images(B);
+    return plan_workspace_elems<T, true>(pl, B, q_count);
 }
 
 template <typename T>
@@ -196,7 +274,7 @@ size_t fused_bdrt_workspace_elems(int64_t B, int64_t n, int q_count)
 {
     plan::Plan pl;
     if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl)) return (size_t)-1;
-    return (pl.ws_slot_elems[0] + pl.ws_slot_elems[1]) * q_count * (size_t)wave_images(B);
+    return plan_workspace_elems<T, false>(pl, B, q_count);
 }
 
 template <typename T>

@@ -14,9 +14,14 @@ struct PassArgs {
     int planes;
     int x_off;              // first d-tile of this launch (streaming passes launch interior and boundary tiles separately)
     int q_first, q_count;   // image loader: plane -> (image = plane / q_count, quadrant = q_first + plane % q_count)
+    int plane0;             // image loader: index of this launch's first plane in the batch (waves, see run_plan)
+    int side_idx;           // host only: which helper stream (aux_stream) takes the boundary tiles of this launch
 };
 
 // fp32 streaming passes (plan::Pass::stream); defined in stream_adrt.cu
+// helper streams of the current device (0: boundary tiles, 1: odd waves, 2: boundary tiles of odd waves); nullptr on failure
+cudaStream_t aux_stream(int idx);
+
 int launch_stream_pass(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a, cudaStream_t s);
 
 }  // namespace adrt_b200

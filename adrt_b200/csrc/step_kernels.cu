@@ -141,11 +141,39 @@ bdrt_step_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, 
     }
 }
 
+// Same outputs, CTA = 32 offsets x 32 columns (8 threads of 4 columns per offset): the operands of
+// an odd block sit on a diagonal of the input, in[d + ci][2 ci ..], so the 32-byte sector a thread
+// touches is shared with the 3 offsets below it -- a 2-D CTA finds them in L1 instead of L2
+// (a CTA spanning one offset row re-reads every sector 4 times).  n % 32 == 0.
+template <typename T, bool kCore>
+__global__ void __launch_bounds__(256)
+bdrt_step_tiled_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int logn, int adrt_iter)
+{
+    const int64_t D = 2 * (int64_t)n - 1;
+    const int ctiles = n >> 5;
+    const int ct = blockIdx.x & (ctiles - 1), dt = blockIdx.x >> (logn - 5);
+    const int c = ct * 32 + (threadIdx.x & 7) * 4;
+    const int64_t d = (int64_t)dt * 32 + (threadIdx.x >> 3);
+    if (d >= D) return;
+    for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
+        const T *I = in + p * D * n;
+        T v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = bdrt_step_one<T, kCore>(I, d, c + i, n, D, adrt_iter);
+        store_outvec<T, 4>(out + p * D * n + d * n + c, v);
+    }
+}
+
 // ---- iadrt stage: adrt_cdefs_iadrt.hpp:52-105 in the Q-layout -----------------
 // One thread per (plane, output column); the offset axis is walked serially
 // from D-1 down (the reference's "must be serial" loop, iadrt.hpp:73-98) with
 // the running value kept in a register.  Adjacent threads own adjacent
-// columns, so every load and store is coalesced.
+// columns, so every load and store is coalesced.  Only the running sum is
+// serial: the operands of kIadrtBatch rows are fetched together before the
+// chain of adds consumes them, which keeps enough loads in flight to hide the
+// DRAM latency (one row at a time is latency bound at a quarter of the bandwidth).
+constexpr int kIadrtBatch = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 iadrt_stage_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int stage)
@@ -157,22 +185,43 @@ iadrt_stage_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes
     const int l = co / C, col = co - l * C;
     const int A = (l >> 1) * Cin + 2 * col;
     const bool even = (l & 1) == 0;
+    // even l: rows d and d+1; odd l: row d+1+col twice -- both as (row ra, column ca) and (row rb, column cb)
+    const int64_t ra_off = even ? 0 : 1 + col, rb_off = 1 + (even ? 0 : col);
+    const int ca = even ? A : A + 1, cb = even ? A + 1 : A;
     for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
         const T *I = in + p * D * n;
         T *O = out + p * D * n;
         T prev = T(0);
-        for (int64_t d = D - 1; d >= 0; --d) {
-            T val = T(0);
-            if (even) {
-                val += I[d * n + A];
-                if (d + 1 < D) val -= I[(d + 1) * n + A + 1];
-            } else if (d + 1 + col < D) {
-                val += I[(d + 1 + col) * n + A + 1];
-                val -= I[(d + 1 + col) * n + A];
+        for (int64_t dtop = D - 1; dtop >= 0; dtop -= kIadrtBatch) {
+            T a[kIadrtBatch], b[kIadrtBatch];
+#pragma unroll
+            for (int u = 0; u < kIadrtBatch; ++u) {
+                const int64_t d = dtop - u;
+                a[u] = T(0);
+                b[u] = T(0);
+                if (d >= 0) {
+                    // even: a always exists, b needs d+1 < D; odd: both need d+1+col < D
+                    if (d + ra_off < D) a[u] = I[(d + ra_off) * n + ca];
+                    if (d + rb_off < D) b[u] = I[(d + rb_off) * n + cb];
+                }
             }
-            if (d + 1 < D) val += prev;
-            O[d * n + co] = val;
-            prev = val;
+#pragma unroll
+            for (int u = 0; u < kIadrtBatch; ++u) {
+                const int64_t d = dtop - u;
+                if (d >= 0) {
+                    T val = T(0);
+                    if (even) {
+                        val += a[u];
+                        if (d + 1 < D) val -= b[u];
+                    } else if (d + 1 + col < D) {
+                        val += a[u];
+                        val -= b[u];
+                    }
+                    if (d + 1 < D) val += prev;
+                    O[d * n + co] = val;
+                    prev = val;
+                }
+            }
         }
     }
 }
@@ -501,6 +550,13 @@ int launch_bdrt_step(const T *in, T *out, int64_t B, int64_t n, int step, bool c
     const int64_t D = 2 * n - 1;
     const int adrt_iter = num_iters(n) - 1 - step;
     const bool vec = n % 4 == 0 && aligned_to(out, 4 * sizeof(T));
+    if (vec && n % 32 == 0) {
+        const dim3 tg = plane_grid(((D + 31) / 32) * (n / 32) * 256, B * 4);
+        if (core_semantics) bdrt_step_tiled_kernel<T, true><<<tg, 256, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
+        else bdrt_step_tiled_kernel<T, false><<<tg, 256, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
+        ADRT_LAUNCH_CHECK();
+        return ADRT_B200_OK;
+    }
     const dim3 grid = plane_grid(vec ? D * n / 4 : D * n, B * 4);
     if (core_semantics && vec) bdrt_step_kernel<T, true, 4><<<grid, kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);
     else if (core_semantics) bdrt_step_kernel<T, true, 1><<<grid, kThreads, 0, s>>>(in, out, B * 4, (int)n, ilog2(n), adrt_iter);

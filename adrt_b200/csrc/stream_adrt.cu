@@ -53,8 +53,9 @@ stream_kernel(const float *__restrict__ src, float *__restrict__ dst, PassArgs a
     for (int plane = blockIdx.z; plane < a.planes; plane += gridDim.z) {
         const float *sp;
         if (Prog::kImage) {
-            c.q = a.q_first + plane % a.q_count;
-            sp = src + (long long)(plane / a.q_count) * a.src_plane_stride;
+            const int gp = plane + a.plane0;
+            c.q = a.q_first + gp % a.q_count;
+            sp = src + (long long)(gp / a.q_count) * a.src_plane_stride;
         } else {
             sp = src + (long long)plane * a.src_plane_stride;
         }
@@ -97,16 +98,6 @@ int dispatch_fwd(const plan::Pass &p, const float *src, float *dst, const PassAr
 
 // A per-device helper stream: the few, slow boundary tiles run beside the interior tiles
 // instead of after them (fork / join with events around the two launches).
-cudaStream_t side_stream()
-{
-    static std::mutex mu;
-    static cudaStream_t streams[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
-    return streams[dev];
-}
 
 // interior tiles and the tiles that reach offset D run as two launches (see BwdStream::phase_ct)
 template <int M, int LOADK, int STOREK>
@@ -115,7 +106,7 @@ int launch_bwd(const plan::Pass &p, const float *src, float *dst, const PassArgs
     int xm = stile::BwdStream<M, LOADK, STOREK, false>::first_masked_tile(a.D);
     if (xm > p.grid_x) xm = p.grid_x;
     const int nmask = p.grid_x - xm;
-    cudaStream_t side = (xm > 0 && nmask > 0) ? side_stream() : nullptr;
+    cudaStream_t side = (xm > 0 && nmask > 0) ? aux_stream(a.side_idx) : nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
     if (side) {
         if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -155,6 +146,18 @@ int dispatch_bwd(const plan::Pass &p, const float *src, float *dst, const PassAr
 }
 
 }  // namespace
+
+cudaStream_t aux_stream(int idx)
+{
+    static std::mutex mu;
+    static cudaStream_t streams[64][3] = {};
+    int dev = 0;
+    if (idx < 0 || idx > 2 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev][idx] && cudaStreamCreateWithFlags(&streams[dev][idx], cudaStreamNonBlocking) != cudaSuccess)
+        streams[dev][idx] = nullptr;
+    return streams[dev][idx];
+}
 
 int launch_stream_pass(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a, cudaStream_t s)
 {

@@ -38,7 +38,7 @@ def timeit(fn, reps=5):
 
 
 for cfg in configs:
-    for k in ("ADRT_B200_SPLIT", "ADRT_B200_SPLIT_BDRT", "ADRT_B200_WAVE", "ADRT_B200_STREAM_SET"):
+    for k in ("ADRT_B200_SPLIT", "ADRT_B200_SPLIT_BDRT", "ADRT_B200_WAVE", "ADRT_B200_STREAM_SET", "ADRT_B200_WAVE_PLANES", "ADRT_B200_WAVE_LANES", "ADRT_B200_L2_PERSIST_MB"):
         os.environ.pop(k, None)
     for k, v in cfg.items():
         if k == "mode":
