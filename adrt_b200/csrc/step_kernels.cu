@@ -14,6 +14,8 @@
 // a lone add, and -fmad=false is set for the whole library anyway.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace adrt_b200 {
 
 namespace {
@@ -172,42 +174,43 @@ bdrt_step_tiled_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t pl
 // serial: the operands of kIadrtBatch rows are fetched together before the
 // chain of adds consumes them, which keeps enough loads in flight to hide the
 // DRAM latency (one row at a time is latency bound at a quarter of the bandwidth).
-constexpr int kIadrtBatch = 8;
 
-template <typename T>
+template <typename T, int kIadrtBatch>
 __global__ void __launch_bounds__(128)
 iadrt_stage_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int stage)
 {
-    const int64_t D = 2 * (int64_t)n - 1;
+    // in-plane offsets fit 32 bits (n <= 16384: D * n < 2^30)
+    const int D = 2 * n - 1;
     const int co = blockIdx.x * 128 + threadIdx.x;
     if (co >= n) return;
     const int Cin = n >> stage, C = Cin >> 1;
     const int l = co / C, col = co - l * C;
     const int A = (l >> 1) * Cin + 2 * col;
     const bool even = (l & 1) == 0;
-    // even l: rows d and d+1; odd l: row d+1+col twice -- both as (row ra, column ca) and (row rb, column cb)
-    const int64_t ra_off = even ? 0 : 1 + col, rb_off = 1 + (even ? 0 : col);
+    // even l: a = in[d][A], b = in[d+1][A+1]; odd l: a = in[d+1+col][A+1], b = in[d+1+col][A]
+    const int ra_off = even ? 0 : 1 + col, rb_off = 1 + (even ? 0 : col);
     const int ca = even ? A : A + 1, cb = even ? A + 1 : A;
     for (int64_t p = blockIdx.y; p < planes; p += gridDim.y) {
-        const T *I = in + p * D * n;
-        T *O = out + p * D * n;
+        const T *Ia = in + p * (int64_t)D * n + ca;
+        const T *Ib = in + p * (int64_t)D * n + cb;
+        T *O = out + p * (int64_t)D * n + co;
         T prev = T(0);
-        for (int64_t dtop = D - 1; dtop >= 0; dtop -= kIadrtBatch) {
+        for (int dtop = D - 1; dtop >= 0; dtop -= kIadrtBatch) {
             T a[kIadrtBatch], b[kIadrtBatch];
 #pragma unroll
             for (int u = 0; u < kIadrtBatch; ++u) {
-                const int64_t d = dtop - u;
+                const int d = dtop - u;
                 a[u] = T(0);
                 b[u] = T(0);
                 if (d >= 0) {
                     // even: a always exists, b needs d+1 < D; odd: both need d+1+col < D
-                    if (d + ra_off < D) a[u] = I[(d + ra_off) * n + ca];
-                    if (d + rb_off < D) b[u] = I[(d + rb_off) * n + cb];
+                    if (d + ra_off < D) a[u] = Ia[(d + ra_off) * n];
+                    if (d + rb_off < D) b[u] = Ib[(d + rb_off) * n];
                 }
             }
 #pragma unroll
             for (int u = 0; u < kIadrtBatch; ++u) {
-                const int64_t d = dtop - u;
+                const int d = dtop - u;
                 if (d >= 0) {
                     T val = T(0);
                     if (even) {
@@ -218,7 +221,7 @@ iadrt_stage_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes
                         val -= b[u];
                     }
                     if (d + 1 < D) val += prev;
-                    O[d * n + co] = val;
+                    O[d * n] = val;
                     prev = val;
                 }
             }
@@ -571,7 +574,12 @@ int launch_iadrt_stage(const T *in, T *out, int64_t B, int64_t n, int stage, cud
 {
     const int64_t planes = B * 4;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)(planes < 65535 ? planes : 65535), 1);
-    iadrt_stage_kernel<T><<<grid, 128, 0, s>>>(in, out, planes, (int)n, stage);
+    // rows fetched together per thread: measured best 16 (fp32) / 12 (fp64) at 16 x 2048^2 (profiles/r01_ops.jsonl)
+    static const int batch_env = [] { const char *e = getenv("ADRT_B200_IADRT_BATCH"); return e ? atoi(e) : 0; }();
+    const int batch = batch_env > 0 ? batch_env : (sizeof(T) == 4 ? 16 : 12);
+    if (batch >= 16) iadrt_stage_kernel<T, 16><<<grid, 128, 0, s>>>(in, out, planes, (int)n, stage);
+    else if (batch >= 12) iadrt_stage_kernel<T, 12><<<grid, 128, 0, s>>>(in, out, planes, (int)n, stage);
+    else iadrt_stage_kernel<T, 8><<<grid, 128, 0, s>>>(in, out, planes, (int)n, stage);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }

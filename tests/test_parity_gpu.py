@@ -384,6 +384,33 @@ def test_native_fmg_step_equals_composed_operators(mode, dn, n, B):
         _eq(got.cpu().numpy(), O.iadrt_fmg_step(a.cpu().numpy()), "fmg_step vs oracle")
 
 
+@pytest.mark.parametrize("dn", list(DTYPES))
+@pytest.mark.parametrize("n,B", [(128, 3), (1024, 2), (2048, 1)])
+def test_step_kernels_large_vs_oracle(dn, n, B):
+    """iadrt (wide stages: lane-skewed odd columns through the shared-memory ring, pair loads),
+    bdrt_step (2-D CTAs) and adrt_step against the oracle at sizes where those kernels are chosen."""
+    dt = DTYPES[dn]
+    s = make_sino(77 + n, (B, 4, 2 * n - 1, n), dt)
+    _eq(adrt.iadrt(s), O.iadrt(s), f"iadrt n={n}")
+    K = O.num_iters(n)
+    for i in sorted({0, 1, K // 2, K - 2, K - 1}):
+        _eq(adrt.core.bdrt_step(s, i), O.bdrt_step(s, i), f"bdrt_step {i} n={n}")
+        _eq(adrt.core.adrt_step(s, i), O.adrt_step(s, i), f"adrt_step {i} n={n}")
+
+
+def test_step_kernels_misaligned_views():
+    """Device tensors that start at an odd element offset take the scalar kernels."""
+    import torch
+
+    n = 128
+    s = make_sino(5, (2, 4, 2 * n - 1, n), np.float32)
+    flat = torch.zeros(s.size + 1, dtype=torch.float32, device="cuda")
+    flat[1:] = torch.from_numpy(s).reshape(-1).cuda()
+    view = flat[1:].reshape(s.shape)
+    _eq(adrt.iadrt(view).cpu().numpy(), O.iadrt(s), "iadrt misaligned")
+    _eq(adrt.core.bdrt_step(view, 2).cpu().numpy(), O.bdrt_step(s, 2), "bdrt_step misaligned")
+
+
 def test_iadrt_roundtrip():
     # reference tests/test_iadrt.py:185-223
     for n in (16, 32):
