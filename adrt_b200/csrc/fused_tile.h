@@ -716,21 +716,12 @@ ADRT_HD T bmask(T v, int pos, int lim, bool odd)
 // previous step, 0 if the rows were loaded); JP = jp & 3 fixes the residues.
 // `dt` = D - d0 and `ag` = global base angle give each row's logical end:
 //   parent rows (block k0 at stage t+2): dt + ag*k0*4e;  node k=1: + ag*2e.
-template <typename T, bool kMask, int JP>
-ADRT_HD void bwd_radix4_chunk(const T *ip, long long P, int a, int x, int jp, int lim_p, int lim_1, T *o)
+// the arithmetic of one chunk on parent windows that are already in registers
+template <typename T, bool kMask>
+ADRT_HD void bwd_radix4_math(T (&g0)[VecOf<T>::L], T (&g1)[VecOf<T>::L + 1], T (&g2)[VecOf<T>::L + 2], T (&g3)[VecOf<T>::L + 3],
+                             int a, int x, int lim_p, int lim_1, T *o)
 {
-    // P = distance between the four parent rows (tile pitch, or the workspace pitch
-    // when the parents are read straight from global memory)
-    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
-    (void)CHUNKS;
-    constexpr int L = VecOf<T>::L;
-    constexpr int Q1 = (JP * 1) % L, Q2 = (JP * 2) % L, Q3 = (JP * 3) % L;
-    const int s0 = jp * 4 * a;  // skew of parent 0; parent p adds jp*p
-    T g0[V], g1[V + 1], g2[V + 2], g3[V + 3];
-    load_window<T, V, 0>(ip + x + s0, g0);
-    load_window<T, V + 1, Q1>(ip + P + (x + s0 + jp - Q1), g1);
-    load_window<T, V + 2, Q2>(ip + 2 * P + (x + s0 + 2 * jp - Q2), g2);
-    load_window<T, V + 3, Q3>(ip + 3 * P + (x + s0 + 3 * jp - Q3), g3);
+    constexpr int V = VecOf<T>::L;
     if (kMask) {
 #pragma unroll
         for (int i = 0; i < V; ++i) g0[i] = bmask<T, kMask>(g0[i], x + i, lim_p, false);
@@ -761,6 +752,23 @@ ADRT_HD void bwd_radix4_chunk(const T *ip, long long P, int a, int x, int jp, in
         o[2 * V + i] = u10[i] + u11[i];
         o[3 * V + i] = u10[i] + u11[i + 1];
     }
+}
+
+template <typename T, bool kMask, int JP>
+ADRT_HD void bwd_radix4_chunk(const T *ip, long long P, int a, int x, int jp, int lim_p, int lim_1, T *o)
+{
+    // P = distance between the four parent rows (tile pitch, or the workspace pitch
+    // when the parents are read straight from global memory)
+    constexpr int V = VecOf<T>::L;
+    constexpr int L = VecOf<T>::L;
+    constexpr int Q1 = (JP * 1) % L, Q2 = (JP * 2) % L, Q3 = (JP * 3) % L;
+    const int s0 = jp * 4 * a;  // skew of parent 0; parent p adds jp*p
+    T g0[V], g1[V + 1], g2[V + 2], g3[V + 3];
+    load_window<T, V, 0>(ip + x + s0, g0);
+    load_window<T, V + 1, Q1>(ip + P + (x + s0 + jp - Q1), g1);
+    load_window<T, V + 2, Q2>(ip + 2 * P + (x + s0 + 2 * jp - Q2), g2);
+    load_window<T, V + 3, Q3>(ip + 3 * P + (x + s0 + 3 * jp - Q3), g3);
+    bwd_radix4_math<T, kMask>(g0, g1, g2, g3, a, x, lim_p, lim_1, o);
 }
 
 // every window (and its over-fetch) must stay inside the row; chunks that fail
@@ -825,6 +833,55 @@ ADRT_HD void bwd_radix4_compute_global(const T *src_plane, const TileCtx &c, int
     for (int cc = 0; cc < CHUNKS; ++cc) {
         const int x = (lane + 32 * cc) * V;
         if (bwd_chunk_ok<T>(x, 0, a)) bwd_radix4_chunk<T, false, 0>(ip, c.in_pitch, a, x, 0, 0, 0, &o[cc * 4 * V]);
+    }
+}
+
+// First transposed step of a pass that reads the public (offset, column) layout: the four
+// parents of butterfly `a` are the four ADJACENT sinogram columns g*G + 4a .. 4a+3, i.e. one
+// 16-byte (fp32) / 32-byte (fp64) piece of every offset row, so the thread that fetches them
+// can run the radix-4 step on the spot and store the four children -- the tile is never staged
+// as loaded, which saves one tile write and the step's over-wide window reads (1.9 tile reads)
+// of shared-memory traffic.  Lanes walk the butterflies first (NB * 16 contiguous bytes per
+// offset row), then the chunks.  Children are stored exactly where bwd_radix4_store puts them.
+template <typename T, int M, bool kMask, int t>
+ADRT_HD void bwd_radix4_from_qcols(T *buf, const T *src_plane, const TileCtx &c, int tid)
+{
+    constexpr int W = VecOf<T>::L, G = Geo<M>::G, NT = Geo<M>::NT, P = Pitch<T>::value;
+    constexpr int e = 1 << t;
+    static_assert(4 * e == G, "the first step's butterflies span the whole group");
+    constexpr int NB = G / 4, SLOTS = NT / NB, NCH = XW / W, CPT = (NCH + SLOTS - 1) / SLOTS;
+    const int a = tid % NB, slot = tid / NB;
+    const long long n1 = c.n;
+    const int dt = c.D - c.d0;
+    const int lim_p = dt, lim_1 = dt + c.a_g * 2 * e;
+    const T *col = src_plane + (long long)c.d0 * n1 + c.g * G + 4 * a;
+    T *orow = buf + a * P;
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) {
+        const int x = (slot + cc * SLOTS) * W;
+        if (x >= XW || !bwd_chunk_ok<T>(x, 0, a)) continue;
+        T g0[W], g1[W + 1], g2[W + 2], g3[W + 3];
+#pragma unroll
+        for (int i = 0; i < W + 3; ++i) {
+            Pack<T> v[4 / W];
+            if (!kMask || x + i < dt) {
+#pragma unroll
+                for (int k = 0; k < 4 / W; ++k) v[k] = *reinterpret_cast<const Pack<T> *>(col + (long long)(x + i) * n1 + k * W);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4 / W; ++k)
+#pragma unroll
+                    for (int q = 0; q < W; ++q) v[k].v[q] = T(0.0);
+            }
+            if (i < W) g0[i] = v[0].v[0];
+            if (i < W + 1) g1[i] = v[1 / W].v[1 % W];
+            if (i < W + 2) g2[i] = v[2 / W].v[2 % W];
+            g3[i] = v[3 / W].v[3 % W];
+        }
+        T o[4 * W];
+        bwd_radix4_math<T, kMask>(g0, g1, g2, g3, a, x, lim_p, lim_1, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) store_cv<T>(orow + j * e * P + x, &o[j * W]);   // skew j*a
     }
 }
 
@@ -1101,6 +1158,10 @@ struct BwdProgram {
     // interior tiles of passes that read workspace rows and start with a radix-4 step
     // skip the staging copy: step 0 reads its windows from global memory
     static constexpr bool kDirect0 = LOADK == LOAD_WROWS && NS > 0 && (step_t(0) + 2 <= M);
+    // passes that read the public layout and start with a radix-4 step fuse that step into the
+    // loader (bwd_radix4_from_qcols); phases 1 and 2 are then empty
+    static constexpr bool kFusedLoad = LOADK == LOAD_QCOLS && NS > 0 && (step_t(0) + 2 <= M) && M >= 4 &&
+                                       (4 << step_t(0)) == G;
 
     ADRT_HD static int classify(const TileCtx &c)
     {
@@ -1121,7 +1182,12 @@ struct BwdProgram {
     template <int PH>
     ADRT_HD static void phase_ct(int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
     {
-        if constexpr (PH == 0) {
+        if constexpr (PH == 0 && kFusedLoad) {
+            if (mode == TILE_FULL_MASKED) bwd_radix4_from_qcols<T, M, true, step_t(0)>(buf, src, c, tid);
+            else bwd_radix4_from_qcols<T, M, false, step_t(0)>(buf, src, c, tid);
+        } else if constexpr (kFusedLoad && (PH == 1 || PH == 2)) {
+            // done in phase 0
+        } else if constexpr (PH == 0) {
             if (LOADK == LOAD_QCOLS) bwd_load_qcols<T, M>(buf, src, c, tid);
             else if (!(kDirect0 && mode == TILE_FULL)) bwd_load_wrows<T, M>(buf, src, c, tid);
         } else if constexpr (PH <= 2 * NS) {
