@@ -12,7 +12,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadrt_b200.so")
+# ADRT_B200_LIB names another build of the same library (A/B tuning of compile-time options)
+LIB_PATH = os.environ.get("ADRT_B200_LIB") or os.path.join(_HERE, "libadrt_b200.so")
 
 F32, F64 = 0, 1
 

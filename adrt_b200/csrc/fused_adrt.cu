@@ -25,8 +25,21 @@ __device__ __forceinline__ void all_phases(int mode, T *buf, T (&regs)[tile::NRE
     }
 }
 
+// resident CTAs the register allocation aims at (launch bound); ADRT_B5P_CTAS: A/B tuning of the
+// fp32 five-stage transposed pass that reads the public layout (fused loader + radix-4 step)
+#ifndef ADRT_B5P_CTAS
+#define ADRT_B5P_CTAS 5
+#endif
+template <typename T, int M, int LOADK, bool kForward>
+constexpr int min_ctas()
+{
+    if (sizeof(T) == 8) return tile::Geo<M>::MIN_CTAS / 2;
+    if (!kForward && LOADK == tile::LOAD_QCOLS && M == 5) return ADRT_B5P_CTAS;
+    return tile::Geo<M>::MIN_CTAS;
+}
+
 template <typename T, int M, int LOADK, int STOREK, bool kForward>
-__global__ void __launch_bounds__(tile::Geo<M>::NT, sizeof(T) == 8 ? tile::Geo<M>::MIN_CTAS / 2 : tile::Geo<M>::MIN_CTAS)
+__global__ void __launch_bounds__(tile::Geo<M>::NT, min_ctas<T, M, LOADK, kForward>())
 pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
 {
     using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,

@@ -293,18 +293,12 @@ constexpr int NREG = 32;   // outputs a thread holds across the barrier of a ste
 //   out[p][d]    = u[0][p>>1][d] + u[1][p>>1][d - 2a - ceil(p/2)]     (stage t+1)
 // with input rows r_j = (k0*4 + j)*e + a, output rows k0*4e + 4a + p.
 // AM = a & 3 fixes the alignment residues of the three shifted windows.
-template <typename T, int AM>
-ADRT_HD void fwd_radix4_chunk(const T *r0, const T *r1, const T *r2, const T *r3, int a, int x, T *o)
+// the arithmetic of one chunk on operand windows that are already in registers
+template <typename T>
+ADRT_HD void fwd_radix4_math(const T (&y0)[VecOf<T>::L], const T (&y1)[VecOf<T>::L + 1], const T (&y2)[VecOf<T>::L + 2],
+                             const T (&y3)[VecOf<T>::L + 3], T *o)
 {
-    constexpr int V = VecOf<T>::L, CHUNKS = XW / (32 * V);  // chunk = one 16-byte vector
-    (void)CHUNKS;
-    constexpr int L = VecOf<T>::L;
-    constexpr int Q1 = neg_mod(AM + 1, L), Q2 = neg_mod(2 * AM + 2, L), Q3 = neg_mod(3 * AM + 3, L);
-    T y0[V], y1[V + 1], y2[V + 2], y3[V + 3];
-    load_window<T, V, 0>(r0 + x, y0);
-    load_window<T, V + 1, Q1>(r1 + (x - a - 1 - Q1), y1);
-    load_window<T, V + 2, Q2>(r2 + (x - 2 * a - 2 - Q2), y2);
-    load_window<T, V + 3, Q3>(r3 + (x - 3 * a - 3 - Q3), y3);
+    constexpr int V = VecOf<T>::L;
     T u00[V], u01[V], u10[V + 2], u11[V + 2];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -323,6 +317,20 @@ ADRT_HD void fwd_radix4_chunk(const T *r0, const T *r1, const T *r2, const T *r3
         o[2 * V + i] = u01[i] + u11[i + 1];
         o[3 * V + i] = u01[i] + u11[i];
     }
+}
+
+template <typename T, int AM>
+ADRT_HD void fwd_radix4_chunk(const T *r0, const T *r1, const T *r2, const T *r3, int a, int x, T *o)
+{
+    constexpr int V = VecOf<T>::L;
+    constexpr int L = VecOf<T>::L;
+    constexpr int Q1 = neg_mod(AM + 1, L), Q2 = neg_mod(2 * AM + 2, L), Q3 = neg_mod(3 * AM + 3, L);
+    T y0[V], y1[V + 1], y2[V + 2], y3[V + 3];
+    load_window<T, V, 0>(r0 + x, y0);
+    load_window<T, V + 1, Q1>(r1 + (x - a - 1 - Q1), y1);
+    load_window<T, V + 2, Q2>(r2 + (x - 2 * a - 2 - Q2), y2);
+    load_window<T, V + 3, Q3>(r3 + (x - 3 * a - 3 - Q3), y3);
+    fwd_radix4_math<T>(y0, y1, y2, y3, o);
 }
 
 template <typename T, int AM>
@@ -449,6 +457,105 @@ ADRT_HD void fwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
                 store_cv<T>(orow + P + x, &o[((u * CHUNKS + c) * 2 + 1) * V]);
             }
         }
+    }
+}
+
+// Image loader that also performs local stages 0 and 1 (first pass: e = 1, a_g = 0).  The four
+// parents of butterfly k0 are the oriented image rows 4*k0 .. 4*k0+3 of the group:
+//   q1, q2: four ADJACENT image columns -- one 16/32-byte piece of every image row the tile
+//           needs; lanes = (butterfly pair, 4 chunks) so that a warp reads whole 128-byte row
+//           pieces and its stores hit 8 distinct 16-byte bank groups;
+//   q0, q3: four image rows read along the row (reversed): lanes walk the chunks.
+// The thread runs the radix-4 step on what it fetched and stores the four children where
+// fwd_radix4_store would put them: the tile is never staged as loaded (one tile write and the
+// step's 1.9 tile reads of shared-memory traffic less).  Offsets below 0 are -0.0, offsets
+// >= n are +0.0 (same rule as fwd_load_image).  Needs ~64 registers for its 4 x 7 operands: used
+// by the fp64 passes (128 registers anyway); fp32 five-stage passes are faster with the plain
+// loader at 48 registers / 5 CTAs per SM (measured 292 vs 315 us, profiles/r01_pass_kinds.txt).
+template <typename T, int M, int LH>
+ADRT_HD void fwd_radix4_from_image(T *buf, const T *img, const TileCtx &c, int tid)
+{
+    constexpr int W = VecOf<T>::L, G = Geo<M>::G, NT = Geo<M>::NT, P = Pitch<T>::value;
+    constexpr int NB = G / 4, NCH = XW / W, JOBS = NB * NCH, ROUNDS = (JOBS + NT - 1) / NT;
+    static_assert(NB >= 2 && NB % 2 == 0, "lanes pair the butterflies");
+    const int n = c.n;
+    const int dbase = c.d0 - LH;
+    const bool cols = (c.q == 1 || c.q == 2);
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int job = tid + rd * NT;
+        if (job >= JOBS) continue;
+        int k0, chunk;
+        if (cols) {
+            const int rest = job >> 3;
+            k0 = 2 * (rest % (NB / 2)) + (job & 1);
+            chunk = 4 * (rest / (NB / 2)) + ((job >> 1) & 3);
+        } else {
+            k0 = job / NCH;
+            chunk = job % NCH;
+        }
+        const int x = chunk * W;
+        if (x < 4) continue;                 // lo_out of the step: windows would start below the tile
+        const int r0 = c.g * G + 4 * k0;     // oriented image row of parent 0
+        const int dlo = dbase + x - 3;       // offset of window element 0
+        T w[4][W + 3];                       // w[j][i] = parent j at offset dlo + i
+        if (cols && dlo >= 0 && dlo + W + 3 <= n) {
+#pragma unroll
+            for (int i = 0; i < W + 3; ++i) {
+                const int d = dlo + i;
+                const T *rp = img + (long long)(c.q == 1 ? n - 1 - d : d) * n + r0;
+#pragma unroll
+                for (int k = 0; k < 4 / W; ++k) {
+                    const Pack<T> v = *reinterpret_cast<const Pack<T> *>(rp + k * W);
+#pragma unroll
+                    for (int q = 0; q < W; ++q) w[k * W + q][i] = v.v[q];
+                }
+            }
+        } else if (!cols && dbase + x >= 4 && dbase + x + W <= n) {
+            // offsets dlo .. dlo+W+2 are the columns col_lo+W+2 .. col_lo of the image row
+            constexpr int NP = (2 * W + 2) / W;
+            const int col_lo = n - dbase - x - W;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const T *rp = img + (long long)(c.q == 0 ? r0 + j : n - 1 - (r0 + j)) * n + col_lo;
+                Pack<T> v[NP];
+#pragma unroll
+                for (int k = 0; k < NP; ++k) v[k] = *reinterpret_cast<const Pack<T> *>(rp + k * W);
+#pragma unroll
+                for (int i = 0; i < W + 3; ++i) w[j][i] = v[(W + 2 - i) / W].v[(W + 2 - i) % W];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + j;
+#pragma unroll
+                for (int i = 0; i < W + 3; ++i) {
+                    const int d = dlo + i;
+                    T v;
+                    if (d < 0) v = T(-0.0);
+                    else if (d >= n) v = T(0.0);
+                    else if (c.q == 0) v = img[(long long)r * n + (n - 1 - d)];
+                    else if (c.q == 1) v = img[(long long)(n - 1 - d) * n + r];
+                    else if (c.q == 2) v = img[(long long)d * n + r];
+                    else v = img[(long long)(n - 1 - r) * n + (n - 1 - d)];
+                    w[j][i] = v;
+                }
+            }
+        }
+        T y0[W], y1[W + 1], y2[W + 2], y3[W + 3];
+#pragma unroll
+        for (int i = 0; i < W; ++i) y0[i] = w[0][i + 3];
+#pragma unroll
+        for (int i = 0; i < W + 1; ++i) y1[i] = w[1][i + 2];
+#pragma unroll
+        for (int i = 0; i < W + 2; ++i) y2[i] = w[2][i + 1];
+#pragma unroll
+        for (int i = 0; i < W + 3; ++i) y3[i] = w[3][i];
+        T o[4 * W];
+        fwd_radix4_math<T>(y0, y1, y2, y3, o);
+        T *orow = buf + (4 * k0) * P + x;
+#pragma unroll
+        for (int p4 = 0; p4 < 4; ++p4) store_cv<T>(orow + p4 * P, &o[p4 * W]);
     }
 }
 
@@ -1097,6 +1204,9 @@ struct FwdProgram {
     static constexpr bool kFused0 = (M & 1) && LOADK == LOAD_WROWS;
     static constexpr int NS = kFused0 ? (M - 1) / 2 : num_steps(M);
     static constexpr int kPhases = 2 + 2 * NS;
+    // fp64 image passes of 4+ stages fuse the first radix-4 step into the loader
+    // (fwd_radix4_from_image); phases 1 and 2 are then empty
+    static constexpr bool kFusedLoad = LOADK == LOAD_IMAGE && M >= 4 && sizeof(T) == 8;
     static constexpr int TD = TileTD<M, STOREK>::value;   // offsets produced per tile
     static constexpr int LH = XW - TD;                    // tile position of offset d0
 
@@ -1128,7 +1238,11 @@ struct FwdProgram {
     ADRT_HD static void phase_ct(int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
     {
         (void)mode;
-        if constexpr (PH == 0) {
+        if constexpr (PH == 0 && kFusedLoad) {
+            fwd_radix4_from_image<T, M, LH>(buf, src, c, tid);
+        } else if constexpr (kFusedLoad && (PH == 1 || PH == 2)) {
+            // done in phase 0
+        } else if constexpr (PH == 0) {
             if (LOADK == LOAD_IMAGE) fwd_load_image<T, M, LH>(buf, src, c, tid);
             else if (kFused0) fwd_load_wrows_stage0<T, M, LH>(buf, src, c, tid);
             else fwd_load_wrows<T, M, LH>(buf, src, c, tid);
