@@ -113,7 +113,10 @@ inline bool use_stream(int M, size_t elem_size, bool forward, int load)
     if (elem_size != 4 || (M != 5 && M != 6)) return false;
     char key[4] = {forward ? 'f' : 'b', (char)('0' + M), load == tile::LOAD_WROWS ? 'w' : 'p', 0};
     const char *set = getenv("ADRT_B200_STREAM_SET");
-    if (!set) set = "f6p,f6w,f5w,b6w,b5w,b6p";
+    // b5p / b6p / f5p: the fused_tile.h kernels win -- their loader runs the first radix-4 step on the
+    // public-layout columns it fetches (16 x 4096^2 bdrt: 8.9 ms with a streaming b6p, 7.3 ms without)
+    // f6p: 16 x 4096^2 adrt 5.53 ms streaming, 5.31 ms with fused_tile.h's fused image loader
+    if (!set) set = "f6w,f5w,b6w,b5w";
     if (!strcmp(set, "all")) return true;
     return strstr(set, key) != nullptr;
 }

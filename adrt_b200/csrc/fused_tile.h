@@ -470,8 +470,8 @@ ADRT_HD void fwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
 // fwd_radix4_store would put them: the tile is never staged as loaded (one tile write and the
 // step's 1.9 tile reads of shared-memory traffic less).  Offsets below 0 are -0.0, offsets
 // >= n are +0.0 (same rule as fwd_load_image).  Needs ~64 registers for its 4 x 7 operands: used
-// by the fp64 passes (128 registers anyway); fp32 five-stage passes are faster with the plain
-// loader at 48 registers / 5 CTAs per SM (measured 292 vs 315 us, profiles/r01_pass_kinds.txt).
+// by the fp64 passes (128 registers anyway) and the fp32 six-stage pass (64); fp32 five-stage passes
+// are faster with the plain loader at 48 registers / 5 CTAs per SM (measured 292 vs 315 us).
 template <typename T, int M, int LH>
 ADRT_HD void fwd_radix4_from_image(T *buf, const T *img, const TileCtx &c, int tid)
 {
@@ -1204,9 +1204,9 @@ struct FwdProgram {
     static constexpr bool kFused0 = (M & 1) && LOADK == LOAD_WROWS;
     static constexpr int NS = kFused0 ? (M - 1) / 2 : num_steps(M);
     static constexpr int kPhases = 2 + 2 * NS;
-    // fp64 image passes of 4+ stages fuse the first radix-4 step into the loader
-    // (fwd_radix4_from_image); phases 1 and 2 are then empty
-    static constexpr bool kFusedLoad = LOADK == LOAD_IMAGE && M >= 4 && sizeof(T) == 8;
+    // fp64 image passes of 4+ stages and the fp32 six-stage one (64 registers anyway) fuse the first
+    // radix-4 step into the loader (fwd_radix4_from_image); phases 1 and 2 are then empty
+    static constexpr bool kFusedLoad = LOADK == LOAD_IMAGE && M >= 4 && (sizeof(T) == 8 || M == 6);
     static constexpr int TD = TileTD<M, STOREK>::value;   // offsets produced per tile
     static constexpr int LH = XW - TD;                    // tile position of offset d0
 
