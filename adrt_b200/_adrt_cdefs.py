@@ -175,6 +175,26 @@ def _empty_like(arr: _Arr, shape, out):
     return np.empty(shape, dtype=arr.np_dtype)
 
 
+# The fused transforms (adrt, bdrt and the helpers built on them) use 16/32-byte vector accesses and
+# the C ABI asks for 32-byte aligned device pointers.  Allocator-owned tensors always are; a view that
+# starts mid-allocation is staged through fresh storage.  (The step kernels, iadrt and the FMG
+# operators pick scalar variants for such pointers themselves.)
+_VEC_OPS = frozenset({"adrt", "bdrt"})
+
+
+def _vec_in(t):
+    return t if t.data_ptr() % 32 == 0 else t.clone()
+
+
+def _vec_out(ret):
+    """(tensor to hand to the kernel, copy-back needed)."""
+    if ret.data_ptr() % 32 == 0:
+        return ret, False
+    import torch
+
+    return torch.empty_like(ret), True
+
+
 def _run(name, arr: _Arr, out_shape, dims, out=None, step=None, workspace=None, extra=()):
     """Dispatch to adrt_b200_host_<name> (NumPy) or adrt_b200_<name> (CUDA tensor).
 
@@ -197,15 +217,21 @@ def _run(name, arr: _Arr, out_shape, dims, out=None, step=None, workspace=None, 
     with torch.cuda.device(t.device):
         stream = torch.cuda.current_stream().cuda_stream
         fn = getattr(lib, f"adrt_b200_{name}")
+        dst, copy_back = ret, False
+        if name in _VEC_OPS:
+            t = _vec_in(t)
+            dst, copy_back = _vec_out(ret)
         if workspace is not None:
             nbytes = getattr(lib, f"adrt_b200_{workspace}_workspace_bytes")(*dims, code)
             ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=t.device)
             # `ws` is freed to torch's caching allocator on return; the allocator only
             # re-issues it to work queued later on this same stream, so that is safe.
-            rc = fn(t.data_ptr(), ret.data_ptr(), *dims, *step_args, code, ws.data_ptr(), int(nbytes), stream)
+            rc = fn(t.data_ptr(), dst.data_ptr(), *dims, *step_args, code, ws.data_ptr(), int(nbytes), stream)
         else:
-            rc = fn(t.data_ptr(), ret.data_ptr(), *dims, *step_args, *extra, code, stream)
-    _lib.check(rc, name)
+            rc = fn(t.data_ptr(), dst.data_ptr(), *dims, *step_args, *extra, code, stream)
+        _lib.check(rc, name)
+        if copy_back:
+            ret.copy_(dst)
     return ret
 
 
@@ -369,9 +395,13 @@ def fmg_step(a, /, *, out=None):
     with torch.cuda.device(arr.obj.device):
         nbytes = int(lib.adrt_b200_fmg_step_workspace_bytes(b, n, code))
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=arr.obj.device)
-        rc = lib.adrt_b200_fmg_step(arr.obj.data_ptr(), ret.data_ptr(), b, n, code, ws.data_ptr(), nbytes,
+        src = _vec_in(arr.obj)
+        dst, copy_back = _vec_out(ret)
+        rc = lib.adrt_b200_fmg_step(src.data_ptr(), dst.data_ptr(), b, n, code, ws.data_ptr(), nbytes,
                                     torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc, "fmg_step")
+        _lib.check(rc, "fmg_step")
+        if copy_back:
+            ret.copy_(dst)
     return ret
 
 
@@ -450,9 +480,13 @@ def adrt_quadrants(a, q_first, q_count, /, *, out=None):
     with torch.cuda.device(t.device):
         nbytes = lib.adrt_b200_adrt_quadrants_workspace_bytes(b, c, code, q_count)
         ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=t.device)
-        rc = lib.adrt_b200_adrt_quadrants(t.data_ptr(), ret.data_ptr(), b, c, code, q_first, q_count,
+        t = _vec_in(t)
+        dst, copy_back = _vec_out(ret)
+        rc = lib.adrt_b200_adrt_quadrants(t.data_ptr(), dst.data_ptr(), b, c, code, q_first, q_count,
                                           ws.data_ptr(), int(nbytes), torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc, "adrt_quadrants")
+        _lib.check(rc, "adrt_quadrants")
+        if copy_back:
+            ret.copy_(dst)
     return ret
 
 
@@ -483,13 +517,17 @@ def bdrt_planes(a, /, *, out=None, rows=None):
     with torch.cuda.device(a.device):
         nbytes = lib.adrt_b200_bdrt_planes_workspace_bytes(planes, n, code)
         ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=a.device)
+        a = _vec_in(a)
+        dst, copy_back = _vec_out(ret)
         if rows is None:
-            rc = lib.adrt_b200_bdrt_planes(a.data_ptr(), ret.data_ptr(), planes, n, code, ws.data_ptr(), int(nbytes),
+            rc = lib.adrt_b200_bdrt_planes(a.data_ptr(), dst.data_ptr(), planes, n, code, ws.data_ptr(), int(nbytes),
                                            torch.cuda.current_stream().cuda_stream)
         else:
-            rc = lib.adrt_b200_bdrt_rows(a.data_ptr(), ret.data_ptr(), planes, n, int(rows), code, ws.data_ptr(),
+            rc = lib.adrt_b200_bdrt_rows(a.data_ptr(), dst.data_ptr(), planes, n, int(rows), code, ws.data_ptr(),
                                          int(nbytes), torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc, "bdrt_planes")
+        _lib.check(rc, "bdrt_planes")
+        if copy_back:
+            ret.copy_(dst)
     return ret
 
 

@@ -31,6 +31,14 @@ namespace {
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// entry points that run the fused passes (16/32-byte vector accesses on the caller's arrays)
+int check_vec_aligned(const void *in, const void *out, const void *ws)
+{
+    auto ok = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 32 == 0; };
+    ADRT_REQUIRE(ok(in) && ok(out) && ok(ws), "device pointers must be 32-byte aligned");
+    return ADRT_B200_OK;
+}
+
 int check_image(const void *in, const void *out, int64_t B, int64_t n, int dtype)
 {
     ADRT_REQUIRE(in && out, "null pointer argument");
@@ -383,6 +391,7 @@ int adrt_b200_adrt(const void *in, void *out, int64_t B, int64_t n, int dtype, v
 {
     int rc = check_image(in, out, B, n, dtype);
     if (rc) return rc;
+    if ((rc = check_vec_aligned(in, out, ws))) return rc;
     return DISPATCH(dtype,
                     adrt_impl<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes, as_stream(stream)),
                     adrt_impl<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes, as_stream(stream)));
@@ -398,6 +407,7 @@ int adrt_b200_bdrt(const void *in, void *out, int64_t B, int64_t n, int dtype, v
 {
     int rc = check_image(in, out, B, n, dtype);
     if (rc) return rc;
+    if ((rc = check_vec_aligned(in, out, ws))) return rc;
     return DISPATCH(dtype,
                     bdrt_impl<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes, as_stream(stream)),
                     bdrt_impl<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes, as_stream(stream)));
@@ -415,6 +425,7 @@ int adrt_b200_adrt_quadrants(const void *in, void *out, int64_t B, int64_t n, in
 {
     int rc = check_image(in, out, B, n, dtype);
     if (rc) return rc;
+    if ((rc = check_vec_aligned(in, out, ws))) return rc;
     ADRT_REQUIRE(q_first >= 0 && q_count >= 1 && q_first + q_count <= 4, "bad quadrant range %d+%d", q_first, q_count);
     return DISPATCH(dtype,
                     adrt_quadrants_impl<float>((const float *)in, (float *)out, B, n, q_first, q_count, (float *)ws, ws_bytes, as_stream(stream)),
@@ -432,6 +443,7 @@ int adrt_b200_bdrt_planes(const void *in, void *out, int64_t planes, int64_t n, 
 {
     int rc = check_image(in, out, planes, n, dtype);
     if (rc) return rc;
+    if ((rc = check_vec_aligned(in, out, ws))) return rc;
     return DISPATCH(dtype,
                     bdrt_planes_impl<float>((const float *)in, (float *)out, planes, n, -1, (float *)ws, ws_bytes, as_stream(stream)),
                     bdrt_planes_impl<double>((const double *)in, (double *)out, planes, n, -1, (double *)ws, ws_bytes, as_stream(stream)));
@@ -442,6 +454,7 @@ int adrt_b200_bdrt_rows(const void *in, void *out, int64_t planes, int64_t n, in
 {
     int rc = check_image(in, out, planes, n, dtype);
     if (rc) return rc;
+    if ((rc = check_vec_aligned(in, out, ws))) return rc;
     ADRT_REQUIRE(rows >= 1 && rows <= 2 * n - 1, "rows %lld out of range", (long long)rows);
     return DISPATCH(dtype,
                     bdrt_planes_impl<float>((const float *)in, (float *)out, planes, n, rows, (float *)ws, ws_bytes, as_stream(stream)),
@@ -536,6 +549,7 @@ int adrt_b200_fmg_step(const void *in, void *out, int64_t B, int64_t n, int dtyp
 {
     int rc = check_image(in, out, B, n, dtype);
     if (rc) return rc;
+    if ((rc = check_vec_aligned(in, out, ws))) return rc;
     return DISPATCH(dtype,
                     fmg_step_impl<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes, as_stream(stream)),
                     fmg_step_impl<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes, as_stream(stream)));

@@ -20,7 +20,11 @@
  *   adrt_b200_<op>(...)       device pointers, asynchronous on `stream`,
  *                             caller-provided workspace (size from
  *                             adrt_b200_<op>_workspace_bytes), no allocation,
- *                             no synchronisation.
+ *                             no synchronisation.  Device pointers (input,
+ *                             output, workspace) must be 32-byte aligned --
+ *                             the kernels use 16/32-byte vector accesses;
+ *                             cudaMalloc and framework allocators satisfy
+ *                             this, a misaligned pointer is ADRT_B200_EINVAL.
  *   adrt_b200_host_<op>(...)  host pointers (pageable or pinned); performs the
  *                             H2D / compute / D2H pipeline in batch chunks on
  *                             device `device` and returns when the output is

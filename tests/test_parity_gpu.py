@@ -409,6 +409,22 @@ def test_step_kernels_misaligned_views():
     view = flat[1:].reshape(s.shape)
     _eq(adrt.iadrt(view).cpu().numpy(), O.iadrt(s), "iadrt misaligned")
     _eq(adrt.core.bdrt_step(view, 2).cpu().numpy(), O.bdrt_step(s, 2), "bdrt_step misaligned")
+    # the fused transforms use 16/32-byte vector accesses: the shim copies such views
+    _eq(adrt.bdrt(view).cpu().numpy(), O.bdrt(s), "bdrt misaligned")
+    x = make_image(6, (2, n, n), np.float32)
+    flat = torch.zeros(x.size + 3, dtype=torch.float32, device="cuda")
+    flat[3:] = torch.from_numpy(x).reshape(-1).cuda()
+    _eq(adrt.adrt(flat[3:].reshape(x.shape)).cpu().numpy(), O.adrt(x), "adrt misaligned")
+    obuf = torch.zeros(2 * 4 * (2 * n - 1) * n + 1, device="cuda")
+    oview = obuf[1:].reshape(2, 4, 2 * n - 1, n)
+    got = adrt.adrt(torch.from_numpy(x).cuda(), out=oview)
+    assert got.data_ptr() == oview.data_ptr()
+    _eq(oview.cpu().numpy(), O.adrt(x), "adrt into a misaligned out")
+    # the C ABI itself refuses such pointers for the fused entry points instead of faulting
+    lib = _lib.load()
+    ws = torch.empty(int(lib.adrt_b200_adrt_workspace_bytes(2, n, 0)), dtype=torch.uint8, device="cuda")
+    rc = lib.adrt_b200_adrt(flat[3:].data_ptr(), oview.data_ptr(), 2, n, 0, ws.data_ptr(), ws.numel(), None)
+    assert rc != 0 and "aligned" in _lib.last_error()
 
 
 def test_iadrt_roundtrip():
