@@ -129,7 +129,9 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
     pl->n = n; pl->K = K; pl->D = 2 * n - 1;
     // fp32: the pass next to the public layout is the long one in both directions (it is a streaming
     // pass, stream_tile.h, and the fastest kernel per stage) -- measured 4.7 vs 5.05 ms at 64 x 2048^2
-    const std::vector<int> ms = split_stages(K, elem_size, "ADRT_B200_SPLIT", elem_size == 4);
+    std::vector<int> ms = split_stages(K, elem_size, "ADRT_B200_SPLIT", elem_size == 4);
+    // 256^2 fp32: (3, 5) ends with a streaming five-stage pass -- 4096 images: 12.5 ms vs 16.3 ms for (4, 4)
+    if (elem_size == 4 && K == 8 && !getenv("ADRT_B200_SPLIT")) ms = {3, 5};
     pl->npass = (int)ms.size();
     pl->ws_slot_elems[0] = pl->ws_slot_elems[1] = 0;
     int s = 0;
