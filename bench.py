@@ -39,6 +39,29 @@ METRIC = "adrt_fwd_plus_bdrt_throughput"
 UNIT = "Gpixel/s"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's "NCCL version ..."
+    banner comes from C code), so file descriptor 1 points at stderr while the benchmark runs and
+    emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -137,7 +160,7 @@ def reference_arm(args, np_dtype):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -362,7 +385,7 @@ def ours(args, np_dtype):
         "roofline": roofline, "cpu_baseline": cpu,
         "mode": "fused" if lib.adrt_b200_get_mode() == 0 else "per-stage",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -385,6 +408,7 @@ def main():
     import numpy as np
 
     np_dtype = np.float32 if args.dtype == "f32" else np.float64
+    quiet_stdout()
     if args.impl == "reference":
         reference_arm(args, np_dtype)
         return
