@@ -30,11 +30,25 @@ __device__ __forceinline__ void all_phases(int mode, T *buf, T (&regs)[tile::NRE
 #ifndef ADRT_B5P_CTAS
 #define ADRT_B5P_CTAS 5
 #endif
+// ADRT_F64_F5_CTAS / ADRT_F64_B5_CTAS: same for the fp64 five-stage passes (70 KB tiles: shared
+// memory allows 3).  Measured at 64 x 2048^2: 3 CTAs (80 registers) take the forward pass pair from
+// 15.57 to 14.46 ms, but the transposed pair from 20.63 to 21.49 ms (its kernels spill)
+#ifndef ADRT_F5I_CTAS
+#define ADRT_F5I_CTAS 5
+#endif
+#ifndef ADRT_F64_F5_CTAS
+#define ADRT_F64_F5_CTAS 3
+#endif
+#ifndef ADRT_F64_B5_CTAS
+#define ADRT_F64_B5_CTAS 2
+#endif
 template <typename T, int M, int LOADK, bool kForward>
 constexpr int min_ctas()
 {
+    if (sizeof(T) == 8 && M == 5) return kForward ? ADRT_F64_F5_CTAS : ADRT_F64_B5_CTAS;
     if (sizeof(T) == 8) return tile::Geo<M>::MIN_CTAS / 2;
     if (!kForward && LOADK == tile::LOAD_QCOLS && M == 5) return ADRT_B5P_CTAS;
+    if (kForward && LOADK == tile::LOAD_IMAGE && M == 5) return ADRT_F5I_CTAS;
     return tile::Geo<M>::MIN_CTAS;
 }
 
