@@ -47,8 +47,14 @@ def iadrt_fmg(a, /, *, max_iters=None):
         dev = a
 
     def residual(x):
-        # same quantity as the reference's float(np.linalg.norm(adrt(x) - a))
+        # the reference's float(np.linalg.norm(adrt(x) - a)) (adrt/__init__.py:135).  The
+        # subtraction runs on the device (elementwise IEEE, same bits as NumPy's); for NumPy
+        # callers the norm itself is NumPy's, so that the stopping rule `res2 < res1` sees the
+        # very numbers the reference would and selects the same iterate.  CUDA-tensor callers
+        # (an extension) get a device reduction: same value up to summation order.
         r = cd.sub(cd.adrt(x), dev)
+        if as_numpy:
+            return float(np.linalg.norm(r.cpu().numpy()))
         return float(r.reshape(-1).norm())
 
     best = None

@@ -57,8 +57,13 @@ def get_device() -> int:
 # ---------------------------------------------------------------------------
 
 def _is_torch_tensor(a) -> bool:
-    t = type(a)
-    return t.__module__.split(".")[0] == "torch" and t.__name__ in ("Tensor", "Parameter")
+    # torch is imported lazily (the NumPy path does not need it): only look it up
+    # when the object's class hierarchy mentions torch at all (covers Tensor subclasses)
+    if not any(c.__module__.split(".")[0] == "torch" for c in type(a).__mro__):
+        return False
+    import torch
+
+    return isinstance(a, torch.Tensor)
 
 
 class _Arr:
@@ -156,7 +161,15 @@ def _result_shape(arr: _Arr, virtual_shape, drop: int = 0):
     return tuple(virtual_shape[len(virtual_shape) - nd:])
 
 
-def _empty_like(arr: _Arr, shape, out):
+def _tensor_span(t):
+    """[first, last) byte addresses a contiguous tensor occupies."""
+    start = t.data_ptr()
+    return start, start + t.numel() * t.element_size()
+
+
+def _empty_like(arr: _Arr, shape, out, alias_ok=False):
+    # No transform runs in place (CTAs read tiles of the input while others write the
+    # output), so an `out` that overlaps the input is rejected instead of racing.
     if arr.is_torch:
         import torch
 
@@ -165,12 +178,17 @@ def _empty_like(arr: _Arr, shape, out):
                     and tuple(out.shape) == tuple(shape) and out.dtype == arr.obj.dtype
                     and out.device == arr.obj.device):
                 raise ValueError("out must be a contiguous CUDA tensor of the result shape, dtype and device")
+            (a0, a1), (b0, b1) = _tensor_span(arr.obj), _tensor_span(out)
+            if not alias_ok and a0 < b1 and b0 < a1:
+                raise ValueError("out must not overlap the input array")
             return out
         return torch.empty(shape, dtype=arr.obj.dtype, device=arr.obj.device)
     if out is not None:
         if not (isinstance(out, np.ndarray) and out.flags.c_contiguous and out.flags.aligned
                 and out.flags.writeable and out.shape == tuple(shape) and out.dtype == arr.np_dtype):
             raise ValueError("out must be a writable C-contiguous ndarray of the result shape and dtype")
+        if not alias_ok and np.may_share_memory(out, arr.obj):
+            raise ValueError("out must not overlap the input array")
         return out
     return np.empty(shape, dtype=arr.np_dtype)
 
@@ -203,8 +221,8 @@ def _run(name, arr: _Arr, out_shape, dims, out=None, step=None, workspace=None, 
     """
     lib = _lib.load()
     code = _dtype_code(arr)
-    _lib.require_device()
     ret = _empty_like(arr, out_shape, out)
+    _lib.require_device()
     step_args = () if step is None else (step,)
     if not arr.is_torch:
         fn = getattr(lib, f"adrt_b200_host_{name}")
@@ -250,8 +268,16 @@ def adrt(a, /, *, out=None):
     return _run("adrt", arr, res, (b, c), out=out, workspace="adrt")
 
 
-def adrt_step(a, step, /, *, out=None):
-    """adrt_cdefs_py.cpp:343-412."""
+def _two_args(name, args):
+    # METH_FASTCALL with an exact-arity check (adrt_cdefs_py.cpp:200-211)
+    if len(args) != 2:
+        raise TypeError(f"{name} expected 2 arguments, got {len(args)}")
+    return args
+
+
+def adrt_step(*args, out=None):
+    """adrt_cdefs_py.cpp:343-412; ``adrt_step(a, step, /)``."""
+    a, step = _two_args("adrt_step", args)
     arr = _extract_array(a)
     shape = _array_shape(arr, 3, 4)
     if not _is_adrt_output_shape(shape):
@@ -280,8 +306,9 @@ def bdrt(a, /, *, out=None):
     return _run("bdrt", arr, arr.shape, (shape[0], shape[3]), out=out, workspace="bdrt")
 
 
-def bdrt_step(a, step, /, *, out=None):
-    """adrt_cdefs_py.cpp:550-619."""
+def bdrt_step(*args, out=None):
+    """adrt_cdefs_py.cpp:550-619; ``bdrt_step(a, step, /)``."""
+    a, step = _two_args("bdrt_step", args)
     arr = _extract_array(a)
     shape = _array_shape(arr, 3, 4)
     if not _is_adrt_output_shape(shape):
@@ -438,7 +465,7 @@ def _binary(name, a, b, out=None):
     a, b = a.contiguous(), b.contiguous()
     arr = _extract_array(a)
     code = _dtype_code(arr)
-    ret = _empty_like(arr, arr.shape, out)
+    ret = _empty_like(arr, arr.shape, out, alias_ok=True)  # elementwise: in place is fine
     lib = _lib.load()
     with torch.cuda.device(a.device):
         rc = getattr(lib, f"adrt_b200_{name}")(a.data_ptr(), b.data_ptr(), ret.data_ptr(), a.numel(), code,

@@ -30,6 +30,11 @@ def _normalize_array(a, /):
     if isinstance(a, np.ndarray):
         a = np.asarray(a, a.dtype.newbyteorder("="), "C")
         return a if a.flags.aligned else a.copy("C")
+    if (not _adrt_cdefs._is_torch_tensor(a) and hasattr(a, "__dlpack__") and hasattr(a, "__dlpack_device__")
+            and int(a.__dlpack_device__()[0]) == 2):  # kDLCUDA producers (CuPy, ...): zero-copy import
+        import torch
+
+        a = torch.from_dlpack(a)
     if _adrt_cdefs._is_torch_tensor(a) and a.is_cuda:
         return a.contiguous()
     raise TypeError(f"array must be numpy.ndarray, but got {_format_object_type(a)}")

@@ -176,8 +176,10 @@ def iadrt_fmg_iter(a, /, *, copy=True):
             return h.copy() if copy else h.view()
         return x.clone() if copy else x
 
-    inv = _fmg_step_device(a)
+    # the public iadrt_fmg_step is looked up at call time, as in the reference (core.py:375-381):
+    # its tests count the calls by patching adrt.core.iadrt_fmg_step (tests/test_iadrt_fmg.py:42-55)
+    inv = iadrt_fmg_step(a)
     yield emit(inv)
     while True:
-        inv = cd.add(inv, _fmg_step_device(cd.sub(a, cd.adrt(inv))))
+        inv = cd.add(inv, iadrt_fmg_step(cd.sub(a, cd.adrt(inv))))
         yield emit(inv)

@@ -42,6 +42,8 @@ int check_vec_aligned(const void *in, const void *out, const void *ws)
 int check_image(const void *in, const void *out, int64_t B, int64_t n, int dtype)
 {
     ADRT_REQUIRE(in && out, "null pointer argument");
+    // every transform here is out of place: CTAs read tiles of `in` while others write `out`
+    ADRT_REQUIRE(in != out, "input and output must not alias (no transform runs in place)");
     ADRT_REQUIRE(dtype_ok(dtype), "unsupported dtype %d", dtype);
     ADRT_REQUIRE(B > 0, "batch must be positive, got %lld", (long long)B);
     ADRT_REQUIRE(is_pow2(n) && n <= kMaxN, "n must be a power of two <= %lld, got %lld", (long long)kMaxN, (long long)n);
@@ -466,7 +468,6 @@ int adrt_b200_adrt_step(const void *in, void *out, int64_t B, int64_t n, int ste
     int rc = check_image(in, out, B, n, dtype);
     if (rc) return rc;
     ADRT_REQUIRE(step >= 0 && step < num_iters(n), "step %d is out of range for n=%lld", step, (long long)n);
-    ADRT_REQUIRE(in != out, "adrt_step cannot run in place");
     return DISPATCH(dtype,
                     launch_adrt_step<float>((const float *)in, (float *)out, B, n, step, as_stream(stream)),
                     launch_adrt_step<double>((const double *)in, (double *)out, B, n, step, as_stream(stream)));
@@ -477,7 +478,6 @@ int adrt_b200_bdrt_step(const void *in, void *out, int64_t B, int64_t n, int ste
     int rc = check_image(in, out, B, n, dtype);
     if (rc) return rc;
     ADRT_REQUIRE(step >= 0 && step < num_iters(n), "step %d is out of range for n=%lld", step, (long long)n);
-    ADRT_REQUIRE(in != out, "bdrt_step cannot run in place");
     return DISPATCH(dtype,
                     launch_bdrt_step<float>((const float *)in, (float *)out, B, n, step, false, as_stream(stream)),
                     launch_bdrt_step<double>((const double *)in, (double *)out, B, n, step, false, as_stream(stream)));
@@ -514,7 +514,7 @@ int adrt_b200_iadrt(const void *in, void *out, int64_t B, int64_t n, int dtype, 
 
 int adrt_b200_fmg_restriction(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream)
 {
-    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0, "bad argument");
+    ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0, "bad argument");
     ADRT_REQUIRE(n >= 2 && n % 2 == 0 && n <= kMaxN, "restriction needs even n >= 2, got %lld", (long long)n);
     return DISPATCH(dtype,
                     launch_fmg_restriction<float>((const float *)in, (float *)out, B, n, as_stream(stream)),
@@ -523,7 +523,7 @@ int adrt_b200_fmg_restriction(const void *in, void *out, int64_t B, int64_t n, i
 
 int adrt_b200_fmg_prolongation(const void *in, void *out, int64_t B, int64_t h, int64_t w, int dtype, void *stream)
 {
-    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0 && h > 0 && w > 0, "bad argument");
+    ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0 && h > 0 && w > 0, "bad argument");
     return DISPATCH(dtype,
                     launch_fmg_prolongation<float>((const float *)in, (float *)out, B, h, w, as_stream(stream)),
                     launch_fmg_prolongation<double>((const double *)in, (double *)out, B, h, w, as_stream(stream)));
@@ -531,7 +531,7 @@ int adrt_b200_fmg_prolongation(const void *in, void *out, int64_t B, int64_t h, 
 
 int adrt_b200_fmg_highpass(const void *in, void *out, int64_t B, int64_t h, int64_t w, int dtype, void *stream)
 {
-    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0, "bad argument");
+    ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0, "bad argument");
     ADRT_REQUIRE(h >= 2 && w >= 2, "array is too small to high-pass filter");
     return DISPATCH(dtype,
                     launch_fmg_highpass<float>((const float *)in, (float *)out, B, h, w, as_stream(stream)),
@@ -574,7 +574,7 @@ int adrt_b200_interp_to_cart(const void *in, void *out, int64_t B, int64_t n, in
 
 int adrt_b200_truncate(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream)
 {
-    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
+    ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
     return DISPATCH(dtype,
                     launch_truncate<float>((const float *)in, (float *)out, B, n, as_stream(stream)),
                     launch_truncate<double>((const double *)in, (double *)out, B, n, as_stream(stream)));
@@ -582,7 +582,7 @@ int adrt_b200_truncate(const void *in, void *out, int64_t B, int64_t n, int dtyp
 
 int adrt_b200_truncate_mean(const void *in, void *out, int64_t B, int64_t n, double divisor, int dtype, void *stream)
 {
-    ADRT_REQUIRE(in && out && dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
+    ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
     return DISPATCH(dtype,
                     launch_truncate_mean<float>((const float *)in, (float *)out, B, n, (float)divisor, as_stream(stream)),
                     launch_truncate_mean<double>((const double *)in, (double *)out, B, n, divisor, as_stream(stream)));

@@ -47,14 +47,22 @@ def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
     # null pointers / bad shapes are rejected before any CUDA call
     assert lib.adrt_b200_adrt(None, None, 1, 8, 0, None, 0, None) == 1
-    buf = ctypes.create_string_buffer(64)
+    buf = ctypes.create_string_buffer(128)
     p = ctypes.addressof(buf)
-    assert lib.adrt_b200_adrt(p, p, 1, 12, 0, None, 0, None) == 1
+    o = p + 64
+    assert lib.adrt_b200_adrt(p, o, 1, 12, 0, None, 0, None) == 1
     assert "power of two" in _lib.last_error()
-    assert lib.adrt_b200_adrt(p, p, 0, 8, 0, None, 0, None) == 1
-    assert lib.adrt_b200_adrt(p, p, 1, 8, 7, None, 0, None) == 1
-    assert lib.adrt_b200_adrt_step(p, p, 1, 8, 3, 0, None) == 1
-    assert lib.adrt_b200_fmg_highpass(p, p, 1, 1, 8, 0, None) == 1
+    assert lib.adrt_b200_adrt(p, o, 0, 8, 0, None, 0, None) == 1
+    assert lib.adrt_b200_adrt(p, o, 1, 8, 7, None, 0, None) == 1
+    assert lib.adrt_b200_adrt_step(p, o, 1, 8, 3, 0, None) == 1
+    assert lib.adrt_b200_fmg_highpass(p, o, 1, 1, 8, 0, None) == 1
+    # no transform runs in place: in == out is an argument error for every one of them
+    for fn in (lib.adrt_b200_adrt, lib.adrt_b200_bdrt, lib.adrt_b200_iadrt, lib.adrt_b200_bdrt_planes):
+        assert fn(p, p, 1, 8, 0, None, 0, None) == 1
+        assert "alias" in _lib.last_error()
+    assert lib.adrt_b200_bdrt_rows(p, p, 1, 8, 8, 0, None, 0, None) == 1
+    assert lib.adrt_b200_adrt_step(p, p, 1, 8, 0, 0, None) == 1
+    assert lib.adrt_b200_bdrt_step(p, p, 1, 8, 0, 0, None) == 1
 
 
 def test_no_gpu_fails_loudly():

@@ -225,3 +225,59 @@ def test_iadrt_fmg_argument_errors():
 def test_threading_enabled_is_bool():
     assert isinstance(adrt.core.threading_enabled(), bool)
     assert isinstance(cd.OPENMP_ENABLED, bool)
+
+
+# ---- round 2: out= aliasing, exact arity, the `adrt` import name -----------------
+def test_out_must_not_overlap_input():
+    # no transform runs in place: rejected before any device work
+    y = np.zeros((4, 15, 8), dtype=np.float32)
+    for fn in (cd.bdrt, cd.iadrt):
+        with pytest.raises(ValueError, match="out must not overlap the input array"):
+            fn(y, out=y)
+    with pytest.raises(ValueError, match="out must not overlap"):
+        cd.bdrt_step(y, 0, out=y)
+    big = np.zeros(2 * y.size, dtype=np.float32)
+    with pytest.raises(ValueError, match="out must not overlap"):
+        cd.bdrt(big[: y.size].reshape(y.shape), out=big[4: 4 + y.size].reshape(y.shape))
+
+
+def test_step_functions_check_arity_like_fastcall():
+    # adrt_cdefs_py.cpp:200-211; reference tests/test_adrt_step.py:41-49
+    arr = np.zeros((4, 31, 16), dtype=np.float32)
+    for name in ("adrt_step", "bdrt_step"):
+        fn = getattr(cd, name)
+        with pytest.raises(TypeError, match=rf"{name} expected 2 arguments, got 1"):
+            fn(arr)
+        with pytest.raises(TypeError, match=rf"{name} expected 2 arguments, got 3"):
+            fn(arr, 0, 0)
+        with pytest.raises(TypeError, match="int"):
+            fn(arr, [])
+
+
+def test_adrt_import_name_is_the_engine():
+    import adrt as ref_name
+    import adrt.core
+    import adrt.utils
+    import adrt_b200
+
+    assert ref_name.core is adrt_b200.core and ref_name.utils is adrt_b200.utils
+    assert ref_name._adrt_cdefs is adrt_b200._adrt_cdefs and ref_name._wrappers is adrt_b200._wrappers
+    assert ref_name.adrt is adrt_b200.adrt and ref_name.iadrt_fmg is adrt_b200.iadrt_fmg
+    assert adrt.core.iadrt_fmg_iter is adrt_b200.core.iadrt_fmg_iter
+    assert isinstance(ref_name._adrt_cdefs.OPENMP_ENABLED, bool)
+    assert ref_name.core.threading_enabled() == ref_name._adrt_cdefs.OPENMP_ENABLED
+    assert sorted(ref_name.__all__) == sorted(["adrt", "iadrt", "bdrt", "iadrt_fmg", "utils", "core"])
+
+
+def test_tensor_subclass_and_dlpack_are_recognised():
+    import torch
+
+    class MyTensor(torch.Tensor):
+        pass
+
+    t = torch.zeros(2, 2).as_subclass(MyTensor)
+    assert cd._is_torch_tensor(t) and cd._is_torch_tensor(torch.nn.Parameter(torch.zeros(1)))
+    assert not cd._is_torch_tensor(np.zeros(2)) and not cd._is_torch_tensor(None)
+    # CPU tensors are not arrays this engine accepts (same TypeError as any non-ndarray)
+    with pytest.raises(TypeError, match="must be numpy.ndarray"):
+        adrt.adrt(torch.zeros(4, 4))
