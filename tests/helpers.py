@@ -44,3 +44,40 @@ def first_diff(a, b):
         return "identical"
     i = tuple(bad[0])
     return f"{len(bad)} of {a.size} differ; first at {i}: got {a[i]!r} want {b[i]!r}"
+
+
+# ---- the reference's multigrid pass driven by its own compiled core ---------------
+def ref_truncate(a):
+    """utils.py:231-242 (test-side NumPy twin of the reference's ``truncate``)."""
+    n = a.shape[-1]
+    return np.stack(
+        [
+            np.flip(a[..., 0, :n, :n], axis=-2).swapaxes(-1, -2),
+            np.flip(a[..., 1, :n, :n], axis=-2),
+            a[..., 2, :n, :n],
+            np.flip(a[..., 3, :n, :n], axis=(-1, -2)).swapaxes(-1, -2),
+        ],
+        axis=-3,
+    )
+
+
+def ref_fmg_step(ref, a):
+    """core.py:318-331 with every native operator taken from `ref`, the reference's own
+    ``_adrt_cdefs`` module (oracle/_ref, multithreaded), and the glue in NumPy exactly as
+    the reference spells it (``np.mean(truncate(.) / (n - 1), axis=-3)``).  Fast enough
+    for BASELINE config 4's 4096^2 on the GPU box's host cores."""
+    stack = []
+    m = a.shape[-1]
+    while m > 1:
+        stack.append(a)
+        a = ref.press_fmg_restriction(np.ascontiguousarray(a))
+        m //= 2
+    ret = np.ascontiguousarray(a[..., 0, :, :])
+    n = 1
+    while stack:
+        n *= 2
+        ret = ref.press_fmg_prolongation(ret)
+        resid = ref.adrt(ret) - stack.pop()
+        ret -= ref.press_fmg_highpass(
+            np.ascontiguousarray(np.mean(ref_truncate(ref.bdrt(resid)) / (n - 1), axis=-3)))
+    return ret

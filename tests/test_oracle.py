@@ -102,3 +102,21 @@ def test_oracle_vs_live_reference(dn):
             assert bytes_equal(O.press_fmg_restriction(s), ref.press_fmg_restriction(s))
             assert bytes_equal(O.press_fmg_highpass(x), ref.press_fmg_highpass(x))
         assert bytes_equal(O.press_fmg_prolongation(x), ref.press_fmg_prolongation(x))
+
+
+def test_helpers_ref_fmg_step_is_the_reference_pass():
+    """tests/helpers.ref_fmg_step (the reference's multigrid pass driven by its compiled core,
+    used by the config-4 GPU test) is bytes-equal to the reference package's own
+    core.iadrt_fmg_step wherever the package can be imported (this container)."""
+    from helpers import ref_fmg_step
+
+    if not ref_loader.have_ref_package():
+        pytest.skip("reference package not mounted")
+    pkg = ref_loader.load_ref_package()
+    ref = ref_loader.load_ref_cdefs()
+    for dt in (np.float32, np.float64):
+        for shape in ((16, 16), (2, 32, 32)):
+            a = pkg.adrt(make_image(5, shape, dt))
+            want = pkg.core.iadrt_fmg_step(a)
+            got = ref_fmg_step(ref, a)
+            assert got.tobytes() == want.tobytes()

@@ -99,8 +99,6 @@ def test_survey_anchors():
 def test_large_vs_oracle(mode, dn, n, B):
     """Sizes of BASELINE configs 1-5 on a batch the CPU oracle finishes in seconds
     (8192 = three fused passes)."""
-    if n >= 4096 and dn == "f64":
-        pytest.skip("covered by fp32; keeps the suite short")
     if n == 8192 and mode == 1:
         pytest.skip("per-stage path is covered up to 4096")
     dt = DTYPES[dn]

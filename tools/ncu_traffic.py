@@ -1,11 +1,13 @@
-"""profiles/r01_traffic.json from an ncu --set full capture of one adrt + bdrt pair
-(tools/prof_once.py B n dtype): python tools/ncu_traffic.py rep B n dtype > profiles/r01_traffic.json"""
+"""profiles/rNN_traffic.json from an ncu --set full capture of one adrt + bdrt pair
+(tools/prof_once.py B n dtype): python tools/ncu_traffic.py rep B n dtype [commit] > profiles/rNN_traffic.json
+bench.py reads the newest such file for roofline.traffic and reports the commit it was taken at."""
 import csv
 import json
 import subprocess
 import sys
 
 rep, B, n, dtype = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+commit = sys.argv[5] if len(sys.argv) > 5 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -33,7 +35,7 @@ for r in data:
 itemsize = 4 if dtype == "f32" else 8
 print(json.dumps({
     "capture": f"{rep} (ncu --set full --clock-control none, tools/prof_once.py {B} {n} {dtype})",
-    "batch_in_capture": B, "n": n, "dtype": dtype, "kernels": kernels,
+    "batch_in_capture": B, "B": B, "commit": commit, "n": n, "dtype": dtype, "kernels": kernels,
     "dram_bytes_per_image_fwd_plus_bdrt": total / B,
     "algorithmic_bytes_per_image": (25 * n * n - 12 * n) * itemsize,
 }, indent=1))
