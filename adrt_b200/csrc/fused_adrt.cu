@@ -5,6 +5,7 @@
 // traffic per transform drops from 2*K sinogram sweeps (per-stage kernels) to
 // one sweep per pass (2 passes up to n = 4096 in fp32).
 #include "pass_args.h"
+#include "sched.cuh"
 
 #include <type_traits>
 
@@ -110,6 +111,75 @@ int launch_pass(const T *src, T *dst, const PassArgs &a, int grid_x, int grid_y,
     return ADRT_B200_OK;
 }
 
+// Persistent variant (sched.cuh): the CTAs pull (plane, group, d-tile) work items from a global counter
+// in plane-major order, wait for the producing pass of their plane where there is one and announce
+// every finished tile where a later pass waits for it.
+template <typename T, int M, int LOADK, int STOREK, bool kForward>
+__global__ void __launch_bounds__(tile::Geo<M>::NT, min_ctas<T, M, LOADK, kForward>())
+pass_kernel_p(const T *__restrict__ src, T *__restrict__ dst, PassArgs a, SchedArgs sc)
+{
+    using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
+                                           tile::BwdProgram<T, M, LOADK, STOREK>>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned slot[2];
+    T *buf = reinterpret_cast<T *>(smem_raw);
+    T regs[tile::NREG];
+    const int tid = threadIdx.x;
+
+    tile::TileCtx c;
+    c.n = a.n;
+    c.D = a.D;
+    c.e = a.e;
+    c.next_g = a.next_g;
+    c.d_need = a.d_need;
+    c.in_pitch = a.in_pitch;
+    c.out_pitch = a.out_pitch;
+    c.q = 0;
+    SchedIter iter;
+    iter.begin(sc, slot, tid);
+    int plane, y, x, ready_plane = -1;
+    while (iter.current(sc, slot, tid, plane, y, x)) {
+        c.g = y;
+        c.k0 = c.g >> a.loge;
+        c.a_g = c.g & (a.e - 1);
+        c.d0 = (x + a.x_off) * Prog::TD;
+        const int mode = Prog::classify(c);
+        if (mode != tile::TILE_SKIP) {
+            const T *sp;
+            if (LOADK == tile::LOAD_IMAGE) {
+                const int gp = plane + a.plane0;
+                c.q = a.q_first + gp % a.q_count;
+                sp = src + (long long)(gp / a.q_count) * a.src_plane_stride;
+            } else {
+                sp = src + (long long)plane * a.src_plane_stride;
+            }
+            T *dp = dst + (long long)plane * a.dst_plane_stride;
+            if (mode == tile::TILE_ZERO) {
+                Prog::zero_tile(buf, dp, c, tid);
+            } else {
+                if (sc.dep && plane != ready_plane) {
+                    sched_wait_plane(sc, plane, tid);
+                    ready_plane = plane;
+                }
+                all_phases<Prog, T, 0>(mode, buf, regs, sp, dp, c, tid);
+            }
+        }
+        if (sc.done) sched_signal_plane(sc, plane, tid);
+        iter.advance();
+    }
+}
+
+template <typename T, int M, int LOADK, int STOREK, bool kForward>
+int launch_pass_p(const T *src, T *dst, const PassArgs &a, const SchedArgs &sc, cudaStream_t s)
+{
+    auto kern = pass_kernel_p<T, M, LOADK, STOREK, kForward>;
+    const size_t smem = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T) + (size_t)sc.smem_pad;
+    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)sc.ctas, tile::Geo<M>::NT, smem, s>>>(src, dst, a, sc);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
 template <typename T, int M, bool kForward>
 int dispatch_kinds(int load, int store, const T *src, T *dst, const PassArgs &a, int gx, int gy, cudaStream_t s)
 {
@@ -126,6 +196,41 @@ int dispatch_kinds(int load, int store, const T *src, T *dst, const PassArgs &a,
         if (load == LOAD_WROWS && store == STORE_QCOLS) return launch_pass<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(src, dst, a, gx, gy, s);
     }
     set_error("internal: bad pass kinds %d/%d", load, store);
+    return ADRT_B200_EINVAL;
+}
+
+template <typename T, int M, bool kForward>
+int dispatch_kinds_p(int load, int store, const T *src, T *dst, const PassArgs &a, const SchedArgs &sc, cudaStream_t s)
+{
+    using namespace tile;
+    if constexpr (kForward) {
+        if (load == LOAD_IMAGE && store == STORE_WROWS) return launch_pass_p<T, M, LOAD_IMAGE, STORE_WROWS, kForward>(src, dst, a, sc, s);
+        if (load == LOAD_WROWS && store == STORE_QCOLS) return launch_pass_p<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(src, dst, a, sc, s);
+    } else {
+        if (load == LOAD_QCOLS && store == STORE_WROWS) return launch_pass_p<T, M, LOAD_QCOLS, STORE_WROWS, kForward>(src, dst, a, sc, s);
+        if (load == LOAD_WROWS && store == STORE_QCOLS) return launch_pass_p<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(src, dst, a, sc, s);
+    }
+    set_error("internal: bad co-scheduled pass kinds %d/%d", load, store);
+    return ADRT_B200_EINVAL;
+}
+
+// co-scheduled (persistent) launch of one pass of a two-pass plan; `side`: helper stream for the boundary
+// tiles of a streaming transposed pass
+template <typename T, bool kForward>
+int dispatch_pass_p(const plan::Pass &p, const T *src, T *dst, const PassArgs &a, const SchedArgs &sc, cudaStream_t s,
+                    cudaStream_t side)
+{
+    if (p.stream) {
+        if constexpr (std::is_same<T, float>::value) return launch_stream_pass_sched(p, kForward, src, dst, a, sc, s, side);
+        set_error("internal: streaming passes are fp32 only");
+        return ADRT_B200_EINVAL;
+    }
+    switch (p.M) {
+    case 4: return dispatch_kinds_p<T, 4, kForward>(p.load, p.store, src, dst, a, sc, s);
+    case 5: return dispatch_kinds_p<T, 5, kForward>(p.load, p.store, src, dst, a, sc, s);
+    case 6: return dispatch_kinds_p<T, 6, kForward>(p.load, p.store, src, dst, a, sc, s);
+    }
+    set_error("internal: no co-scheduled kernel for %d stages per pass", p.M);
     return ADRT_B200_EINVAL;
 }
 

@@ -18,10 +18,26 @@ struct PassArgs {
     int side_idx;           // host only: which helper stream (aux_stream) takes the boundary tiles of this launch
 };
 
+// Persistent, plane-ordered scheduling of one pass (sched.cuh); next == nullptr: ordinary grid launch.
+struct SchedArgs {
+    unsigned *next;         // work counter of this launch, zeroed by the host
+    const unsigned *dep;    // per-plane counters bumped by the producing pass (nullptr: no dependency)
+    unsigned *done;         // per-plane counters this pass bumps after every tile (nullptr: nobody waits)
+    unsigned dep_need;      // dep[plane] at which the plane's input is complete
+    int tiles_x, tiles_y;   // tile grid of one plane (d-tile index = x + PassArgs::x_off)
+    unsigned total;         // planes * tiles_x * tiles_y
+    int ctas;               // persistent grid size
+    int smem_pad;           // extra dynamic shared memory (bytes) that caps the CTAs per SM
+};
+
 // fp32 streaming passes (plan::Pass::stream); defined in stream_adrt.cu
 // helper streams of the current device (0: boundary tiles, 1: odd waves, 2: boundary tiles of odd waves); nullptr on failure
 cudaStream_t aux_stream(int idx);
 
 int launch_stream_pass(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a, cudaStream_t s);
+// persistent variant: `sc` describes the whole pass (all its d-tiles); the transposed direction splits it
+// into an interior and a boundary launch, the latter on `side` with its own work counter sc.next + 1
+int launch_stream_pass_sched(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a,
+                             const SchedArgs &sc, cudaStream_t s, cudaStream_t side);
 
 }  // namespace adrt_b200
