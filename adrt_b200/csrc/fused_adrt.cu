@@ -114,8 +114,19 @@ int launch_pass(const T *src, T *dst, const PassArgs &a, int grid_x, int grid_y,
 // Persistent variant (sched.cuh): the CTAs pull (plane, group, d-tile) work items from a global counter
 // in plane-major order, wait for the producing pass of their plane where there is one and announce
 // every finished tile where a later pass waits for it.
+// Launch bound of the persistent kernels: they share every SM with another pass's CTAs (2-3 of them
+// resident), so the register cap that buys a 4th or 5th resident CTA only costs spills here.
+#ifndef ADRT_CO_CTAS
+#define ADRT_CO_CTAS 3
+#endif
+template <typename T, int M, int LOADK, bool kForward>
+constexpr int min_ctas_p()
+{
+    return min_ctas<T, M, LOADK, kForward>() < ADRT_CO_CTAS ? min_ctas<T, M, LOADK, kForward>() : ADRT_CO_CTAS;
+}
+
 template <typename T, int M, int LOADK, int STOREK, bool kForward>
-__global__ void __launch_bounds__(tile::Geo<M>::NT, min_ctas<T, M, LOADK, kForward>())
+__global__ void __launch_bounds__(tile::Geo<M>::NT, min_ctas_p<T, M, LOADK, kForward>())
 pass_kernel_p(const T *__restrict__ src, T *__restrict__ dst, PassArgs a, SchedArgs sc)
 {
     using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
@@ -173,8 +184,12 @@ template <typename T, int M, int LOADK, int STOREK, bool kForward>
 int launch_pass_p(const T *src, T *dst, const PassArgs &a, const SchedArgs &sc, cudaStream_t s)
 {
     auto kern = pass_kernel_p<T, M, LOADK, STOREK, kForward>;
-    const size_t smem = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T) + (size_t)sc.smem_pad;
-    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    static std::atomic<size_t> cached[8] = {};
+    const size_t base = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T);
+    const int ci = sc.cap_per_sm > 0 && sc.cap_per_sm < 8 ? sc.cap_per_sm : 0;
+    size_t smem = cached[ci].load();
+    if (!smem) cached[ci].store(smem = capped_smem(kern, tile::Geo<M>::NT, base, ci));
     kern<<<(unsigned)sc.ctas, tile::Geo<M>::NT, smem, s>>>(src, dst, a, sc);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
@@ -302,6 +317,117 @@ void set_persist_window(cudaStream_t s, void *base, size_t bytes)
     (void)cudaGetLastError();
 }
 
+// Co-scheduled two-pass plans (sched.cuh).  ADRT_B200_COSCHED=0/1 overrides the default; ADRT_B200_CO_K1 /
+// ADRT_B200_CO_K2 = persistent CTAs per SM of the producing / consuming pass.
+struct CoCfg {
+    bool on;
+    int k1, k2;
+};
+
+template <typename T>
+CoCfg cosched_config(const plan::Plan &pl, int64_t total_planes)
+{
+    CoCfg c = {false, 2, 2};
+    if (pl.npass != 2) return c;
+    // default: the fp32 plans whose second pass is a streaming kernel (bulk-copy loads)
+    c.on = sizeof(T) == 4 && pl.pass[1].stream && pl.pass[1].M == 6;
+    if (const char *e = getenv("ADRT_B200_COSCHED")) c.on = atoi(e) != 0;
+    if (const char *e = getenv("ADRT_B200_CO_K1")) c.k1 = atoi(e);
+    if (const char *e = getenv("ADRT_B200_CO_K2")) c.k2 = atoi(e);
+    if (c.k1 < 1) c.k1 = 1;
+    if (c.k2 < 1) c.k2 = 1;
+    // work items are counted in 32 bits
+    for (int i = 0; i < 2; ++i)
+        if ((double)total_planes * pl.pass[i].grid_x * pl.pass[i].grid_y >= 4.0e9) c.on = false;
+    // the masked / per-M kernels instantiated for co-scheduling
+    for (int i = 0; i < 2; ++i)
+        if (!pl.pass[i].stream && (pl.pass[i].M < 4 || pl.pass[i].M > 6)) c.on = false;
+    return c;
+}
+
+// counters appended to the workspace: per-plane completion counts + the work counters of the launches
+inline size_t cosched_counter_words(int64_t planes) { return ((size_t)planes + 8 + 63) & ~size_t(63); }
+
+template <typename T, bool kForward>
+int run_plan_cosched(const plan::Plan &pl, const CoCfg &cc, const T *in, T *out, int64_t total, int q_first, int q_count,
+                     T *ws_slot0, unsigned *counters, cudaStream_t s)
+{
+    const int n = pl.n, D = pl.D;
+    const long long img_elems = (long long)n * n, sino_plane = (long long)D * n;
+    int dev = 0, sms = 148;
+    ADRT_CUDA_CHECK(cudaGetDevice(&dev));
+    ADRT_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t s2 = aux_stream(1), s3 = aux_stream(3);
+    if (!s2 || !s3) {
+        set_error("co-scheduled passes: helper streams unavailable");
+        return ADRT_B200_ECUDA;
+    }
+    unsigned *done = counters, *next = counters + total;   // next[0]: pass 1, next[1..2]: pass 2 (interior, boundary)
+    ADRT_CUDA_CHECK(cudaMemsetAsync(counters, 0, cosched_counter_words(total) * sizeof(unsigned), s));
+    cudaEvent_t fork = nullptr, join2 = nullptr, join3 = nullptr;
+    ADRT_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    ADRT_CUDA_CHECK(cudaEventCreateWithFlags(&join2, cudaEventDisableTiming));
+    ADRT_CUDA_CHECK(cudaEventCreateWithFlags(&join3, cudaEventDisableTiming));
+    int rc = ADRT_B200_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == ADRT_B200_OK) { set_error("co-scheduled passes: %s", cudaGetErrorString(e)); rc = ADRT_B200_ECUDA; } };
+    fail(cudaEventRecord(fork, s));
+    fail(cudaStreamWaitEvent(s2, fork, 0));
+    fail(cudaStreamWaitEvent(s3, fork, 0));
+    for (int i = 0; i < 2 && rc == ADRT_B200_OK; ++i) {
+        const plan::Pass &p = pl.pass[i];
+        PassArgs a;
+        a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g; a.d_need = p.d_need;
+        a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
+        a.planes = (int)total;
+        a.x_off = 0;
+        a.q_first = q_first; a.q_count = q_count;
+        a.plane0 = 0;
+        a.side_idx = 0;
+        const T *src;
+        T *dst;
+        if (i == 0) {
+            src = in;
+            a.src_plane_stride = kForward ? img_elems : sino_plane;
+            dst = ws_slot0;
+            a.dst_plane_stride = (long long)n * p.out_pitch;
+        } else {
+            src = ws_slot0;
+            a.src_plane_stride = (long long)n * p.in_pitch;
+            dst = out;
+            a.dst_plane_stride = sino_plane;
+        }
+        SchedArgs sc;
+        sc.tiles_x = p.grid_x;
+        sc.tiles_y = p.grid_y;
+        sc.total = (unsigned)total * (unsigned)p.grid_x * (unsigned)p.grid_y;
+        if (i == 0) {
+            sc.next = next;
+            sc.dep = nullptr;
+            sc.done = done;
+            sc.dep_need = 0;
+            sc.ctas = sms * cc.k1;
+            sc.cap_per_sm = 0;
+            rc = dispatch_pass_p<T, kForward>(p, src, dst, a, sc, s, s);
+        } else {
+            sc.next = next + 1;
+            sc.dep = done;
+            sc.done = nullptr;
+            sc.dep_need = (unsigned)pl.pass[0].grid_x * (unsigned)pl.pass[0].grid_y;
+            sc.ctas = sms * cc.k2;
+            sc.cap_per_sm = cc.k2;
+            rc = dispatch_pass_p<T, kForward>(p, src, dst, a, sc, s2, s3);
+        }
+    }
+    fail(cudaEventRecord(join2, s2));
+    fail(cudaEventRecord(join3, s3));
+    fail(cudaStreamWaitEvent(s, join2, 0));
+    fail(cudaStreamWaitEvent(s, join3, 0));
+    cudaEventDestroy(fork);
+    cudaEventDestroy(join2);
+    cudaEventDestroy(join3);
+    return rc;
+}
+
 template <typename T, bool kForward>
 int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, int q_count, T *ws, size_t ws_elems,
              cudaStream_t s)
@@ -311,6 +437,19 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
     const int n = pl.n, D = pl.D;
     const int64_t total = B * q_count;
     const size_t plane_ws = pl.ws_slot_elems[0] + pl.ws_slot_elems[1];
+    const CoCfg cc = cosched_config<T>(pl, total);
+    if (cc.on) {
+        // whole batch, one workspace slot (pass 1 -> pass 2), counters behind it
+        const size_t ws_need = pl.ws_slot_elems[0] * (size_t)total;
+        const size_t ctr_elems = (cosched_counter_words(total) * sizeof(unsigned) + sizeof(T) - 1) / sizeof(T);
+        const size_t ctr_off = (ws_need + 63) & ~size_t(63);
+        if (ctr_off + ctr_elems > ws_elems) {
+            set_error("fused workspace too small: need %zu elements, got %zu", ctr_off + ctr_elems, ws_elems);
+            return ADRT_B200_EWORKSPACE;
+        }
+        return run_plan_cosched<T, kForward>(pl, cc, in, out, total, q_first, q_count, ws,
+                                             reinterpret_cast<unsigned *>(ws + ctr_off), s);
+    }
     const WaveCfg wc = wave_config(total, q_count, plane_ws * sizeof(T));
     const size_t slot0 = pl.ws_slot_elems[0] * (size_t)wc.planes;
     const size_t lane_elems = plane_ws * (size_t)wc.planes;
@@ -388,7 +527,16 @@ size_t plan_workspace_elems(const plan::Plan &pl, int64_t B, int q_count)
 {
     const size_t plane_ws = pl.ws_slot_elems[0] + pl.ws_slot_elems[1];
     const WaveCfg wc = wave_config(B * q_count, q_count, plane_ws * sizeof(T));
-    return plane_ws * (size_t)wc.planes * wc.lanes;
+    size_t need = plane_ws * (size_t)wc.planes * wc.lanes;
+    // room for the co-scheduled variant too (decided per call; one slot + counters), so that a
+    // workspace sized by the query serves either
+    if (pl.npass == 2) {
+        const size_t total = (size_t)(B * q_count);
+        const size_t co = ((pl.ws_slot_elems[0] * total + 63) & ~size_t(63)) +
+                          (cosched_counter_words((int64_t)total) * sizeof(unsigned) + sizeof(T) - 1) / sizeof(T);
+        if (co > need) need = co;
+    }
+    return need;
 }
 
 }  // namespace

@@ -27,8 +27,26 @@ struct SchedArgs {
     int tiles_x, tiles_y;   // tile grid of one plane (d-tile index = x + PassArgs::x_off)
     unsigned total;         // planes * tiles_x * tiles_y
     int ctas;               // persistent grid size
-    int smem_pad;           // extra dynamic shared memory (bytes) that caps the CTAs per SM
+    int cap_per_sm;         // > 0: pad the dynamic shared memory until at most this many CTAs fit on an SM
 };
+
+// dynamic shared memory (>= base) with which at most `cap` CTAs of `kern` are resident per SM
+// (cap <= 0: base).  Cached per kernel instantiation by the callers.
+template <typename Kern>
+inline size_t capped_smem(Kern kern, int threads, size_t base, int cap)
+{
+    if (cap <= 0) return base;
+    size_t smem = base;
+    for (;;) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return base;
+        }
+        if (occ <= cap || smem + 1024 > 227 * 1024) return smem;
+        smem += 1024;
+    }
+}
 
 // fp32 streaming passes (plan::Pass::stream); defined in stream_adrt.cu
 // helper streams of the current device (0: boundary tiles, 1: odd waves, 2: boundary tiles of odd waves); nullptr on failure

@@ -37,8 +37,9 @@ def timeit(fn, reps=5):
     return ts[len(ts) // 2]
 
 
+ref_y = ref_z = None
 for cfg in configs:
-    for k in ("ADRT_B200_SPLIT", "ADRT_B200_SPLIT_BDRT", "ADRT_B200_WAVE", "ADRT_B200_STREAM_SET", "ADRT_B200_WAVE_PLANES", "ADRT_B200_WAVE_LANES", "ADRT_B200_L2_PERSIST_MB"):
+    for k in [k for k in os.environ if k.startswith("ADRT_B200_") and k not in ("ADRT_B200_LIB", "ADRT_B200_DEVICE")]:
         os.environ.pop(k, None)
     for k, v in cfg.items():
         if k == "mode":
@@ -48,7 +49,14 @@ for cfg in configs:
     ta = timeit(lambda: adrt.adrt(x, out=y))
     tb = timeit(lambda: adrt.bdrt(y, out=z))
     gpx = B * n * n / ((ta + tb) * 1e-3) / 1e9
-    print(json.dumps({"B": B, "n": n, "dtype": str(dt), "cfg": cfg, "adrt_ms": round(ta, 3), "bdrt_ms": round(tb, 3),
+    # every configuration must produce the bytes of the first one
+    if ref_y is None:
+        ref_y, ref_z = y.clone(), z.clone()
+        same = True
+    else:
+        same = bool(torch.equal(y.view(torch.uint8), ref_y.view(torch.uint8)) and
+                    torch.equal(z.view(torch.uint8), ref_z.view(torch.uint8)))
+    print(json.dumps({"B": B, "n": n, "dtype": str(dt), "cfg": cfg, "same_bytes_as_first": same, "adrt_ms": round(ta, 3), "bdrt_ms": round(tb, 3),
                       "Gpx/s": round(gpx, 2), "adrt_frac": round(fb / (ta * 1e-3) / 1e9 / peak, 3),
                       "bdrt_frac": round(bb / (tb * 1e-3) / 1e9 / peak, 3),
                       "frac": round((fb + bb) / ((ta + tb) * 1e-3) / 1e9 / peak, 3)}), flush=True)
