@@ -558,6 +558,73 @@ def bdrt_planes(a, /, *, out=None, rows=None):
     return ret
 
 
+def normal_operator(a, divisor=1.0, /, *, out=None):
+    """``mean_q(truncate(bdrt(adrt(a))) / divisor)`` for CUDA tensors ``(B?, n, n)`` in one native
+    call (``adrt_b200_normal_operator``): the operator ``A^T A`` of the CG recipe
+    (docs/examples.cginverse.md:45-52).  The sinogram goes from adrt to bdrt as workspace rows and
+    never takes the public layout; bit-identical to ``truncate_mean(bdrt(adrt(a)), divisor)``."""
+    arr = _extract_array(a)
+    if not arr.is_torch:
+        raise TypeError("normal_operator is a device-only helper (CUDA tensors)")
+    shape = _array_shape(arr, 2, 3)
+    b, r, c = shape
+    if not (r == c and _is_pow2(c)):
+        raise ValueError("array must be square with a power of two shape")
+    code = _dtype_code(arr)
+    lib = _lib.load()
+    _lib.require_device()
+    ret = _empty_like(arr, arr.shape, out)
+    import torch
+
+    t = arr.obj
+    with torch.cuda.device(t.device):
+        nbytes = int(lib.adrt_b200_normal_operator_workspace_bytes(b, c, code))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=t.device)
+        t = _vec_in(t)
+        dst, copy_back = _vec_out(ret)
+        rc = lib.adrt_b200_normal_operator(t.data_ptr(), dst.data_ptr(), b, c, float(divisor), code, ws.data_ptr(), nbytes,
+                                           torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "normal_operator")
+        if copy_back:
+            ret.copy_(dst)
+    return ret
+
+
+def adrt_bdrt_rows(a, q_first, q_count, /, *, out=None):
+    """Offsets ``d < n`` of ``bdrt(adrt(a))`` for quadrants ``q_first .. q_first+q_count-1``:
+    ``(B?, n, n)`` -> ``(B?, q_count, 2n-1, n)`` (rows ``d >= n`` unspecified).  The building block
+    of the quadrant-sharded normal operator; CUDA tensors only, ``n >= 2``."""
+    arr = _extract_array(a)
+    if not arr.is_torch:
+        raise TypeError("adrt_bdrt_rows is a device-only helper (CUDA tensors)")
+    shape = _array_shape(arr, 2, 3)
+    b, r, c = shape
+    if not (r == c and _is_pow2(c) and c >= 2):
+        raise ValueError("array must be square with a power of two shape")
+    q_first, q_count = operator.index(q_first), operator.index(q_count)
+    if not (0 <= q_first and 1 <= q_count and q_first + q_count <= 4):
+        raise ValueError(f"bad quadrant range {q_first}+{q_count}")
+    res = _result_shape(arr, (b, q_count, 2 * c - 1, c), drop=-1)
+    code = _dtype_code(arr)
+    lib = _lib.load()
+    _lib.require_device()
+    ret = _empty_like(arr, res, out)
+    import torch
+
+    t = arr.obj
+    with torch.cuda.device(t.device):
+        nbytes = int(lib.adrt_b200_adrt_bdrt_rows_workspace_bytes(b, c, code, q_count))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=t.device)
+        t = _vec_in(t)
+        dst, copy_back = _vec_out(ret)
+        rc = lib.adrt_b200_adrt_bdrt_rows(t.data_ptr(), dst.data_ptr(), b, c, code, q_first, q_count, ws.data_ptr(), nbytes,
+                                          torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "adrt_bdrt_rows")
+        if copy_back:
+            ret.copy_(dst)
+    return ret
+
+
 def bdrt_truncate_mean(a, divisor, /, *, out=None):
     """``truncate_mean(bdrt(a), divisor)`` for CUDA tensors ``(B?, 4, 2n-1, n)``: the
     back-projection computes only the offsets ``d < n`` that ``truncate`` keeps

@@ -41,6 +41,10 @@ SIGNATURES = {
     "adrt_b200_bdrt_planes_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int]),
     "adrt_b200_bdrt_planes": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp, _c_sz, _c_vp]),
     "adrt_b200_bdrt_rows": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_vp, _c_sz, _c_vp]),
+    "adrt_b200_normal_operator_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int]),
+    "adrt_b200_normal_operator": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_double, _c_int, _c_vp, _c_sz, _c_vp]),
+    "adrt_b200_adrt_bdrt_rows_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int]),
+    "adrt_b200_adrt_bdrt_rows": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_vp, _c_sz, _c_vp]),
     "adrt_b200_adrt_step": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
     "adrt_b200_bdrt_step": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
     "adrt_b200_adrt_init": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),

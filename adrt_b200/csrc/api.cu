@@ -287,6 +287,74 @@ int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, int64_t row
     return fused_bdrt<T>(in, out, planes, n, 1, rows, ws, ws_bytes / sizeof(T), s, &handled);
 }
 
+// ---- fused normal operator ---------------------------------------
+// bdrt(adrt(x)) for quadrants q_first .. q_first + q_count - 1, offsets d < n only (all that truncate
+// keeps).  The sinogram never exists in the public (d, column) layout: the last forward pass stores
+// R-layout rows and the first transposed pass loads them (fused_plan.h rows_out / rows_in), so the
+// transposing public-layout store of adrt and load of bdrt are gone.  Same adds in the same order as
+// the two separate transforms => bit-identical.
+template <typename T>
+size_t normal_rows_elems(int64_t B, int64_t n, int q_count) { return (size_t)(B * q_count) * (size_t)n * (size_t)((2 * n - 1 + 3) & ~int64_t(3)); }
+
+template <typename T>
+size_t normal_transform_ws_elems(int64_t B, int64_t n, int q_count)
+{
+    const size_t a = fused_adrt_workspace_elems<T>(B, n, q_count), b = fused_bdrt_workspace_elems<T>(B * q_count, n, 1);
+    if (a == (size_t)-1 || b == (size_t)-1) return (size_t)-1;
+    return a > b ? a : b;
+}
+
+template <typename T>
+int adrt_bdrt_rows_impl(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems,
+                        cudaStream_t s)
+{
+    const size_t mid = (normal_rows_elems<T>(B, n, q_count) + 63) & ~size_t(63);
+    const size_t tws = normal_transform_ws_elems<T>(B, n, q_count);
+    if (tws == (size_t)-1 || !ws || ws_elems < mid + tws) {
+        set_error("normal operator workspace too small: need %zu elements, got %zu", mid + tws, ws_elems);
+        return ADRT_B200_EWORKSPACE;
+    }
+    bool handled = false;
+    int rc = fused_adrt<T>(in, ws, B, n, q_first, q_count, ws + mid, ws_elems - mid, s, &handled, /*rows_out=*/true);
+    if (rc != ADRT_B200_OK) return rc;
+    if (!handled) { set_error("internal: no fused forward plan for n=%lld", (long long)n); return ADRT_B200_EINVAL; }
+    rc = fused_bdrt<T>(ws, out, B * q_count, n, 1, n, ws + mid, ws_elems - mid, s, &handled, /*rows_in=*/true);
+    if (rc == ADRT_B200_OK && !handled) { set_error("internal: no fused transposed plan for n=%lld", (long long)n); return ADRT_B200_EINVAL; }
+    return rc;
+}
+
+template <typename T>
+size_t normal_operator_ws_elems(int64_t B, int64_t n)
+{
+    if (n < 2) return 0;
+    const size_t tws = normal_transform_ws_elems<T>(B, n, 4);
+    if (tws == (size_t)-1) return (size_t)-1;
+    return ((normal_rows_elems<T>(B, n, 4) + 63) & ~size_t(63)) + tws + (((size_t)sino_elems(B, n) + 63) & ~size_t(63));
+}
+
+template <typename T>
+int normal_operator_impl(const T *in, T *out, int64_t B, int64_t n, T divisor, T *ws, size_t ws_bytes, cudaStream_t s)
+{
+    if (n == 1) {
+        // adrt and bdrt are identities on the four copies of the pixel: ((x/div + x/div) + x/div + x/div) / 4
+        const size_t need = (size_t)B * 4 * sizeof(T);
+        if (!ws || ws_bytes < need) { set_error("normal operator workspace too small"); return ADRT_B200_EWORKSPACE; }
+        int rc = launch_adrt_init<T>(in, ws, B, 1, s);
+        if (rc) return rc;
+        return launch_truncate_mean<T>(ws, out, B, 1, divisor, s);
+    }
+    const size_t need = normal_operator_ws_elems<T>(B, n);
+    if (need == (size_t)-1 || !ws || ws_bytes / sizeof(T) < need) {
+        set_error("normal operator workspace too small: need %zu bytes, got %zu", need * sizeof(T), ws_bytes);
+        return ADRT_B200_EWORKSPACE;
+    }
+    const size_t back = ((size_t)sino_elems(B, n) + 63) & ~size_t(63);
+    T *back_buf = ws, *rest = ws + back;
+    int rc = adrt_bdrt_rows_impl<T>(in, back_buf, B, n, 0, 4, rest, ws_bytes / sizeof(T) - back, s);
+    if (rc) return rc;
+    return launch_truncate_mean<T>(back_buf, out, B, n, divisor, s);
+}
+
 // ---- one full-multigrid pass, all levels, no host round trips --------------------
 // core.py:318-331 (iadrt_fmg_step): restrict the sinogram down to 1 x 1, then per level
 //   ret = prolongation(ret); ret -= highpass(mean_q(truncate(bdrt(adrt(ret) - a_level)) / (m - 1)))
@@ -461,6 +529,48 @@ int adrt_b200_bdrt_rows(const void *in, void *out, int64_t planes, int64_t n, in
     return DISPATCH(dtype,
                     bdrt_planes_impl<float>((const float *)in, (float *)out, planes, n, rows, (float *)ws, ws_bytes, as_stream(stream)),
                     bdrt_planes_impl<double>((const double *)in, (double *)out, planes, n, rows, (double *)ws, ws_bytes, as_stream(stream)));
+}
+
+// ---- fused normal operator -----------------------------------------------------------
+size_t adrt_b200_normal_operator_workspace_bytes(int64_t B, int64_t n, int dtype)
+{
+    if (B <= 0 || !is_pow2(n) || n > kMaxN || !dtype_ok(dtype)) return 0;
+    if (n == 1) return (size_t)B * 4 * dtype_size(dtype);
+    const size_t e = DISPATCH(dtype, normal_operator_ws_elems<float>(B, n), normal_operator_ws_elems<double>(B, n));
+    return e == (size_t)-1 ? 0 : e * dtype_size(dtype);
+}
+
+int adrt_b200_normal_operator(const void *in, void *out, int64_t B, int64_t n, double divisor, int dtype, void *ws,
+                              size_t ws_bytes, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    if ((rc = check_vec_aligned(in, out, ws))) return rc;
+    return DISPATCH(dtype,
+                    normal_operator_impl<float>((const float *)in, (float *)out, B, n, (float)divisor, (float *)ws, ws_bytes, as_stream(stream)),
+                    normal_operator_impl<double>((const double *)in, (double *)out, B, n, divisor, (double *)ws, ws_bytes, as_stream(stream)));
+}
+
+size_t adrt_b200_adrt_bdrt_rows_workspace_bytes(int64_t B, int64_t n, int dtype, int q_count)
+{
+    if (B <= 0 || !is_pow2(n) || n > kMaxN || n < 2 || !dtype_ok(dtype) || q_count < 1 || q_count > 4) return 0;
+    const size_t t = DISPATCH(dtype, normal_transform_ws_elems<float>(B, n, q_count), normal_transform_ws_elems<double>(B, n, q_count));
+    if (t == (size_t)-1) return 0;
+    const size_t mid = DISPATCH(dtype, normal_rows_elems<float>(B, n, q_count), normal_rows_elems<double>(B, n, q_count));
+    return (((mid + 63) & ~size_t(63)) + t) * dtype_size(dtype);
+}
+
+int adrt_b200_adrt_bdrt_rows(const void *in, void *out, int64_t B, int64_t n, int dtype, int q_first, int q_count, void *ws,
+                             size_t ws_bytes, void *stream)
+{
+    int rc = check_image(in, out, B, n, dtype);
+    if (rc) return rc;
+    if ((rc = check_vec_aligned(in, out, ws))) return rc;
+    ADRT_REQUIRE(n >= 2, "adrt_bdrt_rows needs n >= 2");
+    ADRT_REQUIRE(q_first >= 0 && q_count >= 1 && q_first + q_count <= 4, "bad quadrant range %d+%d", q_first, q_count);
+    return DISPATCH(dtype,
+                    adrt_bdrt_rows_impl<float>((const float *)in, (float *)out, B, n, q_first, q_count, (float *)ws, ws_bytes / 4, as_stream(stream)),
+                    adrt_bdrt_rows_impl<double>((const double *)in, (double *)out, B, n, q_first, q_count, (double *)ws, ws_bytes / 8, as_stream(stream)));
 }
 
 int adrt_b200_adrt_step(const void *in, void *out, int64_t B, int64_t n, int step, int dtype, void *stream)

@@ -74,7 +74,9 @@ template <typename T> int launch_binary(const T *a, const T *b, T *out, int64_t 
 // B images with q_count planes each (forward: quadrants q_first..q_first+q_count-1).
 template <typename T> size_t fused_adrt_workspace_elems(int64_t B, int64_t n, int q_count);
 template <typename T> size_t fused_bdrt_workspace_elems(int64_t B, int64_t n, int q_count);
-template <typename T> int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
-template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems, cudaStream_t s, bool *handled);
+// rows_out / rows_in: the caller-side array is in R-layout rows (planes x n x round4(2n-1)) instead of the
+// public (d, column) layout: how the fused normal operator hands adrt's result to bdrt
+template <typename T> int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems, cudaStream_t s, bool *handled, bool rows_out = false);
+template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems, cudaStream_t s, bool *handled, bool rows_in = false);
 
 }  // namespace adrt_b200

@@ -184,7 +184,7 @@ template <typename T, int M, int LOADK, int STOREK, bool kForward>
 int launch_pass_p(const T *src, T *dst, const PassArgs &a, const SchedArgs &sc, cudaStream_t s)
 {
     auto kern = pass_kernel_p<T, M, LOADK, STOREK, kForward>;
-    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     static std::atomic<size_t> cached[8] = {};
     const size_t base = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T);
     const int ci = sc.cap_per_sm > 0 && sc.cap_per_sm < 8 ? sc.cap_per_sm : 0;
@@ -387,14 +387,14 @@ int run_plan_cosched(const plan::Plan &pl, const CoCfg &cc, const T *in, T *out,
         T *dst;
         if (i == 0) {
             src = in;
-            a.src_plane_stride = kForward ? img_elems : sino_plane;
+            a.src_plane_stride = kForward ? img_elems : (p.in_pitch ? (long long)n * p.in_pitch : sino_plane);
             dst = ws_slot0;
             a.dst_plane_stride = (long long)n * p.out_pitch;
         } else {
             src = ws_slot0;
             a.src_plane_stride = (long long)n * p.in_pitch;
             dst = out;
-            a.dst_plane_stride = sino_plane;
+            a.dst_plane_stride = p.out_pitch ? (long long)n * p.out_pitch : sino_plane;
         }
         SchedArgs sc;
         sc.tiles_x = p.grid_x;
@@ -497,15 +497,19 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
             const T *src;
             T *dst;
             if (p.src_buf < 0) {
+                // caller's input: images, a public-layout sinogram, or R-layout rows (plan built with rows_in)
+                const long long in_plane = p.in_pitch ? (long long)n * p.in_pitch : sino_plane;
                 if (kForward) { src = in; a.plane0 = (int)p0; a.src_plane_stride = img_elems; }
-                else { src = in + p0 * sino_plane; a.src_plane_stride = sino_plane; }
+                else { src = in + p0 * in_plane; a.src_plane_stride = in_plane; }
             } else {
                 src = slot[p.src_buf];
                 a.src_plane_stride = (long long)n * p.in_pitch;
             }
             if (p.dst_buf < 0) {
-                dst = out + p0 * sino_plane;
-                a.dst_plane_stride = sino_plane;
+                // caller's output: public layout, or R-layout rows (plan built with rows_out)
+                const long long out_plane = p.out_pitch ? (long long)n * p.out_pitch : sino_plane;
+                dst = out + p0 * out_plane;
+                a.dst_plane_stride = out_plane;
             } else {
                 dst = slot[p.dst_buf];
                 a.dst_plane_stride = (long long)n * p.out_pitch;
@@ -559,24 +563,26 @@ size_t fused_bdrt_workspace_elems(int64_t B, int64_t n, int q_count)
 
 template <typename T>
 int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems,
-               cudaStream_t s, bool *handled)
+               cudaStream_t s, bool *handled, bool rows_out)
 {
+    // rows_out: `out` receives R-layout rows, planes x n x round4(2n-1) elements (fused_plan.h)
     plan::Plan pl;
     *handled = false;
-    if (n > kMaxN || !plan::make_forward_plan(n, sizeof(T), &pl)) return ADRT_B200_OK;
+    if (n > kMaxN || !plan::make_forward_plan(n, sizeof(T), &pl, rows_out)) return ADRT_B200_OK;
     *handled = true;
     return run_plan<T, true>(pl, in, out, B, q_first, q_count, ws, ws_elems, s);
 }
 
 template <typename T>
 int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems,
-               cudaStream_t s, bool *handled)
+               cudaStream_t s, bool *handled, bool rows_in)
 {
     // rows < 2n-1: only offsets d < rows of every output plane are computed, the rest of
     // `out` is left as it was
     plan::Plan pl;
     *handled = false;
-    if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl, rows)) return ADRT_B200_OK;
+    // rows_in: `in` holds R-layout rows as written by fused_adrt(..., rows_out = true)
+    if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl, rows, rows_in)) return ADRT_B200_OK;
     *handled = true;
     return run_plan<T, false>(pl, in, out, B, 0, q_count, ws, ws_elems, s);
 }
@@ -584,8 +590,8 @@ int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t r
 #define INSTANTIATE(T)                                                      \
     template size_t fused_adrt_workspace_elems<T>(int64_t, int64_t, int);   \
     template size_t fused_bdrt_workspace_elems<T>(int64_t, int64_t, int);   \
-    template int fused_adrt<T>(const T *, T *, int64_t, int64_t, int, int, T *, size_t, cudaStream_t, bool *); \
-    template int fused_bdrt<T>(const T *, T *, int64_t, int64_t, int, int64_t, T *, size_t, cudaStream_t, bool *);
+    template int fused_adrt<T>(const T *, T *, int64_t, int64_t, int, int, T *, size_t, cudaStream_t, bool *, bool); \
+    template int fused_bdrt<T>(const T *, T *, int64_t, int64_t, int, int64_t, T *, size_t, cudaStream_t, bool *, bool);
 INSTANTIATE(float)
 INSTANTIATE(double)
 

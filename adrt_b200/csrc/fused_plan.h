@@ -121,7 +121,12 @@ inline bool use_stream(int M, size_t elem_size, bool forward, int load)
     return strstr(set, key) != nullptr;
 }
 
-inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
+// `rows_out`: the last pass stores its result as R-layout rows (row = angle, pitch round4(D), logical
+// positions, zeros above each row's support) into the caller's buffer instead of the public (d, column)
+// layout -- the format the first pass of a transposed plan built with `rows_in` loads.  The fused
+// normal operator hands adrt's result to bdrt this way: neither the public-layout
+// store nor the public-layout load happens.
+inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl, bool rows_out = false)
 {
     const int n = (int)n64;
     const int K = ilog2(n64);
@@ -141,9 +146,9 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
         p.M = ms[i];
         p.s = s;
         p.load = first ? tile::LOAD_IMAGE : tile::LOAD_WROWS;
-        p.store = last ? tile::STORE_QCOLS : tile::STORE_WROWS;
+        p.store = (last && !rows_out) ? tile::STORE_QCOLS : tile::STORE_WROWS;
         p.in_pitch = first ? 0 : fwd_pitch(n, s);
-        p.out_pitch = last ? 0 : fwd_pitch(n, s + p.M);
+        p.out_pitch = last ? (rows_out ? round4(pl->D) : 0) : fwd_pitch(n, s + p.M);
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
@@ -151,7 +156,7 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
         const int TD = tile_td(p.M, p.store, p.stream);
         p.next_g = last ? 0 : (1 << ms[i + 1]);
         p.d_need = pl->D;
-        const long long extent = last ? pl->D : p.out_pitch;  // offsets that must be written
+        const long long extent = (last && !rows_out) ? pl->D : p.out_pitch;  // offsets that must be written
         p.grid_x = (int)((extent + TD - 1) / TD);
         p.grid_y = n / G;
         if (!last) {
@@ -166,7 +171,8 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl)
 // Transposed plan: forward pass i is undone by transposed pass npass-1-i.
 // `rows` < D asks only for output offsets d < rows of the final result (what
 // utils.truncate keeps): every pass then skips the tiles that cannot reach them.
-inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_t rows = -1)
+// `rows_in`: the first pass loads R-layout rows (see make_forward_plan) from the caller's buffer.
+inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_t rows = -1, bool rows_in = false)
 {
     const int n = (int)n64;
     const int K = ilog2(n64);
@@ -182,9 +188,9 @@ inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_
         p.M = ms[pl->npass - 1 - i];
         s -= p.M;
         p.s = s;  // block height of the rows this pass PRODUCES is 2^s
-        p.load = first ? tile::LOAD_QCOLS : tile::LOAD_WROWS;
+        p.load = (first && !rows_in) ? tile::LOAD_QCOLS : tile::LOAD_WROWS;
         p.store = last ? tile::STORE_QCOLS : tile::STORE_WROWS;
-        p.in_pitch = first ? 0 : round4(pl->D);
+        p.in_pitch = (first && !rows_in) ? 0 : round4(pl->D);
         p.out_pitch = last ? 0 : round4(pl->D);
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;

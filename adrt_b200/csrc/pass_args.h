@@ -43,7 +43,7 @@ inline size_t capped_smem(Kern kern, int threads, size_t base, int cap)
             (void)cudaGetLastError();
             return base;
         }
-        if (occ <= cap || smem + 1024 > 227 * 1024) return smem;
+        if (occ <= cap || smem + 1024 > 226 * 1024) return smem;
         smem += 1024;
     }
 }

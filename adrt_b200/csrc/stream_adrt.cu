@@ -154,7 +154,7 @@ int launch_p(const float *src, float *dst, PassArgs a, SchedArgs sc, int x_first
     sc.total = (unsigned)a.planes * (unsigned)tiles_x * (unsigned)sc.tiles_y;
     sc.ctas = ctas;
     auto kern = stream_kernel_p<Prog>;
-    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     static std::atomic<size_t> cached[8] = {};
     const size_t base = (size_t)Prog::G * stile::P * sizeof(float) + 32;
     const int ci = sc.cap_per_sm > 0 && sc.cap_per_sm < 8 ? sc.cap_per_sm : 0;

@@ -4,10 +4,11 @@ The reference ships these only as documentation recipes
 (/root/reference/docs/examples.cginverse.md:40-67 ``ADRTNormalOperator`` /
 ``iadrt_cg``, docs/examples.tomography.md:63-70 ridge variant): a conjugate
 gradient solve of ``A^T A x = A^T b`` with ``A = adrt`` and
-``A^T = mean_q(truncate(bdrt(.)))``.  Here every CG iteration stays on the GPU:
-one ``adrt`` + one ``bdrt`` restricted to the offsets ``truncate`` keeps (fused CUDA
-passes, ``adrt_b200_bdrt_rows``) + the ``truncate_mean`` kernel;
-the vector updates are elementwise torch ops on device tensors.
+``A^T = mean_q(truncate(bdrt(.)))``.  Here every CG iteration stays on the GPU: the
+operator is ONE native call (``adrt_b200_normal_operator``: forward passes, back-projection
+restricted to the offsets ``truncate`` keeps, ``truncate_mean``; the sinogram passes from
+adrt to bdrt as workspace rows and never takes the public layout); the vector updates are
+elementwise torch ops on device tensors.
 """
 from __future__ import annotations
 
@@ -30,7 +31,7 @@ def normal_operator(x, /, *, ridge: float = 0.0, dist=None):
 
         out = sharded_normal_operator(x, dist)
     else:
-        out = cd.bdrt_truncate_mean(cd.adrt(x), 1.0)
+        out = cd.normal_operator(x, 1.0)
     if ridge:
         out = out + ridge * x
     return out

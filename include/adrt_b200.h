@@ -101,6 +101,23 @@ int    adrt_b200_bdrt_planes(const void *in, void *out, int64_t planes, int64_t 
 int    adrt_b200_bdrt_rows(const void *in, void *out, int64_t planes, int64_t n, int64_t rows,
                            int dtype, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Fused normal operator A^T A of the CG recipe (docs/examples.cginverse.md:45-52
+ * ADRTNormalOperator._matmat: mean over quadrants of truncate(bdrt(adrt(x))); the same expression
+ * with a divisor is the gradient term of iadrt_fmg_step, core.py:329):
+ *   out (B,n,n) = mean_q(truncate(bdrt(adrt(in (B,n,n)))) / divisor)
+ * The sinogram is handed from adrt to bdrt as workspace rows (never stored in, nor re-loaded from, the
+ * public (d, column) layout) and the back-projection stops at offset n; bit-identical to composing
+ * adrt_b200_adrt, adrt_b200_bdrt and adrt_b200_truncate_mean.
+ * adrt_bdrt_rows: the same pipeline without the quadrant mean, for quadrants q_first ..
+ * q_first+q_count-1: out (B,q_count,2n-1,n) whose offsets d < n equal bdrt(adrt(in)); n >= 2. */
+size_t adrt_b200_normal_operator_workspace_bytes(int64_t B, int64_t n, int dtype);
+int    adrt_b200_normal_operator(const void *in, void *out, int64_t B, int64_t n, double divisor,
+                                 int dtype, void *workspace, size_t workspace_bytes, void *stream);
+size_t adrt_b200_adrt_bdrt_rows_workspace_bytes(int64_t B, int64_t n, int dtype, int q_count);
+int    adrt_b200_adrt_bdrt_rows(const void *in, void *out, int64_t B, int64_t n, int dtype,
+                                int q_first, int q_count, void *workspace, size_t workspace_bytes,
+                                void *stream);
+
 /* adrt.core.adrt_step / bdrt_step: adrt_cdefs_py.cpp:343-412, 550-619 ->
  * adrt_step (adrt_cdefs_adrt.hpp:215-258), bdrt_step (adrt_cdefs_bdrt.hpp:190-244).
  * 0 <= step < num_iters(n).  in/out (B,4,2n-1,n), must not alias. */

@@ -150,11 +150,13 @@ void run_kinds(const plan::Pass &p, const T *src, T *dst, int n, int D, int plan
     }
 }
 
+// rows_layout: forward stores / transposed loads the caller's array as R-layout rows (fused normal operator)
 template <typename T, bool kForward>
-int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1)
+int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1, bool rows_layout = false)
 {
     plan::Plan pl;
-    const bool ok = kForward ? plan::make_forward_plan(n64, sizeof(T), &pl) : plan::make_transposed_plan(n64, sizeof(T), &pl, rows);
+    const bool ok = kForward ? plan::make_forward_plan(n64, sizeof(T), &pl, rows_layout)
+                             : plan::make_transposed_plan(n64, sizeof(T), &pl, rows, rows_layout);
     if (!ok) return 1;
     const int n = pl.n, D = pl.D, planes = (int)B * 4;
     // workspaces start as NaN so that any read of a never-written element shows up
@@ -166,9 +168,9 @@ int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1)
         const T *src;
         T *dst;
         long long sps, dps;
-        if (p.src_buf < 0) { src = in; sps = kForward ? img : sino; }
+        if (p.src_buf < 0) { src = in; sps = kForward ? img : (p.in_pitch ? (long long)n * p.in_pitch : sino); }
         else { src = slot[p.src_buf]; sps = (long long)n * p.in_pitch; }
-        if (p.dst_buf < 0) { dst = out; dps = sino; }
+        if (p.dst_buf < 0) { dst = out; dps = p.out_pitch ? (long long)n * p.out_pitch : sino; }
         else { dst = slot[p.dst_buf]; dps = (long long)n * p.out_pitch; }
         if (p.stream) {
             run_stream<T, kForward>(p, src, dst, n, D, planes, sps, dps);
@@ -187,6 +189,15 @@ int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1)
     return 0;
 }
 
+// fused normal operator data flow: adrt with R-layout rows out (`mid`: B * 4 * n * round4(2n-1) elements),
+// then bdrt (offsets d < rows) with R-layout rows in
+template <typename T>
+int run_normal(const T *in, T *mid, T *out, int64_t B, int64_t n, int64_t rows)
+{
+    int rc = run<T, true>(in, mid, B, n, -1, true);
+    if (rc) return rc;
+    return run<T, false>(mid, out, B, n, rows, true);
+}
 }  // namespace
 
 extern "C" {
@@ -199,4 +210,6 @@ int emu_bdrt_f64(const double *in, double *out, int64_t B, int64_t n) { return r
 // only offsets d < rows of every output plane are produced
 int emu_bdrt_rows_f32(const float *in, float *out, int64_t B, int64_t n, int64_t rows) { return run<float, false>(in, out, B, n, rows); }
 int emu_bdrt_rows_f64(const double *in, double *out, int64_t B, int64_t n, int64_t rows) { return run<double, false>(in, out, B, n, rows); }
+int emu_normal_f32(const float *in, float *mid, float *out, int64_t B, int64_t n, int64_t rows) { return run_normal<float>(in, mid, out, B, n, rows); }
+int emu_normal_f64(const double *in, double *mid, double *out, int64_t B, int64_t n, int64_t rows) { return run_normal<double>(in, mid, out, B, n, rows); }
 }

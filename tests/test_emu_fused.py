@@ -192,3 +192,53 @@ def test_streaming_two_six_stage_passes(emu):
     # 6 + 5 and 5 + 6 (the 2048^2 plans) are covered through 11-stage splits of n = 2048 on the GPU.
     _check_stream(emu, 512, "6,3")
     _check_stream(emu, 512, "4,5")
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused normal operator: adrt hands its result to bdrt as R-layout rows
+# (fused_plan.h rows_out / rows_in) -- the public-layout store of the last forward pass and the
+# public-layout load of the first transposed pass never happen.
+def _check_normal(emu, n, dt, rows, stream_set=None, split=None):
+    keys = ("ADRT_B200_SPLIT", "ADRT_B200_SPLIT_BDRT", "ADRT_B200_STREAM_SET")
+    for k in keys:
+        os.environ.pop(k, None)
+    if stream_set is not None:
+        os.environ["ADRT_B200_STREAM_SET"] = stream_set
+    if split:
+        os.environ["ADRT_B200_SPLIT"] = split
+        os.environ["ADRT_B200_SPLIT_BDRT"] = split
+    try:
+        suffix = "f32" if dt == np.float32 else "f64"
+        D = 2 * n - 1
+        pitch = (D + 3) & ~3
+        for x in (make_image(23 + n, (1, n, n), dt), np.full((1, n, n), -0.0, dtype=dt)):
+            mid = np.full((1, 4, n, pitch), np.nan, dtype=dt)
+            out = np.full((1, 4, D, n), np.nan, dtype=dt)
+            rc = getattr(emu, f"emu_normal_{suffix}")(ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(mid.ctypes.data),
+                                                       ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(1), ctypes.c_int64(n),
+                                                       ctypes.c_int64(rows))
+            assert rc == 0
+            y = O.adrt(x)
+            # the hand-off buffer is the sinogram transposed (row = angle), complete up to offset D
+            want_mid = np.ascontiguousarray(np.swapaxes(y, -1, -2))
+            assert bytes_equal(mid[..., :D], want_mid), f"rows-layout adrt n={n}: {first_diff(mid[..., :D], want_mid)}"
+            want = O.bdrt(y)
+            assert bytes_equal(out[:, :, :rows], want[:, :, :rows]), f"normal n={n} rows={rows}: {first_diff(out[:, :, :rows], want[:, :, :rows])}"
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [2, 8, 32, 64, 128, 256])
+def test_normal_operator_rows_handoff(emu, n, dt):
+    _check_normal(emu, n, dt, n)
+    if n <= 64:
+        _check_normal(emu, n, dt, 2 * n - 1)
+
+
+@pytest.mark.parametrize("n,split,stream_set", [
+    (256, "3,5", "all"), (256, "5,3", "all"), (512, "3,6", "all"), (512, "6,3", "all"), (1024, None, None), (512, "3,3,3", ""),
+])
+def test_normal_operator_rows_handoff_streaming(emu, n, split, stream_set):
+    _check_normal(emu, n, np.float32, n, stream_set=stream_set, split=split)

@@ -46,6 +46,7 @@ for (B, n, dt) in ((16, 2048, torch.float32), (4, 4096, torch.float32), (8, 2048
     t = timeit(lambda: adrt.bdrt(y)); r["bdrt_ms"] = round(t, 3)
     t = timeit(lambda: cd.bdrt_planes(y, rows=n)); r["bdrt_rows_n_ms"] = round(t, 3)
     t = timeit(lambda: cd.truncate_mean(adrt.bdrt(adrt.adrt(x)), 1.0)); r["normal_op_unfused_ms"] = round(t, 3)
+    t = timeit(lambda: cd.bdrt_truncate_mean(adrt.adrt(x), 1.0)); r["normal_op_r1_rows_ms"] = round(t, 3)
     from adrt_b200 import recipes; t = timeit(lambda: recipes.normal_operator(x)); r["normal_op_ms"] = round(t, 3)
     out.append(r)
     print(json.dumps(r), flush=True)
