@@ -329,9 +329,16 @@ CoCfg cosched_config(const plan::Plan &pl, int64_t total_planes)
 {
     CoCfg c = {false, 2, 2};
     if (pl.npass != 2) return c;
-    // default: the fp32 plans whose second pass is a streaming kernel (bulk-copy loads)
-    c.on = sizeof(T) == 4 && pl.pass[1].stream && pl.pass[1].M == 6;
+    // Opt-in (ADRT_B200_COSCHED=1): measured slower than one launch per pass on every configuration
+    // (profiles/r02_cosched_sweep.jsonl) -- every pass kernel is bound by the shared memory its
+    // resident tiles occupy, so two kernels sharing an SM each run at their share of the tiles'
+    // rate and the L2 hits of the consumer do not make up for it.
+    c.on = false;
     if (const char *e = getenv("ADRT_B200_COSCHED")) c.on = atoi(e) != 0;
+    // only the ordinary two-pass kinds (public layout on the outside) have persistent instantiations
+    if (pl.pass[0].store != tile::STORE_WROWS || pl.pass[1].load != tile::LOAD_WROWS ||
+        pl.pass[1].store != tile::STORE_QCOLS || pl.pass[0].load == tile::LOAD_WROWS)
+        c.on = false;
     if (const char *e = getenv("ADRT_B200_CO_K1")) c.k1 = atoi(e);
     if (const char *e = getenv("ADRT_B200_CO_K2")) c.k2 = atoi(e);
     if (c.k1 < 1) c.k1 = 1;
