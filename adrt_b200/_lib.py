@@ -57,6 +57,8 @@ SIGNATURES = {
     "adrt_b200_fmg_step": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp, _c_sz, _c_vp]),
     "adrt_b200_interp_to_cart": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
     "adrt_b200_truncate": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_vp]),
+    "adrt_b200_stitch": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
+    "adrt_b200_unstitch": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
     "adrt_b200_truncate_mean": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_double, _c_int, _c_vp]),
     "adrt_b200_sub": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "adrt_b200_add": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),

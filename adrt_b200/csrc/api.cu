@@ -690,6 +690,23 @@ int adrt_b200_truncate(const void *in, void *out, int64_t B, int64_t n, int dtyp
                     launch_truncate<double>((const double *)in, (double *)out, B, n, as_stream(stream)));
 }
 
+int adrt_b200_stitch(const void *in, void *out, int64_t B, int64_t n, int remove_repeated, int dtype, void *stream)
+{
+    ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0 && n >= 1 && n <= kMaxN, "bad argument");
+    return DISPATCH(dtype,
+                    launch_stitch<float>((const float *)in, (float *)out, B, n, remove_repeated != 0, as_stream(stream)),
+                    launch_stitch<double>((const double *)in, (double *)out, B, n, remove_repeated != 0, as_stream(stream)));
+}
+
+int adrt_b200_unstitch(const void *in, void *out, int64_t B, int64_t n, int trimmed, int dtype, void *stream)
+{
+    ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0 && n >= 1 && n <= kMaxN, "bad argument");
+    ADRT_REQUIRE(!(trimmed && n < 2), "the narrow stitched form needs n >= 2");
+    return DISPATCH(dtype,
+                    launch_unstitch<float>((const float *)in, (float *)out, B, n, trimmed != 0, as_stream(stream)),
+                    launch_unstitch<double>((const double *)in, (double *)out, B, n, trimmed != 0, as_stream(stream)));
+}
+
 int adrt_b200_truncate_mean(const void *in, void *out, int64_t B, int64_t n, double divisor, int dtype, void *stream)
 {
     ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");

@@ -21,6 +21,7 @@ namespace adrt_b200 {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kRowThreadsS = 128;   // stitch / unstitch: threads along a row
 
 __host__ __device__ inline int ilog2(int64_t n)
 {
@@ -626,6 +627,79 @@ int launch_interp_to_cart(const T *in, T *out, const float *t, const int32_t *ba
     return ADRT_B200_OK;
 }
 
+// ---- stitch_adrt / unstitch_adrt (utils.py:111-134, 162-188) ------------------------
+// Stitched image: (3n-2) rows x 4 bands of w columns (w = n, or n-1 with remove_repeated); band i is
+// quadrant i, flipped on both axes when i is odd; bands 0,1 sit at rows 0 .. 2n-2, bands 2,3 at rows
+// n-1 .. 3n-3; everything else is zero.  Grid: x over the 4w columns, y over rows, z over images.
+template <typename T>
+__global__ void __launch_bounds__(kRowThreadsS)
+stitch_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int n, int w)
+{
+    const int D = 2 * n - 1, R = 3 * n - 2, W = 4 * w;
+    const int x = blockIdx.x * kRowThreadsS + threadIdx.x;
+    if (x >= W) return;
+    const int band = x / w, c = x - band * w;
+    const int off = band < 2 ? 0 : n - 1;
+    for (int64_t b = blockIdx.z; b < B; b += gridDim.z)
+        for (int r = blockIdx.y; r < R; r += gridDim.y) {
+            const int rr = r - off;
+            T v = T(0);
+            if (rr >= 0 && rr < D) {
+                const T *q = in + (b * 4 + band) * (int64_t)D * n;
+                v = (band & 1) ? q[(int64_t)(D - 1 - rr) * n + (n - 1 - c)] : q[(int64_t)rr * n + c];
+            }
+            out[(b * R + r) * (int64_t)W + x] = v;
+        }
+}
+
+// Inverse: out[b, q, d, c].  With the narrow (4n-4) form the dropped last column of a band is the
+// first column of the next band (read upside down for the wrap from band 3 to band 0).
+template <typename T>
+__global__ void __launch_bounds__(kRowThreadsS)
+unstitch_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int n, int w)
+{
+    const int D = 2 * n - 1, R = 3 * n - 2, W = 4 * w;
+    const int c = blockIdx.x * kRowThreadsS + threadIdx.x;
+    if (c >= n) return;
+    for (int64_t p = blockIdx.z; p < B * 4; p += gridDim.z) {
+        const int q = (int)(p & 3);
+        const T *I = in + (p >> 2) * (int64_t)R * W;
+        for (int d = blockIdx.y; d < D; d += gridDim.y) {
+            // position in the band before the odd quadrants' flip
+            const int dd = (q & 1) ? D - 1 - d : d, cc = (q & 1) ? n - 1 - c : c;
+            const int row = dd + (q < 2 ? 0 : n - 1);
+            T v;
+            if (cc < w) v = I[(int64_t)row * W + q * w + cc];
+            else if (q == 3) v = I[(int64_t)(R - 1 - row) * W];
+            else v = I[(int64_t)row * W + (q + 1) * w];
+            out[(p * D + d) * (int64_t)n + c] = v;
+        }
+    }
+}
+
+template <typename T>
+int launch_stitch(const T *in, T *out, int64_t B, int64_t n, bool remove_repeated, cudaStream_t s)
+{
+    const int w = (int)n - (remove_repeated ? 1 : 0);
+    if (w <= 0) return ADRT_B200_OK;   // n = 1 with remove_repeated: zero-width result
+    const int64_t R = 3 * n - 2;
+    dim3 grid((unsigned)((4 * w + kRowThreadsS - 1) / kRowThreadsS), (unsigned)(R < 65535 ? R : 65535), (unsigned)(B < 65535 ? B : 65535));
+    stitch_kernel<T><<<grid, kRowThreadsS, 0, s>>>(in, out, B, (int)n, w);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_unstitch(const T *in, T *out, int64_t B, int64_t n, bool trimmed, cudaStream_t s)
+{
+    const int w = (int)n - (trimmed ? 1 : 0);
+    const int64_t D = 2 * n - 1;
+    dim3 grid((unsigned)((n + kRowThreadsS - 1) / kRowThreadsS), (unsigned)(D < 65535 ? D : 65535), (unsigned)(B * 4 < 65535 ? B * 4 : 65535));
+    unstitch_kernel<T><<<grid, kRowThreadsS, 0, s>>>(in, out, B, (int)n, w);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
 template <typename T>
 int launch_truncate(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s)
 {
@@ -679,6 +753,8 @@ int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStr
     template int launch_interp_to_cart<T>(const T *, T *, const float *, const int32_t *, const float *, const float *, const int32_t *, const T *, int64_t, int64_t, cudaStream_t); \
     template int launch_truncate<T>(const T *, T *, int64_t, int64_t, cudaStream_t);                   \
     template int launch_truncate_mean<T>(const T *, T *, int64_t, int64_t, T, cudaStream_t);           \
+    template int launch_stitch<T>(const T *, T *, int64_t, int64_t, bool, cudaStream_t);               \
+    template int launch_unstitch<T>(const T *, T *, int64_t, int64_t, bool, cudaStream_t);             \
     template int launch_binary<T>(const T *, const T *, T *, int64_t, int, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(double)

@@ -2,13 +2,18 @@
 
 ``stitch_adrt``, ``unstitch_adrt``, ``truncate``, ``coord_adrt``,
 ``coord_cart_to_adrt`` follow /root/reference/src/adrt/utils.py:65-435 and
-work on NumPy arrays with any number of leading dims; ``stitch_adrt``,
-``unstitch_adrt`` and ``truncate`` also take CUDA tensors (pure view /
-flip / copy operations, done with torch indexing so nothing leaves the GPU).
+work on NumPy arrays with any number of leading dims.  ``stitch_adrt``,
+``unstitch_adrt`` and ``truncate`` also take CUDA tensors: float32/float64
+tensors go through the gather kernels ``adrt_b200_stitch`` /
+``adrt_b200_unstitch`` / ``adrt_b200_truncate`` (one pass over the data,
+SURVEY 8f rank 3), other dtypes through torch indexing, so nothing leaves
+the GPU.  ``coord_adrt`` tables are computed once per ``n`` (and once per
+device with ``device=``) and handed out as copies.
 ``interp_to_cart`` is the native gather (adrt_b200_interp_to_cart).
 """
 from __future__ import annotations
 
+import functools
 import operator
 import typing
 
@@ -39,6 +44,38 @@ def _swap(a):
     return a.transpose(-1, -2) if _is_tensor(a) else a.swapaxes(-1, -2)
 
 
+def _device_float(a) -> bool:
+    """CUDA float32 / float64 tensor: the dtypes the gather kernels are instantiated for."""
+    if not (_is_tensor(a) and a.is_cuda):
+        return False
+    import torch
+
+    return a.dtype in (torch.float32, torch.float64)
+
+
+def _device_gather(name, a, lead, in_tail, out_tail, n, flag):
+    """Run adrt_b200_<name>(in, out, B, n, flag, dtype, stream) on a CUDA tensor whose last
+    dims are `in_tail`; leading dims are flattened into the batch."""
+    import torch
+
+    from . import _lib
+
+    batch = 1
+    for s in lead:
+        batch *= int(s)
+    out = torch.empty((*lead, *out_tail), dtype=a.dtype, device=a.device)
+    if batch == 0 or out.numel() == 0:
+        return out
+    src = a.contiguous()
+    lib = _lib.load()
+    code = _lib.F32 if a.dtype == torch.float32 else _lib.F64
+    with torch.cuda.device(a.device):
+        rc = getattr(lib, f"adrt_b200_{name}")(src.data_ptr(), out.data_ptr(), batch, n, int(flag), code,
+                                                torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, name)
+    return out
+
+
 def _stack(parts, axis):
     if _is_tensor(parts[0]):
         import torch
@@ -58,6 +95,8 @@ def stitch_adrt(a, /, *, remove_repeated=False):
     rows_in, rows_out = 2 * n - 1, 3 * n - 2
     width = n - (1 if remove_repeated else 0)
     lead = tuple(a.shape[:-3])
+    if _device_float(a) and n <= 16384:
+        return _device_gather("stitch", a, lead, (4, rows_in, n), (rows_out, 4 * width), n, remove_repeated)
     if _is_tensor(a):
         canvas = a.new_zeros((*lead, rows_out, 4, width))
     else:
@@ -82,6 +121,8 @@ def unstitch_adrt(a, /):
         raise ValueError(f"unsuitable shape for ADRT unstitching {tuple(a.shape)}")
     trimmed = a.shape[-1] == 4 * n - 4
     rows = 2 * n - 1
+    if _device_float(a) and n <= 16384 and a.shape[-1] > 0:
+        return _device_gather("unstitch", a, tuple(a.shape[:-2]), tuple(a.shape[-2:]), (4, rows, n), n, trimmed)
     a = a.reshape((*a.shape[:-1], 4, n - (1 if trimmed else 0)))
     quads = []
     for q in range(4):
@@ -110,6 +151,8 @@ def truncate(a, /):
     n = a.shape[-1]
     if tuple(a.shape[-3:]) != (4, 2 * n - 1, n):
         raise ValueError(f"unsuitable shape for ADRT output processing {tuple(a.shape)}")
+    if _device_float(a) and n <= 16384:
+        return _adrt_cdefs.truncate(a.reshape((-1, 4, 2 * n - 1, n))).reshape((*a.shape[:-3], 4, n, n))
     return _stack(
         [
             _swap(_flip(a[..., 0, :n, :n], (-2,))),
@@ -135,10 +178,30 @@ def _check_domain_size(n) -> int:
     return n
 
 
-def coord_adrt(n, /) -> ADRTCoord:
+def coord_adrt(n, /, *, device=None) -> ADRTCoord:
     """Radon-domain coordinates of every ADRT entry: ``offset`` ``(4, 2n-1, n)``
-    and ``angle`` ``(4, 1, n)`` in float64 (utils.py:304-325)."""
+    and ``angle`` ``(4, 1, n)`` in float64 (utils.py:304-325).
+
+    The tables depend on ``n`` only: they are computed once per ``n`` and every call gets
+    its own writable copy (the reference's contract).  ``device=`` (an extension) returns
+    CUDA tensors instead, uploaded once per ``(n, device)`` and shared read-only."""
     n = _check_domain_size(n)
+    if device is not None:
+        return _coord_adrt_device(n, str(device))
+    base = _coord_adrt_table(n)
+    return ADRTCoord(base.offset.copy(), base.angle.copy())
+
+
+@functools.lru_cache(maxsize=8)
+def _coord_adrt_device(n: int, device: str) -> ADRTCoord:
+    import torch
+
+    base = _coord_adrt_table(n)
+    return ADRTCoord(torch.from_numpy(base.offset).to(device), torch.from_numpy(base.angle).to(device))
+
+
+@functools.lru_cache(maxsize=8)
+def _coord_adrt_table(n: int) -> ADRTCoord:
     heights, step = np.linspace(1, (1 - n) / n, num=2 * n - 1, endpoint=False, retstep=True, dtype=np.float64)
     heights += step / 2
     slope = np.linspace(0, 1, num=n, endpoint=True, dtype=np.float64)
@@ -149,6 +212,8 @@ def coord_adrt(n, /) -> ADRTCoord:
     )
     offsets = np.tile(np.stack([h0, -h0], axis=0), (2, 1, 1))
     angles = np.expand_dims(np.stack([theta_off, -theta, theta, -theta_off], axis=0), axis=1)
+    offsets.setflags(write=False)
+    angles.setflags(write=False)
     return ADRTCoord(offsets, angles)
 
 

@@ -171,6 +171,13 @@ int    adrt_b200_interp_to_cart(const void *in, void *out, int64_t B, int64_t n,
  *   sub / add:       out = a - b, out = a + b  (elementwise, count elements)
  *   sub_inplace:     a -= b                                                  */
 int    adrt_b200_truncate(const void *in, void *out, int64_t B, int64_t n, int dtype, void *stream);
+/* adrt.utils.stitch_adrt / unstitch_adrt (utils.py:111-134, 162-188; pure NumPy in the reference):
+ *   stitch:   (B,4,2n-1,n) -> (B,3n-2,4n), or (B,3n-2,4n-4) with remove_repeated
+ *   unstitch: the inverse, from either width (trimmed != 0: the 4n-4 form, n >= 2)            */
+int    adrt_b200_stitch(const void *in, void *out, int64_t B, int64_t n, int remove_repeated,
+                        int dtype, void *stream);
+int    adrt_b200_unstitch(const void *in, void *out, int64_t B, int64_t n, int trimmed,
+                          int dtype, void *stream);
 int    adrt_b200_truncate_mean(const void *in, void *out, int64_t B, int64_t n, double divisor,
                                int dtype, void *stream);
 int    adrt_b200_sub(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream);
