@@ -48,29 +48,65 @@ def gather_batch(local, dist=None):
 
 
 # ---------------------------------------------------------------------------
-# One large image over several GPUs: quadrant sharding
+# One large image over several GPUs (BASELINE config 5)
 # ---------------------------------------------------------------------------
-# The four quadrants of adrt are independent transforms of four orientations of
-# the image (adrt_cdefs_adrt.hpp:124-175) and bdrt treats planes independently,
-# so `truncate(bdrt(adrt(x)))` splits 4 ways with the image replicated and ONE
-# exchange per application: an all-gather of the four truncated (n, n)
-# back-projections, summed locally in the fixed order ((t0+t1)+t2)+t3 so that
-# the result is bit-identical to the single-GPU `np.mean(..., axis=-3)` order.
+# Two levels.  (i) The four quadrants of adrt are independent transforms of four
+# orientations of the image (adrt_cdefs_adrt.hpp:124-175) and bdrt treats planes
+# independently, so up to 4 ranks each take whole quadrants.  (ii) Beyond 4 ranks
+# every quadrant is shared by `parts` = world / 4 ranks by ANGLE BLOCK: a butterfly
+# stage only pairs rows of adjacent blocks with the same incoming angle
+# (adrt_cdefs_adrt.hpp:78-89), so a rank runs all passes but the last on its own
+# image-row blocks, the ranks of the quadrant swap workspace rows ONCE (row (blk, a)
+# goes from the owner of block blk to the owner of angle a), and the last pass runs
+# on the rank's own angles; bdrt mirrors this (include/adrt_b200.h, adrt_b200_adrt_part).
+# `truncate(bdrt(adrt(x)))` then needs one all-gather of the ranks' (n, n / parts)
+# pieces of the truncated back-projections; every rank sums the four quadrants in
+# the fixed order ((t0+t1)+t2)+t3 so the result is bit-identical to the single-GPU
+# `np.mean(..., axis=-3)` order.
 
-def quadrant_owner_range(world: int, rank: int) -> tuple[int, int]:
-    """Quadrants [q_first, q_first + q_count) owned by `rank` when `world` in {1, 2, 4}
-    ranks share one image (ranks >= 4 own nothing: angle-block sharding inside a
-    quadrant is not implemented yet)."""
-    if world >= 4:
-        return (rank, 1) if rank < 4 else (0, 0)
-    per = 4 // world
-    return rank * per, per
+SUPPORTED_WORLDS = (1, 2, 4, 8, 16, 32)
+M_LAST = 3   # stages fused by the pass after the exchange: 8 adjacent sinogram columns per group (one 32-byte sector in fp32)
 
 
-def truncate_quadrant(z, q: int):
-    """utils.truncate for a single quadrant plane ``(..., 2n-1, n)`` -> ``(..., n, n)``."""
-    n = z.shape[-1]
-    sq = z[..., :n, :]
+def image_layout(world: int, parts: int | None = None) -> tuple[int, int]:
+    """(quadrants per rank group, ranks per group) when `world` ranks share one image.
+
+    The ranks form ``world / parts`` groups of `parts` consecutive ranks; a group works on
+    ``4 / groups`` quadrants and splits each of them into `parts` angle blocks.  Default:
+    whole quadrants up to 4 ranks (parts = 1), 4 groups beyond (8 ranks: 4 quadrants x 2
+    angle halves).  `parts` (or $ADRT_B200_SHARD_PARTS) overrides, e.g. 2 ranks with
+    parts = 2: one group, every quadrant split in two."""
+    import os
+
+    if world not in SUPPORTED_WORLDS:
+        raise ValueError(f"single-image sharding supports world sizes {SUPPORTED_WORLDS}, got {world}")
+    if parts is None and os.environ.get("ADRT_B200_SHARD_PARTS"):
+        parts = int(os.environ["ADRT_B200_SHARD_PARTS"])
+    if parts is None:
+        parts = 1 if world <= 4 else world // 4
+    groups = world // parts if parts >= 1 and world % parts == 0 else 0
+    if groups not in (1, 2, 4) or parts > (1 << M_LAST):
+        raise ValueError(f"cannot split {world} ranks into groups of {parts}: need 1, 2 or 4 groups of at most {1 << M_LAST} ranks")
+    return 4 // groups, parts
+
+
+def quadrant_owner_range(world: int, rank: int, parts: int | None = None) -> tuple[int, int]:
+    """Quadrants [q_first, q_first + q_count) that `rank` works on."""
+    per, parts = image_layout(world, parts)
+    if not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} for world {world}")
+    return (rank // parts) * per, per
+
+
+def part_of(world: int, rank: int, parts: int | None = None) -> tuple[int, int]:
+    """(part, parts): the rank's angle block inside its quadrants."""
+    _, parts = image_layout(world, parts)
+    return rank % parts, parts
+
+
+def orient_square(sq, q: int):
+    """Undo adrt_init's orientation on the top ``(..., n, n)`` square of quadrant `q`
+    (the per-quadrant piece of utils.truncate, utils.py:234-242)."""
     if q == 0:
         return sq.flip(-2).transpose(-1, -2)
     if q == 1:
@@ -80,43 +116,136 @@ def truncate_quadrant(z, q: int):
     return sq.flip((-1, -2)).transpose(-1, -2)
 
 
+def truncate_quadrant(z, q: int):
+    """utils.truncate for a single quadrant plane ``(..., 2n-1, n)`` -> ``(..., n, n)``."""
+    n = z.shape[-1]
+    return orient_square(z[..., :n, :], q)
+
+
 def _local_quadrant_backprojections(x, q_first, q_count):
     from . import _adrt_cdefs as cd
 
-    y = cd.adrt_quadrants(x, q_first, q_count)
-    z = cd.bdrt_planes(y, rows=x.shape[-1])
+    n = x.shape[-1]
+    if n < 2:
+        z = cd.bdrt_planes(cd.adrt_quadrants(x, q_first, q_count), rows=n)
+    else:
+        z = cd.adrt_bdrt_rows(x, q_first, q_count)   # sinogram handed over as workspace rows
     return [truncate_quadrant(z[..., i, :, :], q_first + i).contiguous() for i in range(q_count)]
 
 
-def sharded_normal_operator(x, dist=None, *, local_fn=_local_quadrant_backprojections):
-    """``mean_q(truncate(bdrt(adrt(x))))`` with the quadrants spread over the ranks of
-    the default process group.  `x` ``(n, n)`` or ``(B, n, n)`` must be replicated
-    on every rank; the result is replicated too and bit-identical to the
-    single-GPU ``recipes.normal_operator``.  `local_fn(x, q_first, q_count)` returns
-    the rank's truncated back-projections (overridable so that CPU tests can
-    exercise the exchange with the oracle)."""
+def exchange_rows(xbuf, part: int, parts: int, base_rank: int, dist, forward: bool) -> None:
+    """The one data-path exchange of angle-block sharding, in place on `xbuf`
+    ``(planes, blocks, angles, pitch)``.  Rank ``base_rank + p`` owns blocks
+    ``[p*blocks/parts, (p+1)*blocks/parts)`` and angles ``[p*angles/parts, ...)``.
+    forward (adrt): a rank holds all angles of its blocks and needs all blocks of its
+    angles; transposed (bdrt): the other way round.  One batched send/recv per peer."""
+    import torch
+
+    nblk, e = xbuf.shape[1], xbuf.shape[2]
+    bl = lambda p: slice(p * nblk // parts, (p + 1) * nblk // parts)   # noqa: E731
+    an = lambda p: slice(p * e // parts, (p + 1) * e // parts)         # noqa: E731
+    ops, recvs = [], []
+    for p in range(parts):
+        if p == part:
+            continue
+        if forward:
+            send = xbuf[:, bl(part), an(p)].contiguous()
+            target = xbuf[:, bl(p), an(part)]
+        else:
+            send = xbuf[:, bl(p), an(part)].contiguous()
+            target = xbuf[:, bl(part), an(p)]
+        recv = torch.empty(target.shape, dtype=xbuf.dtype, device=xbuf.device)
+        ops.append(dist.P2POp(dist.isend, send, base_rank + p))
+        ops.append(dist.P2POp(dist.irecv, recv, base_rank + p))
+        recvs.append((target, recv))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for target, recv in recvs:
+        target.copy_(recv)
+
+
+def _part_backprojection(x, q_first: int, q_count: int, part: int, parts: int, base_rank: int, dist, exchange=None):
+    """Offsets ``d < n``, columns ``[part*n/parts, (part+1)*n/parts)`` of quadrants
+    ``q_first .. q_first+q_count-1`` of ``bdrt(adrt(x))`` for `x` ``(B, n, n)``:
+    ``(B, q_count, n, n/parts)``, computed by the `parts` ranks ``base_rank ..`` together
+    (two exchanges: one inside adrt, one inside bdrt)."""
+    exchange = exchange or exchange_rows
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    B, n = int(x.shape[0]), int(x.shape[-1])
+    code = _lib.F32 if x.dtype == torch.float32 else _lib.F64
+    m_last = M_LAST
+    pf = int(lib.adrt_b200_part_exchange_pitch(n, code, m_last, 1))
+    pb = int(lib.adrt_b200_part_exchange_pitch(n, code, m_last, 0))
+    if pf == 0 or pb == 0 or (1 << m_last) < parts:
+        raise ValueError(f"angle-block sharding needs n >= {1 << (m_last + 1)} and at most {1 << m_last} ranks per quadrant")
+    nblk, e = 1 << m_last, n >> m_last
+    D = 2 * n - 1
+    dev = x.device
+    nbytes = int(lib.adrt_b200_part_workspace_bytes(B * q_count, n, code, m_last))
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        planes = B * q_count
+        xf = torch.empty((planes, nblk, e, pf), dtype=x.dtype, device=dev)
+        sino = torch.empty((planes, D, n), dtype=x.dtype, device=dev)
+        args = (B, n, code, q_first, q_count, part, parts, m_last)
+        _lib.check(lib.adrt_b200_adrt_part(x.data_ptr(), xf.data_ptr(), None, *args, 0, ws.data_ptr(), nbytes, stream), "adrt_part")
+        exchange(xf, part, parts, base_rank, dist, True)
+        _lib.check(lib.adrt_b200_adrt_part(None, xf.data_ptr(), sino.data_ptr(), *args, 1, ws.data_ptr(), nbytes, stream), "adrt_part")
+        del xf
+        xb = torch.empty((planes, nblk, e, pb), dtype=x.dtype, device=dev)
+        out = torch.empty((planes, D, n), dtype=x.dtype, device=dev)
+        bargs = (planes, n, n, code, part, parts, m_last)
+        _lib.check(lib.adrt_b200_bdrt_part(sino.data_ptr(), xb.data_ptr(), None, *bargs, 0, ws.data_ptr(), nbytes, stream), "bdrt_part")
+        exchange(xb, part, parts, base_rank, dist, False)
+        _lib.check(lib.adrt_b200_bdrt_part(None, xb.data_ptr(), out.data_ptr(), *bargs, 1, ws.data_ptr(), nbytes, stream), "bdrt_part")
+    cols = slice(part * n // parts, (part + 1) * n // parts)
+    return out.view(B, q_count, D, n)[:, :, :n, cols].contiguous()
+
+
+def sharded_normal_operator(x, dist=None, *, local_fn=_local_quadrant_backprojections, parts=None):
+    """``mean_q(truncate(bdrt(adrt(x))))`` with ONE image (or batch) spread over the ranks
+    of the default process group: by quadrant up to 4 ranks, by quadrant x angle block
+    beyond (8 ranks = 4 quadrants x 2 angle halves).  `x` ``(n, n)`` or ``(B, n, n)`` must
+    be replicated on every rank; the result is replicated too and bit-identical to the
+    single-GPU ``recipes.normal_operator``.  `local_fn(x, q_first, q_count)` returns a
+    rank's truncated back-projections in the quadrant-only mode (overridable so that CPU
+    tests can exercise the exchange with the oracle)."""
     import torch
 
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    q_first, q_count = quadrant_owner_range(world, rank)
-    mine = local_fn(x, q_first, q_count) if q_count else []
-    if world == 1:
-        parts = mine
-    else:
-        per = max(1, 4 // min(world, 4))
-        # fixed-size buffer per rank: `per` images, zero for ranks that own nothing
-        local = torch.zeros((per, *x.shape), dtype=x.dtype, device=x.device)
-        for i, t in enumerate(mine):
-            local[i] = t
-        gathered = [torch.empty_like(local) for _ in range(world)]
-        dist.all_gather(gathered, local)
-        parts = []
-        for r in range(min(world, 4)):
-            qf, qc = quadrant_owner_range(world, r)
-            parts += [gathered[r][i] for i in range(qc)]
-    t0, t1, t2, t3 = parts
-    return (((t0 + t1) + t2) + t3) / 4
+    per, parts = image_layout(world, parts)
+    q_first, q_count = quadrant_owner_range(world, rank, parts)
+    if parts == 1:
+        mine = local_fn(x, q_first, q_count)
+        if world == 1:
+            parts_list = mine
+        else:
+            local = torch.stack(mine, dim=0)                     # (per, ..., n, n)
+            gathered = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(gathered, local)
+            parts_list = [g[i] for g in gathered for i in range(per)]
+        t0, t1, t2, t3 = parts_list
+        return (((t0 + t1) + t2) + t3) / 4
+    squeeze = x.ndim == 2
+    xb = (x[None] if squeeze else x).contiguous()
+    part = rank % parts
+    piece = _part_backprojection(xb, q_first, q_count, part, parts, rank - part, dist)   # (B, per, n, n / parts)
+    gathered = [torch.empty_like(piece) for _ in range(world)]
+    dist.all_gather(gathered, piece)
+    quads = []
+    for q in range(4):
+        grp, i = divmod(q, per)
+        # offsets d < n of quadrant q, all columns: the pieces of the group's ranks side by side
+        square = torch.cat([gathered[grp * parts + p][:, i] for p in range(parts)], dim=-1)
+        quads.append(orient_square(square, q))
+    res = (((quads[0] + quads[1]) + quads[2]) + quads[3]) / 4
+    return res[0] if squeeze else res
 
 
 def bind_host_to_device(index: int) -> bool:

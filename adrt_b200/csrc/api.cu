@@ -573,6 +573,57 @@ int adrt_b200_adrt_bdrt_rows(const void *in, void *out, int64_t B, int64_t n, in
                     adrt_bdrt_rows_impl<double>((const double *)in, (double *)out, B, n, q_first, q_count, (double *)ws, ws_bytes / 8, as_stream(stream)));
 }
 
+// ---- angle-block sharding of single large images --------------------------
+static int check_part(int64_t n, int part, int parts, int m_last, int phase)
+{
+    ADRT_REQUIRE(parts >= 2 && (parts & (parts - 1)) == 0 && part >= 0 && part < parts, "bad part %d of %d", part, parts);
+    ADRT_REQUIRE(m_last >= 1 && (1 << m_last) >= parts && m_last < num_iters(n), "bad m_last %d for n=%lld, parts=%d", m_last,
+                 (long long)n, parts);
+    ADRT_REQUIRE(phase == 0 || phase == 1, "phase must be 0 or 1");
+    return ADRT_B200_OK;
+}
+
+size_t adrt_b200_part_exchange_pitch(int64_t n, int dtype, int m_last, int forward)
+{
+    if (!is_pow2(n) || n > kMaxN || !dtype_ok(dtype) || m_last < 1 || m_last >= num_iters(n)) return 0;
+    return DISPATCH(dtype, part_exchange_pitch<float>(n, m_last, forward != 0), part_exchange_pitch<double>(n, m_last, forward != 0));
+}
+
+size_t adrt_b200_part_workspace_bytes(int64_t planes, int64_t n, int dtype, int m_last)
+{
+    if (planes <= 0 || !is_pow2(n) || n > kMaxN || !dtype_ok(dtype) || m_last < 1 || m_last >= num_iters(n)) return 0;
+    const size_t e = DISPATCH(dtype, part_workspace_elems<float>(planes, n, m_last), part_workspace_elems<double>(planes, n, m_last));
+    return e == (size_t)-1 ? 0 : e * dtype_size(dtype);
+}
+
+int adrt_b200_adrt_part(const void *img, void *xbuf, void *sino, int64_t B, int64_t n, int dtype, int q_first, int q_count,
+                        int part, int parts, int m_last, int phase, void *ws, size_t ws_bytes, void *stream)
+{
+    ADRT_REQUIRE(xbuf && (phase == 0 ? img != nullptr : sino != nullptr), "null pointer argument");
+    ADRT_REQUIRE(dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
+    ADRT_REQUIRE(q_first >= 0 && q_count >= 1 && q_first + q_count <= 4, "bad quadrant range %d+%d", q_first, q_count);
+    int rc = check_part(n, part, parts, m_last, phase);
+    if (rc) return rc;
+    if ((rc = check_vec_aligned(phase == 0 ? img : sino, xbuf, ws))) return rc;
+    return DISPATCH(dtype,
+                    fused_adrt_part<float>((const float *)img, (float *)xbuf, (float *)sino, B, n, q_first, q_count, part, parts, m_last, phase, (float *)ws, ws_bytes / 4, as_stream(stream)),
+                    fused_adrt_part<double>((const double *)img, (double *)xbuf, (double *)sino, B, n, q_first, q_count, part, parts, m_last, phase, (double *)ws, ws_bytes / 8, as_stream(stream)));
+}
+
+int adrt_b200_bdrt_part(const void *sino, void *xbuf, void *out, int64_t planes, int64_t n, int64_t rows, int dtype, int part,
+                        int parts, int m_last, int phase, void *ws, size_t ws_bytes, void *stream)
+{
+    ADRT_REQUIRE(xbuf && (phase == 0 ? sino != nullptr : out != nullptr), "null pointer argument");
+    ADRT_REQUIRE(dtype_ok(dtype) && planes > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
+    ADRT_REQUIRE(rows == -1 || (rows >= 1 && rows <= 2 * n - 1), "rows %lld out of range", (long long)rows);
+    int rc = check_part(n, part, parts, m_last, phase);
+    if (rc) return rc;
+    if ((rc = check_vec_aligned(phase == 0 ? sino : out, xbuf, ws))) return rc;
+    return DISPATCH(dtype,
+                    fused_bdrt_part<float>((const float *)sino, (float *)xbuf, (float *)out, planes, n, rows, part, parts, m_last, phase, (float *)ws, ws_bytes / 4, as_stream(stream)),
+                    fused_bdrt_part<double>((const double *)sino, (double *)xbuf, (double *)out, planes, n, rows, part, parts, m_last, phase, (double *)ws, ws_bytes / 8, as_stream(stream)));
+}
+
 int adrt_b200_adrt_step(const void *in, void *out, int64_t B, int64_t n, int step, int dtype, void *stream)
 {
     int rc = check_image(in, out, B, n, dtype);

@@ -67,7 +67,7 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
     c.n = a.n;
     c.D = a.D;
     c.e = a.e;
-    c.g = blockIdx.y;
+    c.g = blockIdx.y + a.y_off;
     c.k0 = c.g >> a.loge;
     c.a_g = c.g & (a.e - 1);
     c.d0 = blockIdx.x * Prog::TD;
@@ -150,7 +150,7 @@ pass_kernel_p(const T *__restrict__ src, T *__restrict__ dst, PassArgs a, SchedA
     iter.begin(sc, slot, tid);
     int plane, y, x, ready_plane = -1;
     while (iter.current(sc, slot, tid, plane, y, x)) {
-        c.g = y;
+        c.g = y + a.y_off;
         c.k0 = c.g >> a.loge;
         c.a_g = c.g & (a.e - 1);
         c.d0 = (x + a.x_off) * Prog::TD;
@@ -387,6 +387,7 @@ int run_plan_cosched(const plan::Plan &pl, const CoCfg &cc, const T *in, T *out,
         a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
         a.planes = (int)total;
         a.x_off = 0;
+        a.y_off = 0;
         a.q_first = q_first; a.q_count = q_count;
         a.plane0 = 0;
         a.side_idx = 0;
@@ -498,6 +499,7 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
             a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
             a.planes = np;
             a.x_off = 0;
+            a.y_off = 0;
             a.q_first = q_first; a.q_count = q_count;
             a.plane0 = 0;
             a.side_idx = lane == 0 ? 0 : 2;
@@ -529,6 +531,51 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
         cudaStreamWaitEvent(s, join, 0);
         cudaEventDestroy(fork);
         cudaEventDestroy(join);
+    }
+    return rc;
+}
+
+// ---- angle-block sharding (fused_plan.h part_*) ----------------------------------------------
+// phase 0: the passes before the exchange (forward: all but the last, on the rank's blocks; transposed:
+// the first, on the rank's columns) writing the exchange buffer `xbuf` (planes x n rows x pitch);
+// phase 1: the passes after it reading `xbuf`.
+template <typename T, bool kForward>
+int run_part(const plan::Plan &pl, const T *in, T *out, T *xbuf, int64_t total, int q_first, int q_count, int part, int parts,
+             int phase, T *ws, size_t ws_elems, cudaStream_t s)
+{
+    const int n = pl.n, D = pl.D, np = pl.npass;
+    const int xi = kForward ? np - 2 : 0;
+    const size_t slot0 = pl.ws_slot_elems[0] * (size_t)total, slot1 = pl.ws_slot_elems[1] * (size_t)total;
+    if (slot0 + slot1 > ws_elems) {
+        set_error("sharded transform workspace too small: need %zu elements, got %zu", slot0 + slot1, ws_elems);
+        return ADRT_B200_EWORKSPACE;
+    }
+    T *slot[2] = {ws, ws + slot0};
+    const long long img_elems = (long long)n * n, sino_plane = (long long)D * n;
+    const int first = phase == 0 ? 0 : xi + 1, last = phase == 0 ? xi : np - 1;
+    int rc = ADRT_B200_OK;
+    for (int i = first; i <= last && rc == ADRT_B200_OK; ++i) {
+        const plan::Pass &p = pl.pass[i];
+        const bool angle_pass = kForward ? (i == np - 1) : (i == 0);
+        const plan::YRange yr = angle_pass ? plan::part_angle_range(p, part, parts) : plan::part_block_range(p, n, part, parts);
+        plan::Pass q = p;
+        q.grid_y = yr.y_cnt;
+        PassArgs a;
+        a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g; a.d_need = p.d_need;
+        a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
+        a.planes = (int)total;
+        a.x_off = 0;
+        a.y_off = yr.y_off;
+        a.q_first = q_first; a.q_count = q_count;
+        a.plane0 = 0;
+        a.side_idx = 0;
+        const T *src;
+        T *dst;
+        if (p.src_buf < 0) { src = in; a.src_plane_stride = kForward ? img_elems : sino_plane; }
+        else { src = (i == xi + 1) ? xbuf : slot[p.src_buf]; a.src_plane_stride = (long long)n * p.in_pitch; }
+        if (p.dst_buf < 0) { dst = out; a.dst_plane_stride = sino_plane; }
+        else { dst = (i == xi) ? xbuf : slot[p.dst_buf]; a.dst_plane_stride = (long long)n * p.out_pitch; }
+        rc = dispatch_pass<T, kForward>(q, src, dst, a, s);
     }
     return rc;
 }
@@ -594,7 +641,63 @@ int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t r
     return run_plan<T, false>(pl, in, out, B, 0, q_count, ws, ws_elems, s);
 }
 
+template <typename T>
+bool make_part_plan(int64_t n, int parts, int m_last, bool forward, int64_t rows, plan::Plan *pl)
+{
+    if (n > kMaxN || parts < 2 || (parts & (parts - 1)) || m_last < 1 || (1 << m_last) < parts) return false;
+    const int K = plan::ilog2(n);
+    const std::vector<int> ms = plan::part_split(K, sizeof(T), m_last);
+    if (ms.size() < 2) return false;
+    return forward ? plan::make_forward_plan_split(n, sizeof(T), ms, pl) : plan::make_transposed_plan_split(n, sizeof(T), ms, pl, rows);
+}
+
+template <typename T>
+size_t part_exchange_pitch(int64_t n, int m_last, bool forward)
+{
+    plan::Plan pl;
+    if (!make_part_plan<T>(n, 2, m_last, forward, -1, &pl)) return 0;
+    return (size_t)pl.pass[forward ? pl.npass - 2 : 0].out_pitch;
+}
+
+template <typename T>
+size_t part_workspace_elems(int64_t planes, int64_t n, int m_last)
+{
+    plan::Plan f, b;
+    if (!make_part_plan<T>(n, 2, m_last, true, -1, &f) || !make_part_plan<T>(n, 2, m_last, false, -1, &b)) return (size_t)-1;
+    const size_t wf = (f.ws_slot_elems[0] + f.ws_slot_elems[1]) * (size_t)planes;
+    const size_t wb = (b.ws_slot_elems[0] + b.ws_slot_elems[1]) * (size_t)planes;
+    return wf > wb ? wf : wb;
+}
+
+template <typename T>
+int fused_adrt_part(const T *img, T *xbuf, T *sino, int64_t B, int64_t n, int q_first, int q_count, int part, int parts,
+                    int m_last, int phase, T *ws, size_t ws_elems, cudaStream_t s)
+{
+    plan::Plan pl;
+    if (!make_part_plan<T>(n, parts, m_last, true, -1, &pl)) {
+        set_error("no sharded forward plan for n=%lld parts=%d m_last=%d", (long long)n, parts, m_last);
+        return ADRT_B200_EINVAL;
+    }
+    return run_part<T, true>(pl, img, sino, xbuf, B * q_count, q_first, q_count, part, parts, phase, ws, ws_elems, s);
+}
+
+template <typename T>
+int fused_bdrt_part(const T *sino, T *xbuf, T *out, int64_t planes, int64_t n, int64_t rows, int part, int parts, int m_last,
+                    int phase, T *ws, size_t ws_elems, cudaStream_t s)
+{
+    plan::Plan pl;
+    if (!make_part_plan<T>(n, parts, m_last, false, rows, &pl)) {
+        set_error("no sharded transposed plan for n=%lld parts=%d m_last=%d", (long long)n, parts, m_last);
+        return ADRT_B200_EINVAL;
+    }
+    return run_part<T, false>(pl, sino, out, xbuf, planes, 0, 1, part, parts, phase, ws, ws_elems, s);
+}
+
 #define INSTANTIATE(T)                                                      \
+    template size_t part_exchange_pitch<T>(int64_t, int, bool);             \
+    template size_t part_workspace_elems<T>(int64_t, int64_t, int);         \
+    template int fused_adrt_part<T>(const T *, T *, T *, int64_t, int64_t, int, int, int, int, int, int, T *, size_t, cudaStream_t); \
+    template int fused_bdrt_part<T>(const T *, T *, T *, int64_t, int64_t, int64_t, int, int, int, int, T *, size_t, cudaStream_t); \
     template size_t fused_adrt_workspace_elems<T>(int64_t, int64_t, int);   \
     template size_t fused_bdrt_workspace_elems<T>(int64_t, int64_t, int);   \
     template int fused_adrt<T>(const T *, T *, int64_t, int64_t, int, int, T *, size_t, cudaStream_t, bool *, bool); \

@@ -126,17 +126,35 @@ inline bool use_stream(int M, size_t elem_size, bool forward, int load)
 // layout -- the format the first pass of a transposed plan built with `rows_in` loads.  The fused
 // normal operator hands adrt's result to bdrt this way: neither the public-layout
 // store nor the public-layout load happens.
+inline bool make_forward_plan_split(int64_t n64, size_t elem_size, const std::vector<int> &ms, Plan *pl, bool rows_out = false);
+
 inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl, bool rows_out = false)
 {
-    const int n = (int)n64;
     const int K = ilog2(n64);
     if (K < 1) return false;
-    pl->n = n; pl->K = K; pl->D = 2 * n - 1;
     // fp32: the pass next to the public layout is the long one in both directions (it is a streaming
     // pass, stream_tile.h, and the fastest kernel per stage) -- measured 4.7 vs 5.05 ms at 64 x 2048^2
     std::vector<int> ms = split_stages(K, elem_size, "ADRT_B200_SPLIT", elem_size == 4);
     // 256^2 fp32: (3, 5) ends with a streaming five-stage pass -- 4096 images: 12.5 ms vs 16.3 ms for (4, 4)
     if (elem_size == 4 && K == 8 && !getenv("ADRT_B200_SPLIT")) ms = {3, 5};
+    return make_forward_plan_split(n64, elem_size, ms, pl, rows_out);
+}
+
+// Same with the stages-per-pass given explicitly (they must add up to log2 n).
+inline bool make_forward_plan_split(int64_t n64, size_t elem_size, const std::vector<int> &ms, Plan *pl, bool rows_out)
+{
+    const int n = (int)n64;
+    const int K = ilog2(n64);
+    if (K < 1 || ms.empty() || (int)ms.size() > kMaxPasses) return false;
+    {
+        int sum = 0;
+        for (int m : ms) {
+            if (m < 1 || m > max_stages_per_pass(elem_size)) return false;
+            sum += m;
+        }
+        if (sum != K) return false;
+    }
+    pl->n = n; pl->K = K; pl->D = 2 * n - 1;
     pl->npass = (int)ms.size();
     pl->ws_slot_elems[0] = pl->ws_slot_elems[1] = 0;
     int s = 0;
@@ -172,13 +190,32 @@ inline bool make_forward_plan(int64_t n64, size_t elem_size, Plan *pl, bool rows
 // `rows` < D asks only for output offsets d < rows of the final result (what
 // utils.truncate keeps): every pass then skips the tiles that cannot reach them.
 // `rows_in`: the first pass loads R-layout rows (see make_forward_plan) from the caller's buffer.
+inline bool make_transposed_plan_split(int64_t n64, size_t elem_size, const std::vector<int> &ms, Plan *pl, int64_t rows = -1,
+                                       bool rows_in = false);
+
 inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_t rows = -1, bool rows_in = false)
+{
+    const int K = ilog2(n64);
+    if (K < 1) return false;
+    return make_transposed_plan_split(n64, elem_size, split_stages(K, elem_size, "ADRT_B200_SPLIT_BDRT"), pl, rows, rows_in);
+}
+
+// `ms`: stages per pass in FORWARD order (transposed pass i undoes forward pass npass-1-i).
+inline bool make_transposed_plan_split(int64_t n64, size_t elem_size, const std::vector<int> &ms, Plan *pl, int64_t rows,
+                                       bool rows_in)
 {
     const int n = (int)n64;
     const int K = ilog2(n64);
-    if (K < 1) return false;
+    if (K < 1 || ms.empty() || (int)ms.size() > kMaxPasses) return false;
+    {
+        int sum = 0;
+        for (int m : ms) {
+            if (m < 1 || m > max_stages_per_pass(elem_size)) return false;
+            sum += m;
+        }
+        if (sum != K) return false;
+    }
     pl->n = n; pl->K = K; pl->D = 2 * n - 1;
-    const std::vector<int> ms = split_stages(K, elem_size, "ADRT_B200_SPLIT_BDRT");
     pl->npass = (int)ms.size();
     pl->ws_slot_elems[0] = pl->ws_slot_elems[1] = 0;
     int s = K;
@@ -217,6 +254,58 @@ inline bool make_transposed_plan(int64_t n64, size_t elem_size, Plan *pl, int64_
         p.grid_x = (int)((extent + TD - 1) / TD);
     }
     return true;
+}
+
+// ---- angle-block sharding of one plane over `parts` ranks (single large image) --------
+// The last forward pass fuses m_last stages (2^m_last >= parts).  Every earlier pass only combines
+// image rows of the same 2^(K - m_last)-row block, so rank `part` runs them on its own blocks alone;
+// the last pass only combines rows with the same incoming angle a_g, so after ONE exchange of
+// workspace rows (row (blk, a): the owner of block blk sends it to the owner of angle a) rank `part`
+// runs it for its own angle range and ends up with the sinogram columns
+// [part * n / parts, (part + 1) * n / parts).  bdrt is the mirror image: its first pass (the transpose
+// of that last pass) runs on the rank's columns, the exchange goes the other way, the remaining passes
+// run on the rank's blocks.
+struct YRange {
+    int y_off, y_cnt;   // groups (blockIdx.y range) of a pass that belong to a rank
+};
+
+// stages-per-pass of the sharded plans: the first K - m_last stages split as evenly as possible, then m_last
+inline std::vector<int> part_split(int K, size_t elem_size, int m_last)
+{
+    std::vector<int> ms;
+    const int head = K - m_last;
+    if (head < 1 || m_last < 1) return ms;
+    const int cap = max_stages_per_pass(elem_size);
+    const int np = (head + cap - 1) / cap;
+    int left = head;
+    for (int i = 0; i < np; ++i) {
+        const int m = (left + (np - i) - 1) / (np - i);
+        ms.push_back(m);
+        left -= m;
+    }
+    ms.push_back(m_last);
+    return ms;
+}
+
+// a pass that works on whole blocks (every pass but the one that fuses the last m_last stages):
+// groups g = k0 * e + a_g with k0 in the rank's share of the n / (e * G) block groups
+inline YRange part_block_range(const Pass &p, int n, int part, int parts)
+{
+    const int e = 1 << p.s, K0 = n / (e << p.M);
+    YRange r;
+    r.y_off = (K0 / parts) * part * e;
+    r.y_cnt = (K0 / parts) * e;
+    return r;
+}
+
+// the pass that fuses the last m_last stages (one block group, k0 = 0): the rank's share of the angles a_g
+inline YRange part_angle_range(const Pass &p, int part, int parts)
+{
+    const int e = 1 << p.s;
+    YRange r;
+    r.y_off = (e / parts) * part;
+    r.y_cnt = e / parts;
+    return r;
 }
 
 }  // namespace plan

@@ -13,6 +13,7 @@ struct PassArgs {
     long long src_plane_stride, dst_plane_stride;  // elements between consecutive planes
     int planes;
     int x_off;              // first d-tile of this launch (streaming passes launch interior and boundary tiles separately)
+    int y_off;              // first group of this launch (angle-block sharding runs a rank's share of the groups)
     int q_first, q_count;   // image loader: plane -> (image = plane / q_count, quadrant = q_first + plane % q_count)
     int plane0;             // image loader: index of this launch's first plane in the batch (waves, see run_plan)
     int side_idx;           // host only: which helper stream (aux_stream) takes the boundary tiles of this launch

@@ -35,7 +35,7 @@ stream_kernel(const float *__restrict__ src, float *__restrict__ dst, PassArgs a
     c.n = a.n;
     c.D = a.D;
     c.e = a.e;
-    c.g = blockIdx.y;
+    c.g = blockIdx.y + a.y_off;
     c.k0 = c.g >> a.loge;
     c.a_g = c.g & (a.e - 1);
     c.d0 = (blockIdx.x + a.x_off) * Prog::TD;
@@ -112,7 +112,7 @@ stream_kernel_p(const float *__restrict__ src, float *__restrict__ dst, PassArgs
     iter.begin(sc, slot, tid);
     int plane, y, x, ready_plane = -1;
     while (iter.current(sc, slot, tid, plane, y, x)) {
-        c.g = y;
+        c.g = y + a.y_off;
         c.k0 = c.g >> a.loge;
         c.a_g = c.g & (a.e - 1);
         c.d0 = (x + a.x_off) * Prog::TD;

@@ -118,6 +118,27 @@ int    adrt_b200_adrt_bdrt_rows(const void *in, void *out, int64_t B, int64_t n,
                                 int q_first, int q_count, void *workspace, size_t workspace_bytes,
                                 void *stream);
 
+/* Angle-block sharding of ONE large image over `parts` (2, 4, 8) ranks per quadrant (SURVEY.md 8e row 2;
+ * the structure is that of adrt_core, adrt_cdefs_adrt.hpp:55-96: a stage only pairs rows of adjacent
+ * blocks that have the SAME incoming angle).  The last m_last stages (2^m_last >= parts) are one fused
+ * pass.  adrt_part phase 0 runs every earlier pass on the rank's own image-row blocks and writes the
+ * exchange buffer xbuf = (planes, 2^m_last blocks, n / 2^m_last angles, pitch) with the rows (blk, a) of
+ * its blocks; the ranks then exchange rows (the owner of block blk sends row (blk, a) to the owner of
+ * angle a: adrt_b200/_shard.py, one batched NCCL send/recv); phase 1 runs the last pass for the rank's
+ * angles and fills columns [part*n/parts, (part+1)*n/parts) of every (2n-1, n) plane of `sino`.
+ * bdrt_part is the mirror image: phase 0 reads those columns of `sino` and writes rows (blk, a) of the
+ * rank's angles, the exchange goes the other way, phase 1 fills the rank's columns of `out` (offsets
+ * d < rows only; rows = -1: all).  Results are bit-identical to adrt_b200_adrt / _bdrt.
+ * part_exchange_pitch: elements per xbuf row (forward != 0: adrt, else bdrt); 0 = unsupported shape. */
+size_t adrt_b200_part_exchange_pitch(int64_t n, int dtype, int m_last, int forward);
+size_t adrt_b200_part_workspace_bytes(int64_t planes, int64_t n, int dtype, int m_last);
+int    adrt_b200_adrt_part(const void *img, void *xbuf, void *sino, int64_t B, int64_t n, int dtype,
+                           int q_first, int q_count, int part, int parts, int m_last, int phase,
+                           void *workspace, size_t workspace_bytes, void *stream);
+int    adrt_b200_bdrt_part(const void *sino, void *xbuf, void *out, int64_t planes, int64_t n,
+                           int64_t rows, int dtype, int part, int parts, int m_last, int phase,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
 /* adrt.core.adrt_step / bdrt_step: adrt_cdefs_py.cpp:343-412, 550-619 ->
  * adrt_step (adrt_cdefs_adrt.hpp:215-258), bdrt_step (adrt_cdefs_bdrt.hpp:190-244).
  * 0 <= step < num_iters(n).  in/out (B,4,2n-1,n), must not alias. */

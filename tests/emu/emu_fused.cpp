@@ -18,6 +18,9 @@ using namespace adrt_b200;
 
 namespace {
 
+// groups (blockIdx.y range) the next pass runs: angle-block sharding runs a rank's share only
+int g_y_off = 0, g_y_cnt = -1;
+
 template <typename T, int M, int LOADK, int STOREK, bool kForward>
 void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int planes, long long sps, long long dps)
 {
@@ -30,8 +33,9 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
     // per-thread "registers" that live across the barriers of a step
     std::vector<T> regfile((size_t)tile::Geo<M>::NT * tile::NREG);
     const int e = 1 << p.s;
+    const int y_lo = g_y_cnt < 0 ? 0 : g_y_off, y_hi = g_y_cnt < 0 ? p.grid_y : g_y_off + g_y_cnt;
     for (int plane = 0; plane < planes; ++plane)
-        for (int by = 0; by < p.grid_y; ++by)
+        for (int by = y_lo; by < y_hi; ++by)
             for (int bx = 0; bx < p.grid_x; ++bx) {
                 tile::TileCtx c;
                 c.n = n; c.D = D; c.e = e; c.g = by; c.k0 = by / e; c.a_g = by % e;
@@ -74,8 +78,9 @@ void run_stream_pass(const plan::Pass &p, const float *src, float *dst, int n, i
     float *buf = reinterpret_cast<float *>(storeA.data());
     std::vector<typename Prog::State> states(Prog::NT);
     const int e = 1 << p.s;
+    const int y_lo = g_y_cnt < 0 ? 0 : g_y_off, y_hi = g_y_cnt < 0 ? p.grid_y : g_y_off + g_y_cnt;
     for (int plane = 0; plane < planes; ++plane)
-        for (int by = 0; by < p.grid_y; ++by)
+        for (int by = y_lo; by < y_hi; ++by)
             for (int bx = 0; bx < p.grid_x; ++bx) {
                 tile::TileCtx c;
                 c.n = n; c.D = D; c.e = e; c.g = by; c.k0 = by / e; c.a_g = by % e;
@@ -152,6 +157,25 @@ void run_kinds(const plan::Pass &p, const T *src, T *dst, int n, int D, int plan
 
 // rows_layout: forward stores / transposed loads the caller's array as R-layout rows (fused normal operator)
 template <typename T, bool kForward>
+int run_one_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int planes, long long sps, long long dps)
+{
+    if (p.stream) {
+        run_stream<T, kForward>(p, src, dst, n, D, planes, sps, dps);
+        return 0;
+    }
+    switch (p.M) {
+    case 1: run_kinds<T, 1, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+    case 2: run_kinds<T, 2, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+    case 3: run_kinds<T, 3, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+    case 4: run_kinds<T, 4, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+    case 5: run_kinds<T, 5, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+    case 6: run_kinds<T, 6, kForward>(p, src, dst, n, D, planes, sps, dps); break;
+    default: return 2;
+    }
+    return 0;
+}
+
+template <typename T, bool kForward>
 int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1, bool rows_layout = false)
 {
     plan::Plan pl;
@@ -172,19 +196,79 @@ int run(const T *in, T *out, int64_t B, int64_t n64, int64_t rows = -1, bool row
         else { src = slot[p.src_buf]; sps = (long long)n * p.in_pitch; }
         if (p.dst_buf < 0) { dst = out; dps = p.out_pitch ? (long long)n * p.out_pitch : sino; }
         else { dst = slot[p.dst_buf]; dps = (long long)n * p.out_pitch; }
-        if (p.stream) {
-            run_stream<T, kForward>(p, src, dst, n, D, planes, sps, dps);
-            continue;
+        if (run_one_pass<T, kForward>(p, src, dst, n, D, planes, sps, dps)) return 2;
+    }
+    return 0;
+}
+
+// ---- angle-block sharding (fused_plan.h part_*): `parts` ranks emulated one after the other ----------
+// Forward: every rank runs the head passes on its own blocks into its own copy of the exchange buffer
+// (NaN elsewhere), the exchange copies exactly the rows the protocol sends, the tail pass runs on the
+// rank's angle range and fills the rank's columns of `out`.  Transposed: the mirror image.
+template <typename T, bool kForward>
+int run_parts(const T *in, T *out, int64_t B, int64_t n64, int parts, int m_last, int64_t rows)
+{
+    plan::Plan pl;
+    const int K = plan::ilog2(n64);
+    const std::vector<int> ms = plan::part_split(K, sizeof(T), m_last);
+    if (ms.empty() || (1 << m_last) < parts) return 1;
+    const bool ok = kForward ? plan::make_forward_plan_split(n64, sizeof(T), ms, &pl)
+                             : plan::make_transposed_plan_split(n64, sizeof(T), ms, &pl, rows);
+    if (!ok) return 1;
+    const int n = pl.n, D = pl.D, planes = (int)B * 4, np = pl.npass;
+    const long long img = (long long)n * n, sino = (long long)D * n;
+    // the exchange buffer is the workspace between the head passes and the tail pass (forward) /
+    // between the first pass and the rest (transposed)
+    const int xi = kForward ? np - 2 : 0;                       // pass that WRITES the exchange buffer
+    const long long xpitch = pl.pass[xi].out_pitch;
+    const int e = 1 << (K - m_last), nblk = 1 << m_last;        // rows (blk, a): blk < nblk, a < e
+    const size_t xelems = (size_t)planes * n * xpitch;
+    std::vector<std::vector<T>> xbuf(parts, std::vector<T>(xelems, T(NAN)));
+    std::vector<T> ws0(pl.ws_slot_elems[0] * planes), ws1(pl.ws_slot_elems[1] * planes);
+    auto run_range = [&](int first, int last, int part, const T *src_in, T *dst_out) -> int {
+        // passes [first, last]; reads src_in at `first`, writes dst_out at `last`; slots in between
+        for (int i = first; i <= last; ++i) {
+            const plan::Pass &p = pl.pass[i];
+            const bool angle_pass = kForward ? (i == np - 1) : (i == 0);
+            const plan::YRange yr = angle_pass ? plan::part_angle_range(p, part, parts) : plan::part_block_range(p, n, part, parts);
+            g_y_off = yr.y_off; g_y_cnt = yr.y_cnt;
+            T *slot[2] = {ws0.data(), ws1.data()};
+            const T *src = i == first ? src_in : slot[p.src_buf];
+            T *dst = i == last ? dst_out : slot[p.dst_buf];
+            const long long sps = p.src_buf < 0 ? (kForward ? img : sino) : (long long)n * p.in_pitch;
+            const long long dps = p.dst_buf < 0 ? sino : (long long)n * p.out_pitch;
+            const int rc = run_one_pass<T, kForward>(p, src, dst, n, D, planes, sps, dps);
+            g_y_cnt = -1;
+            if (rc) return rc;
         }
-        switch (p.M) {
-        case 1: run_kinds<T, 1, kForward>(p, src, dst, n, D, planes, sps, dps); break;
-        case 2: run_kinds<T, 2, kForward>(p, src, dst, n, D, planes, sps, dps); break;
-        case 3: run_kinds<T, 3, kForward>(p, src, dst, n, D, planes, sps, dps); break;
-        case 4: run_kinds<T, 4, kForward>(p, src, dst, n, D, planes, sps, dps); break;
-        case 5: run_kinds<T, 5, kForward>(p, src, dst, n, D, planes, sps, dps); break;
-        case 6: run_kinds<T, 6, kForward>(p, src, dst, n, D, planes, sps, dps); break;
-        default: return 2;
+        return 0;
+    };
+    // phase 1
+    for (int part = 0; part < parts; ++part) {
+        std::fill(ws0.begin(), ws0.end(), T(NAN));
+        std::fill(ws1.begin(), ws1.end(), T(NAN));
+        if (run_range(0, xi, part, in, xbuf[part].data())) return 2;
+    }
+    // exchange: row (blk, a) of every plane goes from the rank that computed it to the rank that needs it
+    for (int dstp = 0; dstp < parts; ++dstp)
+        for (int srcp = 0; srcp < parts; ++srcp) {
+            if (srcp == dstp) continue;
+            for (int plane = 0; plane < planes; ++plane)
+                for (int blk = 0; blk < nblk; ++blk)
+                    for (int a = 0; a < e; ++a) {
+                        const int blk_owner = blk / (nblk / parts), ang_owner = a / (e / parts);
+                        // forward: computed by the block owner, needed by the angle owner; transposed: the reverse
+                        const int from = kForward ? blk_owner : ang_owner, to = kForward ? ang_owner : blk_owner;
+                        if (from != srcp || to != dstp) continue;
+                        const size_t off = ((size_t)plane * n + (size_t)blk * e + a) * xpitch;
+                        std::copy(xbuf[srcp].begin() + off, xbuf[srcp].begin() + off + xpitch, xbuf[dstp].begin() + off);
+                    }
         }
+    // phase 2
+    for (int part = 0; part < parts; ++part) {
+        std::fill(ws0.begin(), ws0.end(), T(NAN));
+        std::fill(ws1.begin(), ws1.end(), T(NAN));
+        if (run_range(xi + 1, np - 1, part, xbuf[part].data(), out)) return 3;
     }
     return 0;
 }
@@ -210,6 +294,11 @@ int emu_bdrt_f64(const double *in, double *out, int64_t B, int64_t n) { return r
 // only offsets d < rows of every output plane are produced
 int emu_bdrt_rows_f32(const float *in, float *out, int64_t B, int64_t n, int64_t rows) { return run<float, false>(in, out, B, n, rows); }
 int emu_bdrt_rows_f64(const double *in, double *out, int64_t B, int64_t n, int64_t rows) { return run<double, false>(in, out, B, n, rows); }
+// angle-block sharding over `parts` emulated ranks, last pass of m_last stages (rows < 0: all offsets)
+int emu_adrt_parts_f32(const float *in, float *out, int64_t B, int64_t n, int parts, int m_last) { return run_parts<float, true>(in, out, B, n, parts, m_last, -1); }
+int emu_adrt_parts_f64(const double *in, double *out, int64_t B, int64_t n, int parts, int m_last) { return run_parts<double, true>(in, out, B, n, parts, m_last, -1); }
+int emu_bdrt_parts_f32(const float *in, float *out, int64_t B, int64_t n, int parts, int m_last, int64_t rows) { return run_parts<float, false>(in, out, B, n, parts, m_last, rows); }
+int emu_bdrt_parts_f64(const double *in, double *out, int64_t B, int64_t n, int parts, int m_last, int64_t rows) { return run_parts<double, false>(in, out, B, n, parts, m_last, rows); }
 int emu_normal_f32(const float *in, float *mid, float *out, int64_t B, int64_t n, int64_t rows) { return run_normal<float>(in, mid, out, B, n, rows); }
 int emu_normal_f64(const double *in, double *mid, double *out, int64_t B, int64_t n, int64_t rows) { return run_normal<double>(in, mid, out, B, n, rows); }
 }

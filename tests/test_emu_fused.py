@@ -242,3 +242,30 @@ def test_normal_operator_rows_handoff(emu, n, dt):
 ])
 def test_normal_operator_rows_handoff_streaming(emu, n, split, stream_set):
     _check_normal(emu, n, np.float32, n, stream_set=stream_set, split=split)
+
+
+# ---------------------------------------------------------------------------------------------
+# Angle-block sharding of one image over several ranks (fused_plan.h part_*): every rank runs
+# the passes before the last one on its own image-row blocks, ONE exchange of workspace rows, then the last
+# pass on its own angle range (bdrt: the mirror image).  The emulator plays the ranks one after the other
+# with NaN-filled private buffers, so a row the protocol forgets to send shows up as NaN.
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,parts,m_last", [(16, 2, 1), (32, 2, 3), (64, 4, 2), (128, 2, 3), (256, 2, 1), (256, 4, 3), (512, 8, 3)])
+def test_angle_block_sharding(emu, n, parts, m_last, dt):
+    suffix = "f32" if dt == np.float32 else "f64"
+    x = make_image(41 + n, (1, n, n), dt)
+    y = np.full((1, 4, 2 * n - 1, n), np.nan, dtype=dt)
+    rc = getattr(emu, f"emu_adrt_parts_{suffix}")(ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(y.ctypes.data),
+                                                   ctypes.c_int64(1), ctypes.c_int64(n), ctypes.c_int(parts), ctypes.c_int(m_last))
+    assert rc == 0
+    want = O.adrt(x)
+    assert bytes_equal(y, want), f"sharded adrt n={n} parts={parts}: {first_diff(y, want)}"
+    s = make_sino(43 + n, want.shape, dt)
+    for rows in (2 * n - 1, n):
+        z = np.full(s.shape, np.nan, dtype=dt)
+        rc = getattr(emu, f"emu_bdrt_parts_{suffix}")(ctypes.c_void_p(s.ctypes.data), ctypes.c_void_p(z.ctypes.data),
+                                                       ctypes.c_int64(1), ctypes.c_int64(n), ctypes.c_int(parts), ctypes.c_int(m_last),
+                                                       ctypes.c_int64(rows))
+        assert rc == 0
+        wz = O.bdrt(s)
+        assert bytes_equal(z[:, :, :rows], wz[:, :, :rows]), f"sharded bdrt n={n} parts={parts} rows={rows}: {first_diff(z[:, :, :rows], wz[:, :, :rows])}"

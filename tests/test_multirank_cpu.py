@@ -93,7 +93,76 @@ def test_quadrant_owner_range():
     assert quadrant_owner_range(1, 0) == (0, 4)
     assert [quadrant_owner_range(2, r) for r in range(2)] == [(0, 2), (2, 2)]
     assert [quadrant_owner_range(4, r) for r in range(4)] == [(0, 1), (1, 1), (2, 1), (3, 1)]
-    assert [quadrant_owner_range(8, r)[1] for r in range(8)] == [1, 1, 1, 1, 0, 0, 0, 0]
+    # 8 ranks: 4 quadrants x 2 angle halves (every rank works)
+    assert [quadrant_owner_range(8, r) for r in range(8)] == [(0, 1), (0, 1), (1, 1), (1, 1), (2, 1), (2, 1), (3, 1), (3, 1)]
+    from adrt_b200._shard import image_layout, part_of
+
+    assert [part_of(8, r) for r in range(8)] == [(r % 2, 2) for r in range(8)]
+    assert image_layout(16) == (1, 4) and image_layout(2) == (2, 1)
+    # explicit group size: 2 ranks sharing every quadrant as two angle halves
+    assert image_layout(2, 2) == (4, 2) and quadrant_owner_range(2, 1, 2) == (0, 4) and part_of(2, 1, 2) == (1, 2)
+    assert image_layout(8, 4) == (2, 4) and quadrant_owner_range(8, 5, 4) == (2, 2)
+    with pytest.raises(ValueError, match="supports world sizes"):
+        image_layout(3)
+    with pytest.raises(ValueError, match="supports world sizes"):
+        quadrant_owner_range(6, 0)
+    with pytest.raises(ValueError, match="cannot split"):
+        image_layout(32, 2)
+
+
+def _worker_exchange(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from adrt_b200._shard import exchange_rows
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        planes, nblk, e, pitch = 2, 4, 6, 5
+        # every cell carries (plane, blk, a, x) encoded as a number; cells a rank does not own start as -1
+        full = (torch.arange(planes * nblk * e * pitch, dtype=torch.float64).reshape(planes, nblk, e, pitch))
+        bl = slice(rank * nblk // world, (rank + 1) * nblk // world)
+        an = slice(rank * e // world, (rank + 1) * e // world)
+        for forward in (True, False):
+            buf = torch.full_like(full, -1.0)
+            if forward:
+                buf[:, bl] = full[:, bl]          # all angles of my blocks
+            else:
+                buf[:, :, an] = full[:, :, an]    # all blocks of my angles
+            exchange_rows(buf, rank, world, 0, dist, forward)
+            want = torch.full_like(full, -1.0)
+            if forward:
+                want[:, bl] = full[:, bl]
+                want[:, :, an] = full[:, :, an]   # now also every block of my angles
+            else:
+                want[:, :, an] = full[:, :, an]
+                want[:, bl] = full[:, bl]         # now also every angle of my blocks
+            ok = ok and bool(torch.equal(buf, want))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_angle_block_exchange():
+    """The row exchange of angle-block sharding (adrt_b200/_shard.exchange_rows), world size 2 over gloo:
+    after it a rank holds every block of its angles (forward) / every angle of its blocks (transposed),
+    and nothing it was not sent."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_exchange, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), "exchange_rows left the wrong rows behind"
 
 
 def test_shard_bounds():

@@ -1,6 +1,8 @@
 """BASELINE config 5 style run: CG reconstruction of ONE large image with the normal
-operator sharded by quadrant over the ranks (torchrun, NCCL).  Prints ms per CG
-iteration (max over ranks) and checks the sharded result against the 1-GPU one.
+operator sharded over the ranks (torchrun, NCCL) -- by quadrant up to 4 ranks, by quadrant x
+angle block beyond (ADRT_B200_SHARD_PARTS forces the angle-block path on fewer ranks).  Prints ms
+per operator application and per CG iteration (max over ranks) and checks the sharded results
+against the 1-GPU ones bit for bit.
 usage: torchrun --nproc-per-node N tools/cg_sharded.py [n] [iters]"""
 import os
 import sys
@@ -41,9 +43,30 @@ if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 single = recipes.normal_operator(img)  # every rank can also do the whole thing alone
 same = bool(torch.equal(out.view(torch.int32), single.view(torch.int32)))
+# a fixed number of CG iterations on the normal equations (docs/examples.cginverse.md:40-67), sharded vs alone
+from adrt_b200._shard import image_layout  # noqa: E402
+
+
+def cg_fixed(its, dd):
+    try:
+        recipes.iadrt_cg(b, maxiter=its, rtol=1e-30, dist=dd)
+    except ValueError:      # "convergence failed": expected, the iteration count is the point
+        pass
+    torch.cuda.synchronize()
+
+
+cg_fixed(1, d)
+torch.cuda.synchronize()
 t0 = time.perf_counter()
-x, its = recipes.iadrt_cg(b, maxiter=iters, rtol=1e-30, dist=d, return_info=True) if False else (None, 0)
+cg_fixed(iters, d)
+cg_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / iters], device=dev, dtype=torch.float64)
+if world > 1:
+    dist.all_reduce(cg_ms, op=dist.ReduceOp.MAX)
+per, parts = image_layout(world)
 if rank == 0:
-    print({"n": n, "world": world, "normal_operator_ms": round(float(ms.item()), 3), "bit_identical_to_1gpu": same}, flush=True)
+    import json
+    print(json.dumps({"n": n, "world": world, "quadrants_per_group": per, "ranks_per_group": parts,
+                      "normal_operator_ms": round(float(ms.item()), 3), "cg_iteration_ms": round(float(cg_ms.item()), 3),
+                      "bit_identical_to_1gpu": same}), flush=True)
 if world > 1:
     dist.destroy_process_group()
