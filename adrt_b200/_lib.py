@@ -46,6 +46,7 @@ SIGNATURES = {
     "adrt_b200_adrt_bdrt_rows_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int]),
     "adrt_b200_adrt_bdrt_rows": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_vp, _c_sz, _c_vp]),
     "adrt_b200_part_exchange_pitch": (_c_sz, [_c_i64, _c_int, _c_int, _c_int]),
+    "adrt_b200_part_exchange_cols": (_c_sz, [_c_i64, _c_int, _c_int, _c_i64]),
     "adrt_b200_part_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_int, _c_int]),
     "adrt_b200_adrt_part": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_sz, _c_vp]),
     "adrt_b200_bdrt_part": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_sz, _c_vp]),

@@ -122,28 +122,43 @@ def truncate_quadrant(z, q: int):
     return orient_square(z[..., :n, :], q)
 
 
-def _local_quadrant_backprojections(x, q_first, q_count):
+def _local_rows(x, q_first, q_count, part, parts, base_rank, dist):
+    """The rank's share of ``bdrt(adrt(x))``: offsets ``d < n``, quadrants
+    ``q_first .. q_first+q_count-1``, columns ``[part*n/parts, (part+1)*n/parts)``:
+    ``(B, q_count, n, n/parts)`` for `x` ``(B, n, n)``."""
     from . import _adrt_cdefs as cd
 
     n = x.shape[-1]
+    if parts > 1:
+        return _part_backprojection(x, q_first, q_count, part, parts, base_rank, dist)
     if n < 2:
         z = cd.bdrt_planes(cd.adrt_quadrants(x, q_first, q_count), rows=n)
     else:
         z = cd.adrt_bdrt_rows(x, q_first, q_count)   # sinogram handed over as workspace rows
-    return [truncate_quadrant(z[..., i, :, :], q_first + i).contiguous() for i in range(q_count)]
+    return z[:, :, :n, :].contiguous()
 
 
-def exchange_rows(xbuf, part: int, parts: int, base_rank: int, dist, forward: bool) -> None:
+def _finish_mean(zfull):
+    """``mean_q(truncate(z))`` with the single-GPU kernel (NumPy's summation order)."""
+    from . import _adrt_cdefs as cd
+
+    return cd.truncate_mean(zfull, 1.0)
+
+
+def exchange_rows(xbuf, part: int, parts: int, base_rank: int, dist, forward: bool, cols=None) -> None:
     """The one data-path exchange of angle-block sharding, in place on `xbuf`
     ``(planes, blocks, angles, pitch)``.  Rank ``base_rank + p`` owns blocks
     ``[p*blocks/parts, (p+1)*blocks/parts)`` and angles ``[p*angles/parts, ...)``.
     forward (adrt): a rank holds all angles of its blocks and needs all blocks of its
-    angles; transposed (bdrt): the other way round.  One batched send/recv per peer."""
+    angles; transposed (bdrt): the other way round.  One batched send/recv per peer.
+    `cols`: only the first `cols` elements of every row travel (row-limited bdrt)."""
     import torch
 
     nblk, e = xbuf.shape[1], xbuf.shape[2]
     bl = lambda p: slice(p * nblk // parts, (p + 1) * nblk // parts)   # noqa: E731
     an = lambda p: slice(p * e // parts, (p + 1) * e // parts)         # noqa: E731
+    if cols is not None and cols < xbuf.shape[3]:
+        xbuf = xbuf[..., :cols]
     ops, recvs = [], []
     for p in range(parts):
         if p == part:
@@ -201,50 +216,50 @@ def _part_backprojection(x, q_first: int, q_count: int, part: int, parts: int, b
         out = torch.empty((planes, D, n), dtype=x.dtype, device=dev)
         bargs = (planes, n, n, code, part, parts, m_last)
         _lib.check(lib.adrt_b200_bdrt_part(sino.data_ptr(), xb.data_ptr(), None, *bargs, 0, ws.data_ptr(), nbytes, stream), "bdrt_part")
-        exchange(xb, part, parts, base_rank, dist, False)
+        exchange(xb, part, parts, base_rank, dist, False, int(lib.adrt_b200_part_exchange_cols(n, code, m_last, n)))
         _lib.check(lib.adrt_b200_bdrt_part(None, xb.data_ptr(), out.data_ptr(), *bargs, 1, ws.data_ptr(), nbytes, stream), "bdrt_part")
     cols = slice(part * n // parts, (part + 1) * n // parts)
     return out.view(B, q_count, D, n)[:, :, :n, cols].contiguous()
 
 
-def sharded_normal_operator(x, dist=None, *, local_fn=_local_quadrant_backprojections, parts=None):
+def sharded_normal_operator(x, dist=None, *, local_fn=_local_rows, finish_fn=_finish_mean, parts=None):
     """``mean_q(truncate(bdrt(adrt(x))))`` with ONE image (or batch) spread over the ranks
     of the default process group: by quadrant up to 4 ranks, by quadrant x angle block
     beyond (8 ranks = 4 quadrants x 2 angle halves).  `x` ``(n, n)`` or ``(B, n, n)`` must
     be replicated on every rank; the result is replicated too and bit-identical to the
-    single-GPU ``recipes.normal_operator``.  `local_fn(x, q_first, q_count)` returns a
-    rank's truncated back-projections in the quadrant-only mode (overridable so that CPU
-    tests can exercise the exchange with the oracle)."""
+    single-GPU ``recipes.normal_operator``: every rank back-projects its share, ONE
+    all-gather hands every rank all shares, and the quadrant mean is the same
+    ``truncate_mean`` kernel (same summation order) the single-GPU path runs.
+    `local_fn` / `finish_fn` are overridable so that CPU tests can exercise the exchanges
+    with the oracle."""
     import torch
 
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     per, parts = image_layout(world, parts)
     q_first, q_count = quadrant_owner_range(world, rank, parts)
-    if parts == 1:
-        mine = local_fn(x, q_first, q_count)
-        if world == 1:
-            parts_list = mine
-        else:
-            local = torch.stack(mine, dim=0)                     # (per, ..., n, n)
-            gathered = [torch.empty_like(local) for _ in range(world)]
-            dist.all_gather(gathered, local)
-            parts_list = [g[i] for g in gathered for i in range(per)]
-        t0, t1, t2, t3 = parts_list
-        return (((t0 + t1) + t2) + t3) / 4
+    part = rank % parts
     squeeze = x.ndim == 2
     xb = (x[None] if squeeze else x).contiguous()
-    part = rank % parts
-    piece = _part_backprojection(xb, q_first, q_count, part, parts, rank - part, dist)   # (B, per, n, n / parts)
-    gathered = [torch.empty_like(piece) for _ in range(world)]
-    dist.all_gather(gathered, piece)
-    quads = []
-    for q in range(4):
-        grp, i = divmod(q, per)
-        # offsets d < n of quadrant q, all columns: the pieces of the group's ranks side by side
-        square = torch.cat([gathered[grp * parts + p][:, i] for p in range(parts)], dim=-1)
-        quads.append(orient_square(square, q))
-    res = (((quads[0] + quads[1]) + quads[2]) + quads[3]) / 4
+    B, n = int(xb.shape[0]), int(xb.shape[-1])
+    w = n // parts
+    piece = local_fn(xb, q_first, q_count, part, parts, rank - part, dist)       # (B, per, n, w)
+    if world == 1:
+        flat = piece[None]
+    else:
+        flat = torch.empty((world, *piece.shape), dtype=piece.dtype, device=piece.device)
+        try:
+            dist.all_gather_into_tensor(flat, piece.contiguous())
+        except (RuntimeError, NotImplementedError):   # backends without the flat form
+            parts_list = [torch.empty_like(piece) for _ in range(world)]
+            dist.all_gather(parts_list, piece.contiguous())
+            flat = torch.stack(parts_list, dim=0)
+    # the rows truncate keeps, in the public sinogram layout (rows d >= n are never read)
+    zfull = torch.empty((B, 4, 2 * n - 1, n), dtype=piece.dtype, device=piece.device)
+    for r in range(world):
+        grp, p = divmod(r, parts)
+        zfull[:, grp * per:(grp + 1) * per, :n, p * w:(p + 1) * w] = flat[r]
+    res = finish_fn(zfull)
     return res[0] if squeeze else res
 
 

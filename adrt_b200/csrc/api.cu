@@ -589,6 +589,12 @@ size_t adrt_b200_part_exchange_pitch(int64_t n, int dtype, int m_last, int forwa
     return DISPATCH(dtype, part_exchange_pitch<float>(n, m_last, forward != 0), part_exchange_pitch<double>(n, m_last, forward != 0));
 }
 
+size_t adrt_b200_part_exchange_cols(int64_t n, int dtype, int m_last, int64_t rows)
+{
+    if (!is_pow2(n) || n > kMaxN || !dtype_ok(dtype) || m_last < 1 || m_last >= num_iters(n)) return 0;
+    return DISPATCH(dtype, part_exchange_cols<float>(n, m_last, rows), part_exchange_cols<double>(n, m_last, rows));
+}
+
 size_t adrt_b200_part_workspace_bytes(int64_t planes, int64_t n, int dtype, int m_last)
 {
     if (planes <= 0 || !is_pow2(n) || n > kMaxN || !dtype_ok(dtype) || m_last < 1 || m_last >= num_iters(n)) return 0;

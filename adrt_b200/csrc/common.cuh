@@ -84,6 +84,7 @@ template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, 
 // Angle-block sharding of single large images over `parts` ranks (fused_plan.h part_*).
 // phase 0 writes / phase 1 reads the exchange buffer `xbuf` (planes x n rows x part_exchange_pitch elements).
 template <typename T> size_t part_exchange_pitch(int64_t n, int m_last, bool forward);
+template <typename T> size_t part_exchange_cols(int64_t n, int m_last, int64_t rows);
 template <typename T> size_t part_workspace_elems(int64_t planes, int64_t n, int m_last);
 template <typename T> int fused_adrt_part(const T *img, T *xbuf, T *sino, int64_t B, int64_t n, int q_first, int q_count, int part, int parts, int m_last, int phase, T *ws, size_t ws_elems, cudaStream_t s);
 template <typename T> int fused_bdrt_part(const T *sino, T *xbuf, T *out, int64_t planes, int64_t n, int64_t rows, int part, int parts, int m_last, int phase, T *ws, size_t ws_elems, cudaStream_t s);

@@ -659,6 +659,17 @@ size_t part_exchange_pitch(int64_t n, int m_last, bool forward)
     return (size_t)pl.pass[forward ? pl.npass - 2 : 0].out_pitch;
 }
 
+// leading elements of every bdrt exchange row that the passes after the exchange read when only offsets
+// d < rows of the result are wanted (the rest of the row need not travel)
+template <typename T>
+size_t part_exchange_cols(int64_t n, int m_last, int64_t rows)
+{
+    plan::Plan pl;
+    if (!make_part_plan<T>(n, 2, m_last, false, rows, &pl)) return 0;
+    const long long pitch = pl.pass[0].out_pitch, need = plan::round4(pl.pass[0].d_need);
+    return (size_t)(need < pitch ? need : pitch);
+}
+
 template <typename T>
 size_t part_workspace_elems(int64_t planes, int64_t n, int m_last)
 {
@@ -695,6 +706,7 @@ int fused_bdrt_part(const T *sino, T *xbuf, T *out, int64_t planes, int64_t n, i
 
 #define INSTANTIATE(T)                                                      \
     template size_t part_exchange_pitch<T>(int64_t, int, bool);             \
+    template size_t part_exchange_cols<T>(int64_t, int, int64_t);           \
     template size_t part_workspace_elems<T>(int64_t, int64_t, int);         \
     template int fused_adrt_part<T>(const T *, T *, T *, int64_t, int64_t, int, int, int, int, int, int, T *, size_t, cudaStream_t); \
     template int fused_bdrt_part<T>(const T *, T *, T *, int64_t, int64_t, int64_t, int, int, int, int, T *, size_t, cudaStream_t); \

@@ -131,6 +131,9 @@ int    adrt_b200_adrt_bdrt_rows(const void *in, void *out, int64_t B, int64_t n,
  * d < rows only; rows = -1: all).  Results are bit-identical to adrt_b200_adrt / _bdrt.
  * part_exchange_pitch: elements per xbuf row (forward != 0: adrt, else bdrt); 0 = unsupported shape. */
 size_t adrt_b200_part_exchange_pitch(int64_t n, int dtype, int m_last, int forward);
+/* leading elements of every bdrt xbuf row that phase 1 reads when only offsets d < rows are wanted
+ * (rows = -1: all): the exchange need not move the rest of the row */
+size_t adrt_b200_part_exchange_cols(int64_t n, int dtype, int m_last, int64_t rows);
 size_t adrt_b200_part_workspace_bytes(int64_t planes, int64_t n, int dtype, int m_last);
 int    adrt_b200_adrt_part(const void *img, void *xbuf, void *sino, int64_t B, int64_t n, int dtype,
                            int q_first, int q_count, int part, int parts, int m_last, int phase,

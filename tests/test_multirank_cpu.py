@@ -49,23 +49,31 @@ def _worker_quadrants(rank, world, port, q):
     import torch
     import torch.distributed as dist
 
-    from adrt_b200._shard import quadrant_owner_range, sharded_normal_operator, truncate_quadrant
+    from adrt_b200._shard import quadrant_owner_range, sharded_normal_operator
     from oracle import oracle as O
 
-    def oracle_fn(x, q_first, q_count):
-        # CPU stand-in for adrt_quadrants + bdrt_planes: full oracle transform, keep our quadrants
+    def oracle_fn(x, q_first, q_count, part, parts, base_rank, dist_):
+        # CPU stand-in for the rank's share: full oracle transform, keep our quadrants / columns
+        n = x.shape[-1]
         z = torch.from_numpy(O.bdrt(O.adrt(x.numpy())))
-        return [truncate_quadrant(z[..., q_first + i, :, :], q_first + i).contiguous() for i in range(q_count)]
+        w = n // parts
+        return z[:, q_first:q_first + q_count, :n, part * w:(part + 1) * w].contiguous()
+
+    def oracle_finish(zfull):
+        t = O.truncate(zfull.numpy())
+        return torch.from_numpy((((t[:, 0] + t[:, 1]) + t[:, 2]) + t[:, 3]) / 4)
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         n = 16
         x = torch.from_numpy(np.random.default_rng(3).standard_normal((n, n)))
-        got = sharded_normal_operator(x, dist, local_fn=oracle_fn).numpy()
+        got = sharded_normal_operator(x, dist, local_fn=oracle_fn, finish_fn=oracle_finish).numpy()
+        # the same with the two ranks sharing every quadrant as angle halves (columns of the back-projection)
+        got2 = sharded_normal_operator(x, dist, local_fn=oracle_fn, finish_fn=oracle_finish, parts=2).numpy()
         y = O.bdrt(O.adrt(x.numpy()))
         t = O.truncate(y)
         want = (((t[0] + t[1]) + t[2]) + t[3]) / 4
-        q.put((rank, quadrant_owner_range(world, rank), got.tobytes() == want.tobytes()))
+        q.put((rank, quadrant_owner_range(world, rank), got.tobytes() == want.tobytes() and got2.tobytes() == want.tobytes()))
     finally:
         dist.destroy_process_group()
 
