@@ -65,6 +65,7 @@ SIGNATURES = {
     "adrt_b200_stitch": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
     "adrt_b200_unstitch": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, _c_vp]),
     "adrt_b200_truncate_mean": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_double, _c_int, _c_vp]),
+    "adrt_b200_truncate_mean_shares": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, ctypes.c_double, _c_int, _c_vp]),
     "adrt_b200_sub": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "adrt_b200_add": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "adrt_b200_host_adrt": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int]),

@@ -254,6 +254,18 @@ def sharded_normal_operator(x, dist=None, *, local_fn=_local_rows, finish_fn=_fi
             parts_list = [torch.empty_like(piece) for _ in range(world)]
             dist.all_gather(parts_list, piece.contiguous())
             flat = torch.stack(parts_list, dim=0)
+    if finish_fn is _finish_mean and flat.is_cuda and w >= 32 and flat.dtype in (torch.float32, torch.float64):
+        # the quadrant mean reads the gathered shares where they lie (no reassembly pass)
+        from . import _lib
+
+        lib = _lib.load()
+        res = torch.empty((B, n, n), dtype=flat.dtype, device=flat.device)
+        with torch.cuda.device(flat.device):
+            rc = lib.adrt_b200_truncate_mean_shares(flat.data_ptr(), res.data_ptr(), B, n, per, parts, 1.0,
+                                                    _lib.F32 if flat.dtype == torch.float32 else _lib.F64,
+                                                    torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "truncate_mean_shares")
+        return res[0] if squeeze else res
     # the rows truncate keeps, in the public sinogram layout (rows d >= n are never read)
     zfull = torch.empty((B, 4, 2 * n - 1, n), dtype=piece.dtype, device=piece.device)
     for r in range(world):

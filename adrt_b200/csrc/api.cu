@@ -772,6 +772,17 @@ int adrt_b200_truncate_mean(const void *in, void *out, int64_t B, int64_t n, dou
                     launch_truncate_mean<double>((const double *)in, (double *)out, B, n, divisor, as_stream(stream)));
 }
 
+int adrt_b200_truncate_mean_shares(const void *in, void *out, int64_t B, int64_t n, int per, int parts, double divisor, int dtype,
+                                   void *stream)
+{
+    ADRT_REQUIRE(in && out && in != out && dtype_ok(dtype) && B > 0 && is_pow2(n) && n <= kMaxN, "bad argument");
+    ADRT_REQUIRE((per == 1 || per == 2 || per == 4) && parts >= 1 && (parts & (parts - 1)) == 0 && n / parts >= 32,
+                 "bad share layout: per=%d parts=%d n=%lld (needs n / parts >= 32)", per, parts, (long long)n);
+    return DISPATCH(dtype,
+                    launch_truncate_mean_shares<float>((const float *)in, (float *)out, B, n, per, parts, (float)divisor, as_stream(stream)),
+                    launch_truncate_mean_shares<double>((const double *)in, (double *)out, B, n, per, parts, divisor, as_stream(stream)));
+}
+
 int adrt_b200_sub(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream)
 {
     ADRT_REQUIRE(a && b && out && dtype_ok(dtype) && count > 0, "bad argument");

@@ -67,6 +67,7 @@ template <typename T> int launch_fmg_highpass(const T *in, T *out, int64_t B, in
 template <typename T> int launch_interp_to_cart(const T *in, T *out, const float *t, const int32_t *base, const float *h_base, const float *cosv, const int32_t *sgn, const T *factor, int64_t B, int64_t n, cudaStream_t s);
 template <typename T> int launch_truncate(const T *in, T *out, int64_t B, int64_t n, cudaStream_t s);
 template <typename T> int launch_truncate_mean(const T *in, T *out, int64_t B, int64_t n, T divisor, cudaStream_t s);
+template <typename T> int launch_truncate_mean_shares(const T *in, T *out, int64_t B, int64_t n, int per, int parts, T divisor, cudaStream_t s);
 template <typename T> int launch_stitch(const T *in, T *out, int64_t B, int64_t n, bool remove_repeated, cudaStream_t s);
 template <typename T> int launch_unstitch(const T *in, T *out, int64_t B, int64_t n, bool trimmed, cudaStream_t s);
 template <typename T> int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStream_t s);

@@ -455,16 +455,33 @@ truncate_mean_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, i
 
 // n >= 32: 32 x 32 output tiles; the two transposed quadrants (0 and 3) go through
 // shared memory so that every global access runs along the contiguous axis.
-template <typename T>
+// kShares: the input is not a (B, 4, 2n-1, n) sinogram but the all-gathered shares of a sharded
+// back-projection (adrt_b200/_shard.py): rank r = group * parts + p contributes (B, per, n, w) --
+// offsets d < n, columns [p*w, (p+1)*w), w = n / parts, of the group's `per` quadrants -- and the
+// shares lie rank-major: element (b, q, d, k) sits at ((r*B + b)*per + q % per)*n*w + d*w + k % w with
+// r = (q / per)*parts + k / w.
+struct ShareLayout {
+    int per, parts, logw;
+};
+
+template <typename T, bool kShares>
+__device__ __forceinline__ int64_t tm_addr(int64_t b, int64_t B, int q, int64_t d, int k, int n, int64_t D, const ShareLayout &L)
+{
+    if (!kShares) return ((b * 4 + q) * D + d) * n + k;
+    const int w = 1 << L.logw;
+    const int64_t r = (int64_t)(q / L.per) * L.parts + (k >> L.logw);
+    return (((r * B + b) * L.per + q % L.per) * n + d) * w + (k & (w - 1));
+}
+
+template <typename T, bool kShares>
 __global__ void __launch_bounds__(256)
-truncate_mean_tiled_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int n, T divisor)
+truncate_mean_tiled_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t B, int n, T divisor, ShareLayout L)
 {
     __shared__ T s0[32][33], s3[32][33];
     const int64_t D = 2 * (int64_t)n - 1;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int64_t b = blockIdx.z; b < B; b += gridDim.z) {
-        const T *I = in + b * 4 * D * n;
         // s0[i][j] = a0[n-1-(c0+i), r0+j] = T0[r0+j, c0+i];  s3[i][j] = a3[n-1-(c0+i), n-1-(r0+j)] = T3[r0+j, c0+i]
         // all sixteen loads of a thread are issued before anything waits on them
         T a0[4], a3[4], a1[4], a2[4];
@@ -472,11 +489,11 @@ truncate_mean_tiled_kernel(const T *__restrict__ in, T *__restrict__ out, int64_
         for (int m = 0; m < 4; ++m) {
             const int i = ty + 8 * m;
             const int64_t d = n - 1 - (c0 + i);
-            a0[m] = I[(0 * D + d) * n + (r0 + tx)];
-            a3[m] = I[(3 * D + d) * n + (n - 1 - (r0 + tx))];
+            a0[m] = in[tm_addr<T, kShares>(b, B, 0, d, r0 + tx, n, D, L)];
+            a3[m] = in[tm_addr<T, kShares>(b, B, 3, d, n - 1 - (r0 + tx), n, D, L)];
             const int r = r0 + i;
-            a1[m] = I[(1 * D + (n - 1 - r)) * n + c0 + tx];
-            a2[m] = I[(2 * D + r) * n + c0 + tx];
+            a1[m] = in[tm_addr<T, kShares>(b, B, 1, n - 1 - r, c0 + tx, n, D, L)];
+            a2[m] = in[tm_addr<T, kShares>(b, B, 2, r, c0 + tx, n, D, L)];
         }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
@@ -713,10 +730,20 @@ int launch_truncate_mean(const T *in, T *out, int64_t B, int64_t n, T divisor, c
 {
     if (n >= 32) {
         dim3 grid((unsigned)(n / 32), (unsigned)(n / 32), (unsigned)(B < 65535 ? B : 65535));
-        truncate_mean_tiled_kernel<T><<<grid, 256, 0, s>>>(in, out, B, (int)n, divisor);
+        truncate_mean_tiled_kernel<T, false><<<grid, 256, 0, s>>>(in, out, B, (int)n, divisor, ShareLayout{4, 1, 0});
     } else {
         truncate_mean_kernel<T><<<plane_grid(n * n, B), kThreads, 0, s>>>(in, out, B, (int)n, ilog2(n), divisor);
     }
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+// quadrant mean straight from the all-gathered shares of a sharded back-projection (see ShareLayout)
+template <typename T>
+int launch_truncate_mean_shares(const T *in, T *out, int64_t B, int64_t n, int per, int parts, T divisor, cudaStream_t s)
+{
+    dim3 grid((unsigned)(n / 32), (unsigned)(n / 32), (unsigned)(B < 65535 ? B : 65535));
+    truncate_mean_tiled_kernel<T, true><<<grid, 256, 0, s>>>(in, out, B, (int)n, divisor, ShareLayout{per, parts, ilog2(n / parts)});
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
 }
@@ -753,6 +780,7 @@ int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStr
     template int launch_interp_to_cart<T>(const T *, T *, const float *, const int32_t *, const float *, const float *, const int32_t *, const T *, int64_t, int64_t, cudaStream_t); \
     template int launch_truncate<T>(const T *, T *, int64_t, int64_t, cudaStream_t);                   \
     template int launch_truncate_mean<T>(const T *, T *, int64_t, int64_t, T, cudaStream_t);           \
+    template int launch_truncate_mean_shares<T>(const T *, T *, int64_t, int64_t, int, int, T, cudaStream_t); \
     template int launch_stitch<T>(const T *, T *, int64_t, int64_t, bool, cudaStream_t);               \
     template int launch_unstitch<T>(const T *, T *, int64_t, int64_t, bool, cudaStream_t);             \
     template int launch_binary<T>(const T *, const T *, T *, int64_t, int, cudaStream_t);

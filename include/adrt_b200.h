@@ -204,6 +204,13 @@ int    adrt_b200_unstitch(const void *in, void *out, int64_t B, int64_t n, int t
                           int dtype, void *stream);
 int    adrt_b200_truncate_mean(const void *in, void *out, int64_t B, int64_t n, double divisor,
                                int dtype, void *stream);
+/* truncate_mean over the all-gathered shares of a sharded back-projection (single image over several
+ * GPUs, adrt_b200/_shard.py): rank r = group * parts + p contributed (B, per, n, n/parts) -- offsets
+ * d < n, columns [p*n/parts, (p+1)*n/parts) of its group's `per` quadrants -- and `in` holds the
+ * shares rank-major: (4 / per * parts, B, per, n, n / parts).  Same arithmetic and order as
+ * truncate_mean; n / parts >= 32. */
+int    adrt_b200_truncate_mean_shares(const void *in, void *out, int64_t B, int64_t n, int per, int parts,
+                                      double divisor, int dtype, void *stream);
 int    adrt_b200_sub(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream);
 int    adrt_b200_add(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream);
 
