@@ -1,0 +1,210 @@
+// Fused multi-stage passes of the exact inverse (adrt.iadrt) -- warp-level algorithm.
+//
+// Plain C++ that compiles as CUDA device code (iadrt_fused.cu) and as host code
+// (tests/emu/emu_fused.cpp plays the 32 lanes of a warp phase by phase), like fused_tile.h.
+//
+// ---------------------------------------------------------------------------
+// The maths (reference adrt_cdefs_iadrt.hpp:52-105).  Stage s (C_in = n >> s
+// columns per block, C = C_in / 2, L = 2^(s+1) blocks) in the public (d, column) layout: output
+// column (l, col), l < L, col < C, reads the input columns A = (l >> 1, 2 col) and A1 = (l >> 1, 2 col + 1):
+//
+//   l even:  delta[d] = (0 + A[d]) - A1[d + 1]                      (second term if d + 1 < D)
+//   l odd:   delta[d] = (0 + A1[d + 1 + col]) - A[d + 1 + col]      (0 if d + 1 + col >= D)
+//   out[d]   = delta[d] + out[d + 1]                                 (no add at d = D - 1)
+//
+// i.e. a serial suffix scan along d (the reference's "must be serial" loop) of a difference of two
+// input columns.  One kernel per stage moves the sinogram through HBM 2 K times.
+//
+// Fusing m stages s0 .. s0+m-1 (G = 2^m): the G adjacent input columns (l', c0 G + j), j < G, produce
+// the G output columns (l' G + lambda, c0), lambda < G.  At inner level t (0 = inputs, m = outputs) the
+// nodes are (lambda_t < 2^t, j_t < 2^(m-t)) = column (l' 2^t + lambda_t, c0 2^(m-t) + j_t); G nodes per
+// level -> one lane each, k = lambda_t 2^(m-t) + j_t.  The odd-branch shift 1 + col has the large part
+// c0 2^(m-t) in common for the whole group.  Pre-shifted frames remove it: node (t, lambda_t) is
+// handled in the coordinate
+//
+//       x = d + psi,   psi = c0 2^(m-t) lambda_t
+//
+// and then a level-t node at x reads its parents (level t-1, lanes kA = (lambda_t >> 1) 2^(m-t+1) + 2 j_t
+// and kA + 1) at x and x + 1 (even lambda_t) or at x + 1 + j_t (odd lambda_t): look-ahead <= 2^(m-t).
+// The scans run downwards in d, hence downwards in x, so everything a node needs was produced a few
+// rows earlier: a warp sweeps x from the top, every lane scanning its node of every level, the
+// levels one row apart (level t works on row X + t while level t-1 works on X + t - 1), the last
+// rows of every level in a small shared-memory ring.  Each element costs exactly the reference's
+// operations in the reference's order; only the iteration space is re-indexed, so results are
+// bit-identical (signed zeros included: "0 + a" is kept).
+//
+// Layouts: the first pass reads the public layout (rows coalesced across the lanes' adjacent columns),
+// the last pass writes it (its psi is 0: C_out = 1 means c0 = 0).  Between passes the data lives in a
+// column-major workspace W[column][2n] (2n - 1 offsets + 1 pad: rows 16-byte aligned): a lane streams
+// its own column with 16-byte vectors, four offsets per access, in phase with all other lanes.
+#pragma once
+
+#include "fused_tile.h"
+
+namespace adrt_b200 {
+namespace itile {
+
+constexpr int kLanes = 32;
+
+ADRT_HD constexpr int pow2_ceil(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <int M> struct Geo {
+    static_assert(M >= 1 && M <= 5, "a team is at most one warp");
+    static constexpr int G = 1 << M;              // lanes per team
+    static constexpr int TEAMS = kLanes / G;      // teams per warp
+    // rows of level t (t < M) that are live at once: the reader (level t+1) looks ahead 2^(M-1-t) + 1 rows;
+    // level 0 is committed four rows at a time, three rows early
+    ADRT_HD static constexpr int depth(int t) { return pow2_ceil((1 << (M - 1 - t)) + 2 + (t == 0 ? 3 : 0)); }
+    ADRT_HD static constexpr int base(int t) { return t == 0 ? 0 : base(t - 1) + depth(t - 1); }
+    static constexpr int OUT_DEPTH = 8;           // level-M ring (workspace stores): one aligned group + skew
+    static constexpr int OUT_BASE = base(M);
+    static constexpr int ROWS = OUT_BASE + OUT_DEPTH;   // ring rows per warp (x 32 lanes)
+};
+
+// Everything a lane needs to know about its team's group.
+struct Team {
+    int n, D;          // image side, 2n - 1
+    int c0;            // group index inside its block
+    long long in_col;  // first input column of the group (public layout: column index; workspace: row index)
+    long long out_col; // output column of lambda = 0 (public layout) / workspace row of lambda = 0
+    long long out_stride;  // distance between the output columns / rows of consecutive lambda
+    bool active;       // false: padding team (more teams in the warp than groups left)
+};
+
+// per-lane registers that live across iterations
+template <typename T, int M> struct LaneState {
+    T prev[M + 1];     // running scan value of the lane's node at level t (index t, 1..M)
+    T v[4];            // four input rows fetched for the next trip
+};
+
+template <typename T>
+ADRT_HD T *ring_cell(T *ring, int row_base, int depth, int x, int lane)
+{
+    return ring + (long long)(row_base + (x & (depth - 1))) * kLanes + lane;
+}
+
+// ---- input side ---------------------------------------------------------------------------------
+// Rows X0-3 .. X0 (X0 = 3 mod 4) of the lane's input column, to be committed at the start of the trip
+// with base rows X0 .. X0-3.  kInQ: public layout in[d][col] (pitch n), else workspace W[col][2n].
+template <typename T, bool kInQ>
+ADRT_HD void fetch_inputs(const T *in_plane, const Team &tm, int k, int X0, T (&v)[4])
+{
+    if (!tm.active || X0 < 0 || X0 - 3 >= tm.D) return;
+    if (kInQ) {
+        const T *p = in_plane + tm.in_col + k;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int x = X0 - 3 + e;
+            if (x < tm.D) v[e] = p[(long long)x * tm.n];
+        }
+    } else {
+        // aligned 16-byte group(s) of the padded row; the pad cell (offset 2n - 1) is loaded and never used
+        const T *p = in_plane + (tm.in_col + k) * (long long)(2 * tm.n) + (X0 - 3);
+        constexpr int L = tile::VecOf<T>::L;
+#pragma unroll
+        for (int g = 0; g < 4 / L; ++g) {
+            const tile::Pack<T> w = *reinterpret_cast<const tile::Pack<T> *>(p + g * L);
+#pragma unroll
+            for (int i = 0; i < L; ++i) v[g * L + i] = w.v[i];
+        }
+    }
+}
+
+template <typename T, int M>
+ADRT_HD void commit_inputs(T *ring, const Team &tm, int lane, int X0, const T (&v)[4])
+{
+    if (!tm.active || X0 < 0 || X0 - 3 >= tm.D) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int x = X0 - 3 + e;
+        if (x < tm.D) *ring_cell(ring, Geo<M>::base(0), Geo<M>::depth(0), x, lane) = v[e];
+    }
+}
+
+// ---- one level of one base row ---------------------------------------------------------------------
+// Level t (1..M) for the lane's node at row x = X + t.  Returns true and sets `val` when the node's
+// offset d = x - psi lies in [0, D).
+template <typename T, int M, int t>
+ADRT_HD bool level_step(const T *ring, const Team &tm, int team_lane0, int k, int X, T &prev, T &val, int &d_out)
+{
+    constexpr int sh = M - t;
+    const int lam = k >> sh, j = k & ((1 << sh) - 1);
+    const int psi = (tm.c0 << sh) * lam;
+    const int x = X + t, d = x - psi;
+    d_out = d;
+    if (!tm.active || d < 0 || d >= tm.D) return false;
+    const int kA = ((lam >> 1) << (sh + 1)) + 2 * j + team_lane0;
+    constexpr int rb = Geo<M>::base(t - 1), dp = Geo<M>::depth(t - 1);
+    T acc = T(0);
+    if ((lam & 1) == 0) {
+        acc += *ring_cell(ring, rb, dp, x, kA);
+        if (d + 1 < tm.D) acc -= *ring_cell(ring, rb, dp, x + 1, kA + 1);
+    } else {
+        const int col = (tm.c0 << sh) + j;
+        if (d + 1 + col < tm.D) {
+            const int xp = x + 1 + j;
+            acc += *ring_cell(ring, rb, dp, xp, kA + 1);
+            acc -= *ring_cell(ring, rb, dp, xp, kA);
+        }
+    }
+    if (d + 1 < tm.D) acc += prev;
+    prev = acc;
+    val = acc;
+    return true;
+}
+
+// all levels of base row X for one lane; kOutQ: the last level is stored straight to the public layout
+template <typename T, int M, bool kOutQ, int t = 1>
+ADRT_HD void all_levels(T *ring, const Team &tm, int team_lane0, int k, int lane, int X, LaneState<T, M> &st, T *out_plane)
+{
+    if constexpr (t <= M) {
+        T val;
+        int d;
+        const bool ok = level_step<T, M, t>(ring, tm, team_lane0, k, X, st.prev[t], val, d);
+        if (ok) {
+            if constexpr (t < M) {
+                *ring_cell(ring, Geo<M>::base(t), Geo<M>::depth(t), X + t, lane) = val;
+            } else if constexpr (kOutQ) {
+                // last pass: c0 = 0, every lane is at the same offset d: one coalesced row piece
+                out_plane[(long long)d * tm.n + tm.out_col + k] = val;
+            } else {
+                *ring_cell(ring, Geo<M>::OUT_BASE, Geo<M>::OUT_DEPTH, X + t, lane) = val;
+            }
+        }
+        all_levels<T, M, kOutQ, t + 1>(ring, tm, team_lane0, k, lane, X, st, out_plane);
+    }
+}
+
+// ---- workspace stores -------------------------------------------------------------------------------
+// After the trip with base rows X0 .. X0-3 the lane's output column is complete down to offset
+// X0 - 3 + M - psi: flush the one aligned group of four offsets that became complete in this trip.
+template <typename T, int M>
+ADRT_HD void flush_outputs(const T *ring, const Team &tm, int k, int lane, int X0, T *out_plane)
+{
+    if (!tm.active) return;
+    const int psi = tm.c0 * k;
+    const int lo = X0 - 3 + M - psi;           // lowest offset computed so far
+    const int d0 = (lo + 3) & ~3;              // lowest complete aligned group
+    if (d0 < 0 || d0 >= 2 * tm.n) return;
+    T w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[e] = *ring_cell(ring, Geo<M>::OUT_BASE, Geo<M>::OUT_DEPTH, d0 + e + psi, lane);
+    T *p = out_plane + (tm.out_col + (long long)k * tm.out_stride) * (long long)(2 * tm.n) + d0;
+    constexpr int L = tile::VecOf<T>::L;
+#pragma unroll
+    for (int g = 0; g < 4 / L; ++g) tile::store_cv<T>(p + g * L, &w[g * L]);
+}
+
+// Sweep bounds of a warp: base rows from x_top (= 3 mod 4) down to x_end (inclusive, multiple of 4 trips).
+ADRT_HD int sweep_top(int D, int psi_max)
+{
+    return ((D - 1 + psi_max) | 3);
+}
+
+}  // namespace itile
+}  // namespace adrt_b200
