@@ -662,7 +662,10 @@ int adrt_b200_adrt_init(const void *in, void *out, int64_t B, int64_t n, int dty
 size_t adrt_b200_iadrt_workspace_bytes(int64_t B, int64_t n, int dtype)
 {
     if (B <= 0 || !is_pow2(n) || !dtype_ok(dtype)) return 0;
-    return num_iters(n) <= 1 ? 0 : (size_t)sino_elems(B, n) * dtype_size(dtype);
+    // enough for either path: per-stage ping-pong (one sinogram) or the fused passes' column-major buffers
+    const size_t steps = num_iters(n) <= 1 ? 0 : (size_t)sino_elems(B, n);
+    const size_t fused = n > kMaxN ? 0 : DISPATCH(dtype, fused_iadrt_workspace_elems<float>(B, n), fused_iadrt_workspace_elems<double>(B, n));
+    return (steps > fused ? steps : fused) * dtype_size(dtype);
 }
 
 int adrt_b200_iadrt(const void *in, void *out, int64_t B, int64_t n, int dtype, void *ws, size_t ws_bytes, void *stream)
@@ -674,6 +677,12 @@ int adrt_b200_iadrt(const void *in, void *out, int64_t B, int64_t n, int dtype, 
         set_error("iadrt workspace too small: need %zu bytes, got %zu", need, ws_bytes);
         return ADRT_B200_EWORKSPACE;
     }
+    // fused multi-stage passes (iadrt_fused.cu) need 16-byte aligned workspace rows; mode 1 and
+    // misaligned workspaces take the one-kernel-per-stage path
+    if (g_mode.load() == 0 && num_iters(n) >= 1 && reinterpret_cast<uintptr_t>(ws) % 16 == 0)
+        return DISPATCH(dtype,
+                        fused_iadrt<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes / 4, as_stream(stream)),
+                        fused_iadrt<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes / 8, as_stream(stream)));
     return DISPATCH(dtype,
                     iadrt_by_stages<float>((const float *)in, (float *)out, B, n, (float *)ws, as_stream(stream)),
                     iadrt_by_stages<double>((const double *)in, (double *)out, B, n, (double *)ws, as_stream(stream)));

@@ -82,6 +82,10 @@ template <typename T> size_t fused_bdrt_workspace_elems(int64_t B, int64_t n, in
 template <typename T> int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems, cudaStream_t s, bool *handled, bool rows_out = false);
 template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems, cudaStream_t s, bool *handled, bool rows_in = false);
 
+// adrt.iadrt as fused multi-stage passes (iadrt_fused.cu); workspace in elements
+template <typename T> size_t fused_iadrt_workspace_elems(int64_t B, int64_t n);
+template <typename T> int fused_iadrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s);
+
 // Angle-block sharding of single large images over `parts` ranks (fused_plan.h part_*).
 // phase 0 writes / phase 1 reads the exchange buffer `xbuf` (planes x n rows x part_exchange_pitch elements).
 template <typename T> size_t part_exchange_pitch(int64_t n, int m_last, bool forward);

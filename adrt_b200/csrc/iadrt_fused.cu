@@ -1,0 +1,130 @@
+// adrt.iadrt as fused multi-stage passes (iadrt_tile.h): one warp sweeps a group of up to 32 columns
+// through up to 5 stages at once, so the sinogram crosses HBM once per pass (3 passes for n = 2048)
+// instead of once per stage (11).  Reference: adrt_cdefs_iadrt.hpp:52-176.
+#include "common.cuh"
+#include "iadrt_tile.h"
+
+namespace adrt_b200 {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+template <typename T, int M, bool kInQ, bool kOutQ>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int s0)
+{
+    using G = itile::Geo<M>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *ring = reinterpret_cast<T *>(smem_raw) + (size_t)warp * G::ROWS * itile::kLanes;
+    const int team = lane / G::G, k = lane % G::G, team_lane0 = team * G::G;
+    const int tp0 = (blockIdx.x * kWarpsPerBlock + warp) * G::TEAMS;
+    const itile::Team tm = itile::make_team<M>(n, s0, tp0 + team);
+    // the warp's first team has the largest c0, i.e. the longest sweep
+    const itile::Team t0 = itile::make_team<M>(n, s0, tp0);
+    if (!t0.active) return;
+    const int top = itile::sweep_top(tm.D, t0.c0 * (G::G - 1));
+    const long long in_plane = kInQ ? (long long)tm.D * n : (long long)n * 2 * n;
+    const long long out_plane = kOutQ ? (long long)tm.D * n : (long long)n * 2 * n;
+    for (int64_t plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const T *ip = in + plane * in_plane;
+        T *op = out + plane * out_plane;
+        itile::LaneState<T, M> st;
+#pragma unroll
+        for (int t = 0; t <= M; ++t) st.prev[t] = T(0);
+        itile::fetch_inputs<T, kInQ>(ip, tm, k, top, st.v);
+        for (int X0 = top; X0 >= -M; X0 -= 4) {
+            itile::commit_inputs<T, M>(ring, tm, lane, X0, st.v);
+            itile::fetch_inputs<T, kInQ>(ip, tm, k, X0 - 4, st.v);
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                itile::all_levels<T, M, kOutQ>(ring, tm, team_lane0, k, lane, X0 - u, st, op);
+                __syncwarp();
+            }
+            if (!kOutQ) itile::flush_outputs<T, M>(ring, tm, k, lane, X0, op);
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T, int M, bool kInQ, bool kOutQ>
+int launch_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0, cudaStream_t s)
+{
+    using G = itile::Geo<M>;
+    const int teams = n >> M;                                       // per plane
+    const int warps = (teams + G::TEAMS - 1) / G::TEAMS;
+    const int blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const size_t smem = (size_t)kWarpsPerBlock * G::ROWS * itile::kLanes * sizeof(T);
+    auto kern = iadrt_pass_kernel<T, M, kInQ, kOutQ>;
+    ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)blocks, (unsigned)(planes < 65535 ? planes : 65535));
+    kern<<<grid, kWarpsPerBlock * 32, smem, s>>>(in, out, planes, n, s0);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T, bool kInQ, bool kOutQ>
+int dispatch_m(int M, const T *in, T *out, int64_t planes, int n, int s0, cudaStream_t s)
+{
+    switch (M) {
+    case 1: return launch_iadrt_pass<T, 1, kInQ, kOutQ>(in, out, planes, n, s0, s);
+    case 2: return launch_iadrt_pass<T, 2, kInQ, kOutQ>(in, out, planes, n, s0, s);
+    case 3: return launch_iadrt_pass<T, 3, kInQ, kOutQ>(in, out, planes, n, s0, s);
+    case 4: return launch_iadrt_pass<T, 4, kInQ, kOutQ>(in, out, planes, n, s0, s);
+    case 5: return launch_iadrt_pass<T, 5, kInQ, kOutQ>(in, out, planes, n, s0, s);
+    }
+    set_error("internal: bad iadrt stages per pass %d", M);
+    return ADRT_B200_EINVAL;
+}
+
+}  // namespace
+
+// workspace: one column-major buffer (planes x n x 2n) per intermediate, at most two
+template <typename T>
+size_t fused_iadrt_workspace_elems(int64_t B, int64_t n)
+{
+    const int K = num_iters(n);
+    if (K < 1 || n > kMaxN) return 0;
+    int ms[8];
+    const int np = itile::iadrt_split(K, ms);
+    const size_t w = (size_t)(B * 4) * (size_t)n * (size_t)(2 * n);
+    return np <= 1 ? 0 : (np == 2 ? w : 2 * w);
+}
+
+template <typename T>
+int fused_iadrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elems, cudaStream_t s)
+{
+    const int K = num_iters(n);
+    int ms[8];
+    const int np = itile::iadrt_split(K, ms);
+    const size_t need = fused_iadrt_workspace_elems<T>(B, n);
+    if (need > 0 && (!ws || ws_elems < need)) {
+        set_error("iadrt workspace too small: need %zu elements, got %zu", need, ws_elems);
+        return ADRT_B200_EWORKSPACE;
+    }
+    const int64_t planes = B * 4;
+    const size_t w = (size_t)planes * (size_t)n * (size_t)(2 * n);
+    T *wbuf[2] = {ws, ws + w};
+    const T *src = in;
+    int s0 = 0, rc = ADRT_B200_OK;
+    for (int i = 0; i < np && rc == ADRT_B200_OK; ++i) {
+        const bool first = i == 0, last = i == np - 1;
+        T *dst = last ? out : wbuf[i & 1];
+        if (first && last) rc = dispatch_m<T, true, true>(ms[i], src, dst, planes, (int)n, s0, s);
+        else if (first) rc = dispatch_m<T, true, false>(ms[i], src, dst, planes, (int)n, s0, s);
+        else if (last) rc = dispatch_m<T, false, true>(ms[i], src, dst, planes, (int)n, s0, s);
+        else rc = dispatch_m<T, false, false>(ms[i], src, dst, planes, (int)n, s0, s);
+        src = dst;
+        s0 += ms[i];
+    }
+    return rc;
+}
+
+template size_t fused_iadrt_workspace_elems<float>(int64_t, int64_t);
+template size_t fused_iadrt_workspace_elems<double>(int64_t, int64_t);
+template int fused_iadrt<float>(const float *, float *, int64_t, int64_t, float *, size_t, cudaStream_t);
+template int fused_iadrt<double>(const double *, double *, int64_t, int64_t, double *, size_t, cudaStream_t);
+
+}  // namespace adrt_b200

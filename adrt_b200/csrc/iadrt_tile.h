@@ -208,3 +208,56 @@ ADRT_HD int sweep_top(int D, int psi_max)
 
 }  // namespace itile
 }  // namespace adrt_b200
+
+// ---- pass / team bookkeeping shared by the CUDA driver and the host emulator -----------------------
+namespace adrt_b200 {
+namespace itile {
+
+// stages per pass: as even as possible with at most 5 per pass (a team is at most one warp);
+// ADRT_B200_IADRT_SPLIT="4,4,3" overrides
+inline int iadrt_split(int K, int *ms /* [8] */)
+{
+    if (const char *e = getenv("ADRT_B200_IADRT_SPLIT")) {
+        int cnt = 0, sum = 0;
+        bool ok = true;
+        for (const char *p = e; *p && cnt < 8;) {
+            const int v = (int)strtol(p, const_cast<char **>(&p), 10);
+            if (v < 1 || v > 5) ok = false;
+            ms[cnt++] = v;
+            sum += v;
+            if (*p == ',') ++p;
+        }
+        if (ok && sum == K && cnt <= 3) return cnt;
+    }
+    const int np = (K + 4) / 5;
+    int left = K;
+    for (int i = 0; i < np; ++i) {
+        const int m = (left + (np - i) - 1) / (np - i);
+        ms[i] = m;
+        left -= m;
+    }
+    return np;
+}
+
+// teams of one plane are numbered tp = 0 .. n/G - 1: heaviest groups (largest c0: longest sweep) first,
+// the 2^s0 blocks of one c0 next to each other (a warp's teams then sweep the same rows)
+template <int M>
+ADRT_HD Team make_team(int n, int s0, int tp)
+{
+    constexpr int G = Geo<M>::G;
+    Team tm;
+    tm.n = n;
+    tm.D = 2 * n - 1;
+    const int Cin0 = n >> s0, gpb = Cin0 / G, L0 = 1 << s0;
+    tm.active = tp < gpb * L0;
+    const int lp = tp & (L0 - 1);
+    tm.c0 = gpb - 1 - (tp >> s0);
+    if (!tm.active) tm.c0 = 0;
+    tm.in_col = (long long)lp * Cin0 + (long long)tm.c0 * G;
+    tm.out_col = (long long)lp * Cin0 + tm.c0;
+    tm.out_stride = Cin0 / G;
+    return tm;
+}
+
+}  // namespace itile
+}  // namespace adrt_b200

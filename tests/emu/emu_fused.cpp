@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../adrt_b200/csrc/fused_plan.h"
+#include "../../adrt_b200/csrc/iadrt_tile.h"
 
 using namespace adrt_b200;
 
@@ -282,9 +283,93 @@ int run_normal(const T *in, T *mid, T *out, int64_t B, int64_t n, int64_t rows)
     if (rc) return rc;
     return run<T, false>(mid, out, B, n, rows, true);
 }
+// ---- fused iadrt passes (iadrt_tile.h): the 32 lanes of every warp played phase by phase ------------
+template <typename T, int M, bool kInQ, bool kOutQ>
+void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
+{
+    using G = itile::Geo<M>;
+    const int teams = n >> M, warps = (teams + G::TEAMS - 1) / G::TEAMS;
+    const int D = 2 * n - 1;
+    const long long in_plane = kInQ ? (long long)D * n : (long long)n * 2 * n;
+    const long long out_plane = kOutQ ? (long long)D * n : (long long)n * 2 * n;
+    std::vector<T> ring((size_t)G::ROWS * itile::kLanes);
+    for (int64_t plane = 0; plane < planes; ++plane)
+        for (int w = 0; w < warps; ++w) {
+            const int tp0 = w * G::TEAMS;
+            const itile::Team t0 = itile::make_team<M>(n, s0, tp0);
+            if (!t0.active) continue;
+            const int top = itile::sweep_top(D, t0.c0 * (G::G - 1));
+            const T *ip = in + plane * in_plane;
+            T *op = out + plane * out_plane;
+            std::fill(ring.begin(), ring.end(), T(NAN));   // reads of never-written cells show up
+            itile::Team tm[32];
+            itile::LaneState<T, M> st[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                tm[lane] = itile::make_team<M>(n, s0, tp0 + lane / G::G);
+                for (int t = 0; t <= M; ++t) st[lane].prev[t] = T(0);
+                for (int e = 0; e < 4; ++e) st[lane].v[e] = T(NAN);
+                itile::fetch_inputs<T, kInQ>(ip, tm[lane], lane % G::G, top, st[lane].v);
+            }
+            for (int X0 = top; X0 >= -M; X0 -= 4) {
+                for (int i = 0; i < 32; ++i) {
+                    const int lane = g_order ? 31 - i : i;
+                    itile::commit_inputs<T, M>(ring.data(), tm[lane], lane, X0, st[lane].v);
+                    itile::fetch_inputs<T, kInQ>(ip, tm[lane], lane % G::G, X0 - 4, st[lane].v);
+                }
+                for (int u = 0; u < 4; ++u)
+                    for (int i = 0; i < 32; ++i) {
+                        const int lane = g_order ? 31 - i : i;
+                        itile::all_levels<T, M, kOutQ>(ring.data(), tm[lane], (lane / G::G) * G::G, lane % G::G, lane, X0 - u, st[lane], op);
+                    }
+                if (!kOutQ)
+                    for (int lane = 0; lane < 32; ++lane) itile::flush_outputs<T, M>(ring.data(), tm[lane], lane % G::G, lane, X0, op);
+            }
+        }
+}
+
+template <typename T, bool kInQ, bool kOutQ>
+void run_iadrt_m(int M, const T *in, T *out, int64_t planes, int n, int s0)
+{
+    switch (M) {
+    case 1: run_iadrt_pass<T, 1, kInQ, kOutQ>(in, out, planes, n, s0); break;
+    case 2: run_iadrt_pass<T, 2, kInQ, kOutQ>(in, out, planes, n, s0); break;
+    case 3: run_iadrt_pass<T, 3, kInQ, kOutQ>(in, out, planes, n, s0); break;
+    case 4: run_iadrt_pass<T, 4, kInQ, kOutQ>(in, out, planes, n, s0); break;
+    default: run_iadrt_pass<T, 5, kInQ, kOutQ>(in, out, planes, n, s0); break;
+    }
+}
+
+template <typename T>
+int run_iadrt(const T *in, T *out, int64_t B, int64_t n64)
+{
+    const int n = (int)n64, K = plan::ilog2(n64);
+    if (K < 1) return 1;
+    int ms[8];
+    const int np = itile::iadrt_split(K, ms);
+    const int64_t planes = B * 4;
+    const size_t w = (size_t)planes * n * 2 * n;
+    std::vector<T> w0(np > 1 ? w : 0, T(NAN)), w1(np > 2 ? w : 0, T(NAN));
+    T *wbuf[2] = {w0.data(), w1.data()};
+    const T *src = in;
+    int s0 = 0;
+    for (int i = 0; i < np; ++i) {
+        const bool first = i == 0, last = i == np - 1;
+        T *dst = last ? out : wbuf[i & 1];
+        if (first && last) run_iadrt_m<T, true, true>(ms[i], src, dst, planes, n, s0);
+        else if (first) run_iadrt_m<T, true, false>(ms[i], src, dst, planes, n, s0);
+        else if (last) run_iadrt_m<T, false, true>(ms[i], src, dst, planes, n, s0);
+        else run_iadrt_m<T, false, false>(ms[i], src, dst, planes, n, s0);
+        src = dst;
+        s0 += ms[i];
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
+int emu_iadrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run_iadrt<float>(in, out, B, n); }
+int emu_iadrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run_iadrt<double>(in, out, B, n); }
 void emu_set_order(int order) { g_order = order; }
 long long emu_stream_tiles(void) { return g_stream_tiles; }
 int emu_adrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, true>(in, out, B, n); }

@@ -20,7 +20,7 @@ SO = os.path.join(HERE, "emu", "_build", "libemu.so")
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [SRC] + [os.path.join(HERE, "..", "adrt_b200", "csrc", f) for f in ("fused_tile.h", "fused_plan.h", "stream_tile.h")]
+    deps = [SRC] + [os.path.join(HERE, "..", "adrt_b200", "csrc", f) for f in ("fused_tile.h", "fused_plan.h", "stream_tile.h", "iadrt_tile.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
@@ -269,3 +269,30 @@ def test_angle_block_sharding(emu, n, parts, m_last, dt):
         assert rc == 0
         wz = O.bdrt(s)
         assert bytes_equal(z[:, :, :rows], wz[:, :, :rows]), f"sharded bdrt n={n} parts={parts} rows={rows}: {first_diff(z[:, :, :rows], wz[:, :, :rows])}"
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused multi-stage iadrt passes (adrt_b200/csrc/iadrt_tile.h): warp-level sweeps in pre-shifted frames,
+# levels one row apart, rings in shared memory, column-major workspace between passes.  The emulator
+# plays the 32 lanes of every warp phase by phase (ascending and descending lane order).
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,split", [
+    (2, None), (4, None), (8, None), (16, None), (32, None),          # one pass of 1..5 stages
+    (8, "1,2"), (16, "2,2"), (32, "3,2"), (32, "1,1,3"), (64, "3,3"),  # workspace hand-off, 2 and 3 passes
+    (64, None), (128, None), (256, "4,4"), (256, "5,3"), (512, None), (1024, "5,5"),
+])
+def test_fused_iadrt(emu, n, split, dt):
+    os.environ.pop("ADRT_B200_IADRT_SPLIT", None)
+    if split:
+        os.environ["ADRT_B200_IADRT_SPLIT"] = split
+    try:
+        B = 2 if n <= 64 else 1
+        for s in (make_sino(29 + n, (B, 4, 2 * n - 1, n), dt), np.full((B, 4, 2 * n - 1, n), -0.0, dtype=dt)):
+            want = O.iadrt(s)
+            for order in (0, 1):
+                emu.emu_set_order(order)
+                got = _run(emu, "emu_iadrt", s, s.shape)
+                assert bytes_equal(got, want), f"iadrt n={n} split={split} order={order}: {first_diff(got, want)}"
+    finally:
+        emu.emu_set_order(0)
+        os.environ.pop("ADRT_B200_IADRT_SPLIT", None)
