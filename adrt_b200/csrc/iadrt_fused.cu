@@ -27,23 +27,27 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
     const int top = itile::sweep_top(tm.D, t0.c0 * (G::G - 1));
     const long long in_plane = kInQ ? (long long)tm.D * n : (long long)n * 2 * n;
     const long long out_plane = kOutQ ? (long long)tm.D * n : (long long)n * 2 * n;
+    itile::LaneConst<M> lc;
+    itile::setup_levels<M>(tm, team_lane0, k, lane, lc);
+    const int psi_out = tm.c0 * k;
     for (int64_t plane = blockIdx.y; plane < planes; plane += gridDim.y) {
-        const T *ip = in + plane * in_plane;
-        T *op = out + plane * out_plane;
+        // the lane's input column and output column / workspace row
+        const T *ip = in + plane * in_plane + (kInQ ? tm.in_col + k : (tm.in_col + k) * (long long)(2 * n));
+        T *op = out + plane * out_plane + (kOutQ ? tm.out_col + k : (tm.out_col + (long long)k * tm.out_stride) * (long long)(2 * n));
         itile::LaneState<T, M> st;
 #pragma unroll
         for (int t = 0; t <= M; ++t) st.prev[t] = T(0);
-        itile::fetch_inputs<T, kInQ>(ip, tm, k, top, st.v);
+        itile::fetch_inputs<T, kInQ>(ip, tm, top, st.v);
         for (int X0 = top; X0 >= -M; X0 -= 4) {
             itile::commit_inputs<T, M>(ring, tm, lane, X0, st.v);
-            itile::fetch_inputs<T, kInQ>(ip, tm, k, X0 - 4, st.v);
+            itile::fetch_inputs<T, kInQ>(ip, tm, X0 - 4, st.v);
             __syncwarp();
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                itile::all_levels<T, M, kOutQ>(ring, tm, team_lane0, k, lane, X0 - u, st, op);
+                itile::all_levels<T, M, kOutQ>(ring, lc, n, X0 - u, st, op);
                 __syncwarp();
             }
-            if (!kOutQ) itile::flush_outputs<T, M>(ring, tm, k, lane, X0, op);
+            if (!kOutQ) itile::flush_outputs<T, M>(ring, tm, psi_out, lane, X0, op);
         }
         __syncwarp();
     }

@@ -82,29 +82,64 @@ template <typename T, int M> struct LaneState {
     T v[4];            // four input rows fetched for the next trip
 };
 
-template <typename T>
-ADRT_HD T *ring_cell(T *ring, int row_base, int depth, int x, int lane)
+// Per-lane constants of the sweep, one set per level t = 1..M (index t): where the two operands of the
+// lane's node live in the ring of level t-1 and for which base rows X (the warp-uniform loop variable;
+// the node's row is x = X + t, its offset d = x - psi) each term of the reference's expression exists.
+//   even lambda:  acc = (0 + A[x]) - A1[x + 1]            second term iff d + 1 < D
+//   odd lambda:   acc = (0 + A1[x + 1 + j]) - A[x + 1 + j]  both terms iff d + 1 + col < D
+//   acc += prev iff d + 1 < D;  the node exists iff 0 <= d < D
+// Both parities are "first minus second" with per-lane operand positions, so the warp does not diverge.
+template <int M> struct LaneConst {
+    int colF[M + 1], colS[M + 1];   // ring element offset (row 0) of the first / second operand's column
+    int dF[M + 1], dS[M + 1];       // their row look-ahead relative to x
+    int lo[M + 1], hi[M + 1];       // node exists for lo <= X <= hi
+    int thr1[M + 1], thr2[M + 1];   // first / second term exists for X <= thr
+    int own[M + 1];                 // ring element offset (row 0) of the lane's own column at level t
+};
+
+template <int M, int t = 1>
+ADRT_HD void setup_levels(const Team &tm, int team_lane0, int k, int lane, LaneConst<M> &lc)
 {
-    return ring + (long long)(row_base + (x & (depth - 1))) * kLanes + lane;
+    if constexpr (t <= M) {
+        constexpr int sh = M - t;
+        const int lam = k >> sh, j = k & ((1 << sh) - 1);
+        const int psi = (tm.c0 << sh) * lam;
+        const int kA = ((lam >> 1) << (sh + 1)) + 2 * j + team_lane0;
+        constexpr int rb = Geo<M>::base(t - 1);
+        const bool odd = lam & 1;
+        lc.colF[t] = rb * kLanes + (odd ? kA + 1 : kA);
+        lc.colS[t] = rb * kLanes + (odd ? kA : kA + 1);
+        lc.dF[t] = odd ? 1 + j : 0;
+        lc.dS[t] = odd ? 1 + j : 1;
+        // d = X + t - psi
+        lc.lo[t] = psi - t;
+        lc.hi[t] = tm.D - 1 + psi - t;
+        const int col = (tm.c0 << sh) + j;
+        const int t_odd = tm.D - 2 - col + psi - t;     // d + 1 + col < D
+        lc.thr1[t] = odd ? t_odd : 0x7fffffff;
+        lc.thr2[t] = odd ? t_odd : tm.D - 2 + psi - t;  // even: d + 1 < D
+        if (!tm.active) { lc.lo[t] = 1; lc.hi[t] = 0; } // padding team: no node ever exists
+        lc.own[t] = (t < M ? Geo<M>::base(t) : Geo<M>::OUT_BASE) * kLanes + lane;
+        setup_levels<M, t + 1>(tm, team_lane0, k, lane, lc);
+    }
 }
 
 // ---- input side ---------------------------------------------------------------------------------
 // Rows X0-3 .. X0 (X0 = 3 mod 4) of the lane's input column, to be committed at the start of the trip
 // with base rows X0 .. X0-3.  kInQ: public layout in[d][col] (pitch n), else workspace W[col][2n].
+// `col_ptr`: the lane's column (public layout: &in[0][col]; workspace: &W[col][0]).
 template <typename T, bool kInQ>
-ADRT_HD void fetch_inputs(const T *in_plane, const Team &tm, int k, int X0, T (&v)[4])
+ADRT_HD void fetch_inputs(const T *col_ptr, const Team &tm, int X0, T (&v)[4])
 {
     if (!tm.active || X0 < 0 || X0 - 3 >= tm.D) return;
     if (kInQ) {
-        const T *p = in_plane + tm.in_col + k;
+        const T *p = col_ptr + (long long)(X0 - 3) * tm.n;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int x = X0 - 3 + e;
-            if (x < tm.D) v[e] = p[(long long)x * tm.n];
-        }
+        for (int e = 0; e < 4; ++e)
+            if (X0 - 3 + e < tm.D) v[e] = p[(long long)e * tm.n];
     } else {
         // aligned 16-byte group(s) of the padded row; the pad cell (offset 2n - 1) is loaded and never used
-        const T *p = in_plane + (tm.in_col + k) * (long long)(2 * tm.n) + (X0 - 3);
+        const T *p = col_ptr + (X0 - 3);
         constexpr int L = tile::VecOf<T>::L;
 #pragma unroll
         for (int g = 0; g < 4 / L; ++g) {
@@ -119,85 +154,59 @@ template <typename T, int M>
 ADRT_HD void commit_inputs(T *ring, const Team &tm, int lane, int X0, const T (&v)[4])
 {
     if (!tm.active || X0 < 0 || X0 - 3 >= tm.D) return;
+    constexpr int mask = Geo<M>::depth(0) - 1;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int x = X0 - 3 + e;
-        if (x < tm.D) *ring_cell(ring, Geo<M>::base(0), Geo<M>::depth(0), x, lane) = v[e];
+        if (x < tm.D) ring[((x & mask) << 5) + lane] = v[e];
     }
 }
 
-// ---- one level of one base row ---------------------------------------------------------------------
-// Level t (1..M) for the lane's node at row x = X + t.  Returns true and sets `val` when the node's
-// offset d = x - psi lies in [0, D).
-template <typename T, int M, int t>
-ADRT_HD bool level_step(const T *ring, const Team &tm, int team_lane0, int k, int X, T &prev, T &val, int &d_out)
-{
-    constexpr int sh = M - t;
-    const int lam = k >> sh, j = k & ((1 << sh) - 1);
-    const int psi = (tm.c0 << sh) * lam;
-    const int x = X + t, d = x - psi;
-    d_out = d;
-    if (!tm.active || d < 0 || d >= tm.D) return false;
-    const int kA = ((lam >> 1) << (sh + 1)) + 2 * j + team_lane0;
-    constexpr int rb = Geo<M>::base(t - 1), dp = Geo<M>::depth(t - 1);
-    T acc = T(0);
-    if ((lam & 1) == 0) {
-        acc += *ring_cell(ring, rb, dp, x, kA);
-        if (d + 1 < tm.D) acc -= *ring_cell(ring, rb, dp, x + 1, kA + 1);
-    } else {
-        const int col = (tm.c0 << sh) + j;
-        if (d + 1 + col < tm.D) {
-            const int xp = x + 1 + j;
-            acc += *ring_cell(ring, rb, dp, xp, kA + 1);
-            acc -= *ring_cell(ring, rb, dp, xp, kA);
-        }
-    }
-    if (d + 1 < tm.D) acc += prev;
-    prev = acc;
-    val = acc;
-    return true;
-}
-
-// all levels of base row X for one lane; kOutQ: the last level is stored straight to the public layout
+// ---- all levels of one base row X for one lane -----------------------------------------------------------
+// kOutQ: the last level is stored straight to the public layout (`out_ptr` = &out[0][lane's column]; the
+// last pass has psi = 0, so every lane is at the same offset d = X + M: one coalesced row piece).
 template <typename T, int M, bool kOutQ, int t = 1>
-ADRT_HD void all_levels(T *ring, const Team &tm, int team_lane0, int k, int lane, int X, LaneState<T, M> &st, T *out_plane)
+ADRT_HD void all_levels(T *ring, const LaneConst<M> &lc, int n, int X, LaneState<T, M> &st, T *out_ptr)
 {
     if constexpr (t <= M) {
-        T val;
-        int d;
-        const bool ok = level_step<T, M, t>(ring, tm, team_lane0, k, X, st.prev[t], val, d);
-        if (ok) {
+        constexpr int mask = Geo<M>::depth(t - 1) - 1;
+        const int x = X + t;
+        const T first = ring[lc.colF[t] + (((x + lc.dF[t]) & mask) << 5)];
+        const T second = ring[lc.colS[t] + (((x + lc.dS[t]) & mask) << 5)];
+        T acc = X <= lc.thr1[t] ? T(0) + first : T(0);
+        acc = X <= lc.thr2[t] ? acc - second : acc;
+        acc = X < lc.hi[t] ? acc + st.prev[t] : acc;
+        if (X >= lc.lo[t] && X <= lc.hi[t]) {
+            st.prev[t] = acc;
             if constexpr (t < M) {
-                *ring_cell(ring, Geo<M>::base(t), Geo<M>::depth(t), X + t, lane) = val;
+                ring[lc.own[t] + ((x & (Geo<M>::depth(t) - 1)) << 5)] = acc;
             } else if constexpr (kOutQ) {
-                // last pass: c0 = 0, every lane is at the same offset d: one coalesced row piece
-                out_plane[(long long)d * tm.n + tm.out_col + k] = val;
+                out_ptr[(long long)x * n] = acc;
             } else {
-                *ring_cell(ring, Geo<M>::OUT_BASE, Geo<M>::OUT_DEPTH, X + t, lane) = val;
+                ring[lc.own[t] + ((x & (Geo<M>::OUT_DEPTH - 1)) << 5)] = acc;
             }
         }
-        all_levels<T, M, kOutQ, t + 1>(ring, tm, team_lane0, k, lane, X, st, out_plane);
+        all_levels<T, M, kOutQ, t + 1>(ring, lc, n, X, st, out_ptr);
     }
 }
 
 // ---- workspace stores -------------------------------------------------------------------------------
 // After the trip with base rows X0 .. X0-3 the lane's output column is complete down to offset
 // X0 - 3 + M - psi: flush the one aligned group of four offsets that became complete in this trip.
+// `row_ptr`: the lane's workspace row (&W[output column][0]); psi = c0 * lambda.
 template <typename T, int M>
-ADRT_HD void flush_outputs(const T *ring, const Team &tm, int k, int lane, int X0, T *out_plane)
+ADRT_HD void flush_outputs(const T *ring, const Team &tm, int psi, int lane, int X0, T *row_ptr)
 {
     if (!tm.active) return;
-    const int psi = tm.c0 * k;
     const int lo = X0 - 3 + M - psi;           // lowest offset computed so far
     const int d0 = (lo + 3) & ~3;              // lowest complete aligned group
     if (d0 < 0 || d0 >= 2 * tm.n) return;
     T w[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) w[e] = *ring_cell(ring, Geo<M>::OUT_BASE, Geo<M>::OUT_DEPTH, d0 + e + psi, lane);
-    T *p = out_plane + (tm.out_col + (long long)k * tm.out_stride) * (long long)(2 * tm.n) + d0;
+    for (int e = 0; e < 4; ++e) w[e] = ring[Geo<M>::OUT_BASE * kLanes + lane + (((d0 + e + psi) & (Geo<M>::OUT_DEPTH - 1)) << 5)];
     constexpr int L = tile::VecOf<T>::L;
 #pragma unroll
-    for (int g = 0; g < 4 / L; ++g) tile::store_cv<T>(p + g * L, &w[g * L]);
+    for (int g = 0; g < 4 / L; ++g) tile::store_cv<T>(row_ptr + d0 + g * L, &w[g * L]);
 }
 
 // Sweep bounds of a warp: base rows from x_top (= 3 mod 4) down to x_end (inclusive, multiple of 4 trips).

@@ -299,30 +299,36 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
             const itile::Team t0 = itile::make_team<M>(n, s0, tp0);
             if (!t0.active) continue;
             const int top = itile::sweep_top(D, t0.c0 * (G::G - 1));
-            const T *ip = in + plane * in_plane;
-            T *op = out + plane * out_plane;
             std::fill(ring.begin(), ring.end(), T(NAN));   // reads of never-written cells show up
             itile::Team tm[32];
             itile::LaneState<T, M> st[32];
+            itile::LaneConst<M> lc[32];
+            const T *ip[32];
+            T *op[32];
             for (int lane = 0; lane < 32; ++lane) {
+                const int k = lane % G::G;
                 tm[lane] = itile::make_team<M>(n, s0, tp0 + lane / G::G);
+                itile::setup_levels<M>(tm[lane], (lane / G::G) * G::G, k, lane, lc[lane]);
+                ip[lane] = in + plane * in_plane + (kInQ ? tm[lane].in_col + k : (tm[lane].in_col + k) * (long long)(2 * n));
+                op[lane] = out + plane * out_plane + (kOutQ ? tm[lane].out_col + k : (tm[lane].out_col + (long long)k * tm[lane].out_stride) * (long long)(2 * n));
                 for (int t = 0; t <= M; ++t) st[lane].prev[t] = T(0);
                 for (int e = 0; e < 4; ++e) st[lane].v[e] = T(NAN);
-                itile::fetch_inputs<T, kInQ>(ip, tm[lane], lane % G::G, top, st[lane].v);
+                itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], top, st[lane].v);
             }
             for (int X0 = top; X0 >= -M; X0 -= 4) {
                 for (int i = 0; i < 32; ++i) {
                     const int lane = g_order ? 31 - i : i;
                     itile::commit_inputs<T, M>(ring.data(), tm[lane], lane, X0, st[lane].v);
-                    itile::fetch_inputs<T, kInQ>(ip, tm[lane], lane % G::G, X0 - 4, st[lane].v);
+                    itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], X0 - 4, st[lane].v);
                 }
                 for (int u = 0; u < 4; ++u)
                     for (int i = 0; i < 32; ++i) {
                         const int lane = g_order ? 31 - i : i;
-                        itile::all_levels<T, M, kOutQ>(ring.data(), tm[lane], (lane / G::G) * G::G, lane % G::G, lane, X0 - u, st[lane], op);
+                        itile::all_levels<T, M, kOutQ>(ring.data(), lc[lane], n, X0 - u, st[lane], op[lane]);
                     }
                 if (!kOutQ)
-                    for (int lane = 0; lane < 32; ++lane) itile::flush_outputs<T, M>(ring.data(), tm[lane], lane % G::G, lane, X0, op);
+                    for (int lane = 0; lane < 32; ++lane)
+                        itile::flush_outputs<T, M>(ring.data(), tm[lane], tm[lane].c0 * (lane % G::G), lane, X0, op[lane]);
             }
         }
 }
