@@ -30,6 +30,11 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
     itile::LaneConst<M> lc;
     itile::setup_levels<M>(tm, team_lane0, k, lane, lc);
     const int psi_out = tm.c0 * k;
+    // base rows for which no lane of the warp needs a guard
+    int ilo, ihi;
+    itile::interior_range<M>(lc, tm.active, ilo, ihi);
+    ilo = __reduce_max_sync(0xffffffffu, ilo);
+    ihi = __reduce_min_sync(0xffffffffu, ihi);
     for (int64_t plane = blockIdx.y; plane < planes; plane += gridDim.y) {
         // the lane's input column and output column / workspace row
         const T *ip = in + plane * in_plane + (kInQ ? tm.in_col + k : (tm.in_col + k) * (long long)(2 * n));
@@ -42,10 +47,18 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
             itile::commit_inputs<T, M>(ring, tm, lane, X0, st.v);
             itile::fetch_inputs<T, kInQ>(ip, tm, X0 - 4, st.v);
             __syncwarp();
+            if (X0 - 3 >= ilo && X0 <= ihi) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                itile::all_levels<T, M, kOutQ>(ring, lc, n, X0 - u, st, op);
-                __syncwarp();
+                for (int u = 0; u < 4; ++u) {
+                    itile::all_levels_interior<T, M, kOutQ>(ring, lc, n, X0 - u, st, op);
+                    __syncwarp();
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    itile::all_levels<T, M, kOutQ>(ring, lc, n, X0 - u, st, op);
+                    __syncwarp();
+                }
             }
             if (!kOutQ) itile::flush_outputs<T, M>(ring, tm, psi_out, lane, X0, op);
         }

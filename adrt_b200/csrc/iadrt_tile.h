@@ -190,6 +190,47 @@ ADRT_HD void all_levels(T *ring, const LaneConst<M> &lc, int n, int X, LaneState
     }
 }
 
+// The same for base rows where every term of every level exists for every lane of the warp
+// (interior_range): no comparisons, no selects.
+template <typename T, int M, bool kOutQ, int t = 1>
+ADRT_HD void all_levels_interior(T *ring, const LaneConst<M> &lc, int n, int X, LaneState<T, M> &st, T *out_ptr)
+{
+    if constexpr (t <= M) {
+        constexpr int mask = Geo<M>::depth(t - 1) - 1;
+        const int x = X + t;
+        const T first = ring[lc.colF[t] + (((x + lc.dF[t]) & mask) << 5)];
+        const T second = ring[lc.colS[t] + (((x + lc.dS[t]) & mask) << 5)];
+        const T acc = ((T(0) + first) - second) + st.prev[t];
+        st.prev[t] = acc;
+        if constexpr (t < M) {
+            ring[lc.own[t] + ((x & (Geo<M>::depth(t) - 1)) << 5)] = acc;
+        } else if constexpr (kOutQ) {
+            out_ptr[(long long)x * n] = acc;
+        } else {
+            ring[lc.own[t] + ((x & (Geo<M>::OUT_DEPTH - 1)) << 5)] = acc;
+        }
+        all_levels_interior<T, M, kOutQ, t + 1>(ring, lc, n, X, st, out_ptr);
+    }
+}
+
+// Base rows X for which this lane needs no guard at any level: [lo, hi] (empty for padding teams).
+// The warp takes the unguarded path for a trip X0 .. X0-3 when it lies inside every lane's range.
+template <int M>
+ADRT_HD void interior_range(const LaneConst<M> &lc, bool active, int &lo, int &hi)
+{
+    lo = -0x40000000;
+    hi = 0x40000000;
+#pragma unroll
+    for (int t = 1; t <= M; ++t) {
+        if (lc.lo[t] > lo) lo = lc.lo[t];
+        int h = lc.hi[t] - 1;                       // "+ prev" needs X < hi
+        if (lc.thr1[t] < h) h = lc.thr1[t];
+        if (lc.thr2[t] < h) h = lc.thr2[t];
+        if (h < hi) hi = h;
+    }
+    if (!active) { lo = 1; hi = 0; }
+}
+
 // ---- workspace stores -------------------------------------------------------------------------------
 // After the trip with base rows X0 .. X0-3 the lane's output column is complete down to offset
 // X0 - 3 + M - psi: flush the one aligned group of four offsets that became complete in this trip.

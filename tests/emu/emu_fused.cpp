@@ -315,6 +315,13 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
                 for (int e = 0; e < 4; ++e) st[lane].v[e] = T(NAN);
                 itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], top, st[lane].v);
             }
+            int ilo = -0x40000000, ihi = 0x40000000;   // the warp-wide reduction of the lanes' interior ranges
+            for (int lane = 0; lane < 32; ++lane) {
+                int lo, hi;
+                itile::interior_range<M>(lc[lane], tm[lane].active, lo, hi);
+                ilo = std::max(ilo, lo);
+                ihi = std::min(ihi, hi);
+            }
             for (int X0 = top; X0 >= -M; X0 -= 4) {
                 for (int i = 0; i < 32; ++i) {
                     const int lane = g_order ? 31 - i : i;
@@ -324,7 +331,8 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
                 for (int u = 0; u < 4; ++u)
                     for (int i = 0; i < 32; ++i) {
                         const int lane = g_order ? 31 - i : i;
-                        itile::all_levels<T, M, kOutQ>(ring.data(), lc[lane], n, X0 - u, st[lane], op[lane]);
+                        if (X0 - 3 >= ilo && X0 <= ihi) itile::all_levels_interior<T, M, kOutQ>(ring.data(), lc[lane], n, X0 - u, st[lane], op[lane]);
+                        else itile::all_levels<T, M, kOutQ>(ring.data(), lc[lane], n, X0 - u, st[lane], op[lane]);
                     }
                 if (!kOutQ)
                     for (int lane = 0; lane < 32; ++lane)
