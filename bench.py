@@ -388,10 +388,14 @@ def ours(args, np_dtype):
             barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
+                # adrt's copies then bdrt's, as the two calls order them: D2H of y, then H2D of y beside D2H of z
+                x.copy_(hx, non_blocking=True); hy.copy_(y, non_blocking=True)
+                cs.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(cs):
-                    x.copy_(hx, non_blocking=True); hy.copy_(y, non_blocking=True)   # adrt: image in, sinogram out
-                y.copy_(hy, non_blocking=True); hz.copy_(z, non_blocking=True)       # bdrt: sinogram in, sinogram out
-                torch.cuda.synchronize()
+                    y.copy_(hy, non_blocking=True)
+                hz.copy_(z, non_blocking=True)
+                torch.cuda.current_stream().wait_stream(cs)
+            torch.cuda.synchronize()
             ceil_step = max_over_ranks(time.perf_counter() - t0) / e2e_steps
             del z
             e2e = {
@@ -402,7 +406,7 @@ def ours(args, np_dtype):
                 "numa_bound": bool(numa_bound),
                 "copy_ceiling": {
                     "value": total_images * n * n / ceil_step / 1e9, "unit": UNIT, "ms_per_step": ceil_step * 1e3,
-                    "what": "same H2D+D2H bytes as bare cudaMemcpyAsync on every rank at once (two streams, full duplex), no kernels",
+                    "what": "the same H2D and D2H bytes, in the order the two calls need them (image in, sinogram out; then sinogram in beside sinogram out, full duplex), as bare cudaMemcpyAsync on every rank at once, no kernels",
                     "gbs_per_gpu": (h2d + d2h) / ceil_step / 1e9,
                 },
                 "frac_of_ceiling": ceil_step / dt_step,
