@@ -190,7 +190,15 @@ def _empty_like(arr: _Arr, shape, out, alias_ok=False):
         if not alias_ok and np.may_share_memory(out, arr.obj):
             raise ValueError("out must not overlap the input array")
         return out
-    return np.empty(shape, dtype=arr.np_dtype)
+    # large results: fresh arrays in page-locked memory the GPU writes directly (_pinned.py)
+    from . import _pinned
+
+    fresh = None
+    try:
+        fresh = _pinned.empty(shape, arr.np_dtype)
+    except Exception:   # no library / no device yet: the ordinary array; the call itself reports the problem
+        fresh = None
+    return fresh if fresh is not None else np.empty(shape, dtype=arr.np_dtype)
 
 
 # The fused transforms (adrt, bdrt and the helpers built on them) use 16/32-byte vector accesses and

@@ -417,7 +417,10 @@ def ours(args, np_dtype):
             # ---- the reference's calling convention: pageable in, fresh pageable out ----
             px = np.array(nx, copy=True)  # ordinary (pageable) ndarray
             del nx, ny
-            adrt.bdrt(adrt.adrt(px[:1]))
+            # one untimed step: the engine hands out large results from a pool of page-locked blocks
+            # (adrt_b200/_pinned.py), which the first call of a size has to allocate
+            pz = adrt.bdrt(adrt.adrt(px))
+            del pz
             barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
@@ -429,7 +432,9 @@ def ours(args, np_dtype):
                 "value": total_images * n * n / dt_def / 1e9, "unit": UNIT, "ms_per_step": dt_def * 1e3,
                 "steps": e2e_steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "y = adrt_b200.adrt(x); z = adrt_b200.bdrt(y) on pageable numpy.ndarray, fresh result arrays "
-                       "(the reference's own contract: py.cpp:177 PyArray_SimpleNew)",
+                       "(the reference's own contract: py.cpp:177 PyArray_SimpleNew); results >= 32 MiB come from the "
+                       "engine's pool of page-locked blocks (warm: one untimed step before)",
+                "pinned_result_pool": os.environ.get("ADRT_B200_PINNED_RESULTS", "1") != "0",
             }
             assert np.array_equal(py[0], y[0].cpu().numpy()), "default host path and device path disagree"
             del py, px
