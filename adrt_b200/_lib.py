@@ -80,6 +80,7 @@ SIGNATURES = {
     "adrt_b200_host_interp_to_cart": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int]),
     "adrt_b200_host_alloc_pinned": (_c_vp, [_c_sz]),
     "adrt_b200_host_free_pinned": (None, [_c_vp]),
+    "adrt_b200_host_is_pinned": (_c_int, [_c_vp]),
 }
 
 _lib = None

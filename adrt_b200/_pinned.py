@@ -10,7 +10,7 @@ of page-locked blocks (``cudaHostAlloc`` through ``adrt_b200_host_alloc_pinned``
 writes them directly, and a result that is fed back into the next call (``bdrt(adrt(x))``)
 is read directly too.  A block returns to the pool when the last view of its array dies
 (``weakref.finalize``); the pool keeps at most ``ADRT_B200_PINNED_POOL_MB`` (default: a
-quarter of the host's memory, at most 64 GiB) and frees the rest.
+quarter of the host's memory divided by $LOCAL_WORLD_SIZE, at most 64 GiB) and frees the rest.
 ``ADRT_B200_PINNED_RESULTS=0`` turns the feature off (plain ``np.empty``, ``owndata`` true).
 """
 from __future__ import annotations
@@ -48,7 +48,9 @@ def _pool_cap() -> int:
                 total = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
             except (ValueError, OSError):
                 total = 16 << 30
-            _cap = min(total // 4, 64 << 30)
+            # one process per GPU (torchrun): the ranks of a node share the quarter
+            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+            _cap = min(total // 4 // ranks, 64 << 30)
     return _cap
 
 

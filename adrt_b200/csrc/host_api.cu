@@ -67,12 +67,14 @@ int grow(void **p, size_t *cap, size_t need, bool pinned)
     return ADRT_B200_OK;
 }
 
+}  // namespace
 bool is_pinned(const void *p)
 {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return attr.type == cudaMemoryTypeHost;
 }
+namespace {
 
 int host_threads()
 {
@@ -351,5 +353,7 @@ void adrt_b200_host_free_pinned(void *p)
 {
     if (p) cudaFreeHost(p);
 }
+
+int adrt_b200_host_is_pinned(const void *p) { return p && adrt_b200::is_pinned(p) ? 1 : 0; }
 
 }  // extern "C"

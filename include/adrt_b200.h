@@ -233,6 +233,8 @@ int adrt_b200_host_interp_to_cart(const void *in, void *out, int64_t B, int64_t 
 /* Pinned host memory helpers for callers that want the fast NumPy path.     */
 void *adrt_b200_host_alloc_pinned(size_t bytes);
 void  adrt_b200_host_free_pinned(void *p);
+/* 1 if `p` points into page-locked host memory known to CUDA (the host entry points then copy directly) */
+int   adrt_b200_host_is_pinned(const void *p);
 
 #ifdef __cplusplus
 }
