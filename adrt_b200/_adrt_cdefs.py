@@ -36,6 +36,10 @@ _INT_MIN = -(2**31)
 _SIZE_BITS = 64
 _MAX_SIZE = 1 << (_SIZE_BITS - 1)  # adrt_cdefs_common.cpp:62
 
+# Largest image side n the kernels index (32-bit in-plane offsets, csrc/common.cuh kMaxN): a float32
+# (4, 2n-1, n) array of that size is 8.6 GB.  Larger power-of-two sides raise ValueError here.
+MAX_SIDE = 16384
+
 _device = None
 
 
@@ -229,6 +233,9 @@ def _run(name, arr: _Arr, out_shape, dims, out=None, step=None, workspace=None, 
     """
     lib = _lib.load()
     code = _dtype_code(arr)
+    if len(dims) == 2 and dims[1] > MAX_SIDE:
+        # documented limit of this engine (32-bit in-plane indices: (2n-1) n < 2^31); the reference has none
+        raise ValueError(f"array is too big: image side {dims[1]} exceeds the {MAX_SIDE} this engine supports")
     ret = _empty_like(arr, out_shape, out)
     _lib.require_device()
     step_args = () if step is None else (step,)

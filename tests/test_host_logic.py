@@ -281,3 +281,12 @@ def test_tensor_subclass_and_dlpack_are_recognised():
     # CPU tensors are not arrays this engine accepts (same TypeError as any non-ndarray)
     with pytest.raises(TypeError, match="must be numpy.ndarray"):
         adrt.adrt(torch.zeros(4, 4))
+
+
+def test_size_limit_is_a_value_error():
+    # n > 16384 used to surface as a RuntimeError from the C ABI; now a ValueError raised before
+    # anything is allocated (a real array of that size would be 34 GB, so the dispatcher is driven directly)
+    fake = cd._Arr(np.zeros(1, dtype=np.float32), (4, 2 * 32768 - 1, 32768), np.dtype(np.float32), False)
+    with pytest.raises(ValueError, match="image side 32768 exceeds the 16384"):
+        cd._run("bdrt", fake, fake.shape, (1, 32768), workspace="bdrt")
+    assert cd.MAX_SIDE == 16384
