@@ -18,13 +18,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int s0)
 {
     using G = itile::Geo<M>;
-    using R = itile::Ring<T, M>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // every warp's ring starts at a multiple of its largest region (see itile::Ring)
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const unsigned aligned = (sbase + R::largest() - 1) & ~(unsigned)(R::largest() - 1);
-    char *ring = reinterpret_cast<char *>(smem_raw) + (aligned - sbase) + (size_t)warp * R::BYTES;
+    T *ring = reinterpret_cast<T *>(smem_raw) + (size_t)warp * G::ROWS * itile::kLanes;
     const int team = lane / G::G, k = lane % G::G, team_lane0 = team * G::G;
     const int tp0 = (blockIdx.x * kWarpsPerBlock + warp) * G::TEAMS;
     const itile::Team tm = itile::make_team<M>(n, s0, tp0 + team);
@@ -34,12 +30,12 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
     const int top = itile::sweep_top(tm.D, t0.c0 * (G::G - 1));
     const long long in_plane = kInQ ? (long long)tm.D * n : (long long)n * 2 * n;
     const long long out_plane = kOutQ ? (long long)tm.D * n : (long long)n * 2 * n;
-    itile::LaneConst<M> lc0;
-    itile::setup_levels<T, M>(tm, team_lane0, k, lane, top, lc0);
+    itile::LaneConst<M> lc;
+    itile::setup_levels<M>(tm, team_lane0, k, lane, lc);
     const int psi_out = tm.c0 * k;
     // base rows for which no lane of the warp needs a guard
     int ilo, ihi;
-    itile::interior_range<M>(lc0, tm.active, ilo, ihi);
+    itile::interior_range<M>(lc, tm.active, ilo, ihi);
     ilo = __reduce_max_sync(0xffffffffu, ilo);
     ihi = __reduce_min_sync(0xffffffffu, ihi);
     for (int64_t plane = blockIdx.y; plane < planes; plane += gridDim.y) {
@@ -47,24 +43,23 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
         const T *ip = in + plane * in_plane + (kInQ ? tm.in_col + k : (tm.in_col + k) * (long long)(2 * n));
         T *op = out + plane * out_plane + (kOutQ ? tm.out_col + k : (tm.out_col + (long long)k * tm.out_stride) * (long long)(2 * n));
         itile::LaneState<T, M> st;
-        itile::LaneConst<M> lc = lc0;   // the ring addresses restart at the top of every plane's sweep
 #pragma unroll
         for (int t = 0; t <= M; ++t) st.prev[t] = T(0);
         itile::fetch_inputs<T, kInQ>(ip, tm, top, st.v);
         for (int X0 = top; X0 >= -M; X0 -= 4) {
-            itile::commit_inputs<T, M>(ring, tm, lc, X0, st.v);
+            itile::commit_inputs<T, M>(ring, tm, lane, X0, st.v);
             itile::fetch_inputs<T, kInQ>(ip, tm, X0 - 4, st.v);
             __syncwarp();
             if (X0 - 3 >= ilo && X0 <= ihi) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    itile::all_levels<T, M, kOutQ, false>(ring, lc, n, X0 - u, st, op);
+                    itile::all_levels_interior<T, M, kOutQ>(ring, lc, n, X0 - u, st, op);
                     __syncwarp();
                 }
             } else {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    itile::all_levels<T, M, kOutQ, true>(ring, lc, n, X0 - u, st, op);
+                    itile::all_levels<T, M, kOutQ>(ring, lc, n, X0 - u, st, op);
                     __syncwarp();
                 }
             }
@@ -81,7 +76,7 @@ int launch_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0, cudaSt
     const int teams = n >> M;                                       // per plane
     const int warps = (teams + G::TEAMS - 1) / G::TEAMS;
     const int blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const size_t smem = (size_t)kWarpsPerBlock * itile::Ring<T, M>::BYTES + itile::Ring<T, M>::largest();
+    const size_t smem = (size_t)kWarpsPerBlock * G::ROWS * itile::kLanes * sizeof(T);
     auto kern = iadrt_pass_kernel<T, M, kInQ, kOutQ>;
     ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)blocks, (unsigned)(planes < 65535 ? planes : 65535));

@@ -66,31 +66,6 @@ template <int M> struct Geo {
     static constexpr int ROWS = OUT_BASE + OUT_DEPTH;   // ring rows per warp (x 32 lanes)
 };
 
-ADRT_HD constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
-
-// Byte layout of a warp's ring: region r = level r (r < M) or the output ring (r = M), each `depth`
-// rows of 32 lanes, placed at an offset that is a multiple of its own (power-of-two) size.  A cell
-// address then steps one row down with  a' = ((a - ROW) & (size - 1)) | offset  -- two instructions,
-// the lane's column bits (below ROW) ride along -- instead of being recomputed from the row index.
-// The warp's ring must start at an address that is a multiple of the largest region (BYTES is one).
-template <typename T, int M> struct Ring {
-    static constexpr int ROW = kLanes * (int)sizeof(T);
-    ADRT_HD static constexpr int size(int r) { return (r < M ? Geo<M>::depth(r) : Geo<M>::OUT_DEPTH) * ROW; }
-    ADRT_HD static constexpr int off(int r) { return r == 0 ? 0 : align_up(off(r - 1) + size(r - 1), size(r)); }
-    ADRT_HD static constexpr int largest(int r = M) { return r == 0 ? size(0) : (size(r) > largest(r - 1) ? size(r) : largest(r - 1)); }
-    static constexpr int BYTES = align_up(off(M) + size(M), largest());
-    // one row down (towards smaller x) inside region r
-    template <int r> ADRT_HD static int down(int a, int rows = 1) { return ((a - rows * ROW) & (size(r) - 1)) | off(r); }
-    // cell of row x, lane `col` in region r
-    template <int r> ADRT_HD static int cell(int x, int col)
-    {
-        return off(r) + (x & ((r < M ? Geo<M>::depth(r) : Geo<M>::OUT_DEPTH) - 1)) * ROW + col * (int)sizeof(T);
-    }
-};
-
-template <typename T> ADRT_HD T &at(char *ring, int a) { return *reinterpret_cast<T *>(ring + a); }
-template <typename T> ADRT_HD const T &at(const char *ring, int a) { return *reinterpret_cast<const T *>(ring + a); }
-
 // Everything a lane needs to know about its team's group.
 struct Team {
     int n, D;          // image side, 2n - 1
@@ -107,37 +82,35 @@ template <typename T, int M> struct LaneState {
     T v[4];            // four input rows fetched for the next trip
 };
 
-// Per-lane state of the sweep, one set per level t = 1..M (index t): the ring addresses of the two
-// operands of the lane's node (level t-1 cells) and of the node's own cell, all for the CURRENT base
-// row X and stepped down after every row, and the base rows X (the warp-uniform loop variable; the
-// node's row is x = X + t, its offset d = x - psi) for which each term of the reference's expression exists.
+// Per-lane constants of the sweep, one set per level t = 1..M (index t): where the two operands of the
+// lane's node live in the ring of level t-1 and for which base rows X (the warp-uniform loop variable;
+// the node's row is x = X + t, its offset d = x - psi) each term of the reference's expression exists.
 //   even lambda:  acc = (0 + A[x]) - A1[x + 1]            second term iff d + 1 < D
 //   odd lambda:   acc = (0 + A1[x + 1 + j]) - A[x + 1 + j]  both terms iff d + 1 + col < D
 //   acc += prev iff d + 1 < D;  the node exists iff 0 <= d < D
 // Both parities are "first minus second" with per-lane operand positions, so the warp does not diverge.
 template <int M> struct LaneConst {
-    int aF[M + 1], aS[M + 1], aO[M + 1];   // ring byte addresses: first operand, second operand, own cell
-    int a0;                                // level-0 cell of row X0 - 3 (input commit), stepped per trip
-    int lo[M + 1], hi[M + 1];              // node exists for lo <= X <= hi
-    int thr1[M + 1], thr2[M + 1];          // first / second term exists for X <= thr
+    int colF[M + 1], colS[M + 1];   // ring element offset (row 0) of the first / second operand's column
+    int dF[M + 1], dS[M + 1];       // their row look-ahead relative to x
+    int lo[M + 1], hi[M + 1];       // node exists for lo <= X <= hi
+    int thr1[M + 1], thr2[M + 1];   // first / second term exists for X <= thr
+    int own[M + 1];                 // ring element offset (row 0) of the lane's own column at level t
 };
 
-// `top`: the first base row of the sweep (the addresses start there)
-template <typename T, int M, int t = 1>
-ADRT_HD void setup_levels(const Team &tm, int team_lane0, int k, int lane, int top, LaneConst<M> &lc)
+template <int M, int t = 1>
+ADRT_HD void setup_levels(const Team &tm, int team_lane0, int k, int lane, LaneConst<M> &lc)
 {
-    using R = Ring<T, M>;
-    if constexpr (t == 1) lc.a0 = R::template cell<0>(top - 3, lane);
     if constexpr (t <= M) {
         constexpr int sh = M - t;
         const int lam = k >> sh, j = k & ((1 << sh) - 1);
         const int psi = (tm.c0 << sh) * lam;
         const int kA = ((lam >> 1) << (sh + 1)) + 2 * j + team_lane0;
+        constexpr int rb = Geo<M>::base(t - 1);
         const bool odd = lam & 1;
-        const int x = top + t;
-        lc.aF[t] = R::template cell<t - 1>(x + (odd ? 1 + j : 0), odd ? kA + 1 : kA);
-        lc.aS[t] = R::template cell<t - 1>(x + (odd ? 1 + j : 1), odd ? kA : kA + 1);
-        lc.aO[t] = R::template cell<t>(x, lane);
+        lc.colF[t] = rb * kLanes + (odd ? kA + 1 : kA);
+        lc.colS[t] = rb * kLanes + (odd ? kA : kA + 1);
+        lc.dF[t] = odd ? 1 + j : 0;
+        lc.dS[t] = odd ? 1 + j : 1;
         // d = X + t - psi
         lc.lo[t] = psi - t;
         lc.hi[t] = tm.D - 1 + psi - t;
@@ -146,7 +119,8 @@ ADRT_HD void setup_levels(const Team &tm, int team_lane0, int k, int lane, int t
         lc.thr1[t] = odd ? t_odd : 0x7fffffff;
         lc.thr2[t] = odd ? t_odd : tm.D - 2 + psi - t;  // even: d + 1 < D
         if (!tm.active) { lc.lo[t] = 1; lc.hi[t] = 0; } // padding team: no node ever exists
-        setup_levels<T, M, t + 1>(tm, team_lane0, k, lane, top, lc);
+        lc.own[t] = (t < M ? Geo<M>::base(t) : Geo<M>::OUT_BASE) * kLanes + lane;
+        setup_levels<M, t + 1>(tm, team_lane0, k, lane, lc);
     }
 }
 
@@ -176,50 +150,66 @@ ADRT_HD void fetch_inputs(const T *col_ptr, const Team &tm, int X0, T (&v)[4])
     }
 }
 
-// The four rows of a trip are an aligned group (X0 = 3 mod 4, the depth is a multiple of 4): no wrap inside.
 template <typename T, int M>
-ADRT_HD void commit_inputs(char *ring, const Team &tm, LaneConst<M> &lc, int X0, const T (&v)[4])
+ADRT_HD void commit_inputs(T *ring, const Team &tm, int lane, int X0, const T (&v)[4])
 {
-    using R = Ring<T, M>;
-    if (tm.active && X0 >= 0 && X0 - 3 < tm.D) {
+    if (!tm.active || X0 < 0 || X0 - 3 >= tm.D) return;
+    constexpr int mask = Geo<M>::depth(0) - 1;
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (X0 - 3 + e < tm.D) at<T>(ring, lc.a0 + e * R::ROW) = v[e];
+    for (int e = 0; e < 4; ++e) {
+        const int x = X0 - 3 + e;
+        if (x < tm.D) ring[((x & mask) << 5) + lane] = v[e];
     }
-    lc.a0 = R::template down<0>(lc.a0, 4);
 }
 
 // ---- all levels of one base row X for one lane -----------------------------------------------------------
 // kOutQ: the last level is stored straight to the public layout (`out_ptr` = &out[0][lane's column]; the
 // last pass has psi = 0, so every lane is at the same offset d = X + M: one coalesced row piece).
-// kGuard = false: base rows where every term of every level exists for every lane of the warp
-// (interior_range): no comparisons, no selects.
-template <typename T, int M, bool kOutQ, bool kGuard, int t = 1>
-ADRT_HD void all_levels(char *ring, LaneConst<M> &lc, int n, int X, LaneState<T, M> &st, T *out_ptr)
+template <typename T, int M, bool kOutQ, int t = 1>
+ADRT_HD void all_levels(T *ring, const LaneConst<M> &lc, int n, int X, LaneState<T, M> &st, T *out_ptr)
 {
-    using R = Ring<T, M>;
     if constexpr (t <= M) {
-        const T first = at<T>(ring, lc.aF[t]);
-        const T second = at<T>(ring, lc.aS[t]);
-        T acc;
-        bool in = true;
-        if constexpr (kGuard) {
-            acc = X <= lc.thr1[t] ? T(0) + first : T(0);
-            acc = X <= lc.thr2[t] ? acc - second : acc;
-            acc = X < lc.hi[t] ? acc + st.prev[t] : acc;
-            in = X >= lc.lo[t] && X <= lc.hi[t];
-        } else {
-            acc = ((T(0) + first) - second) + st.prev[t];
-        }
-        if (in) {
+        constexpr int mask = Geo<M>::depth(t - 1) - 1;
+        const int x = X + t;
+        const T first = ring[lc.colF[t] + (((x + lc.dF[t]) & mask) << 5)];
+        const T second = ring[lc.colS[t] + (((x + lc.dS[t]) & mask) << 5)];
+        T acc = X <= lc.thr1[t] ? T(0) + first : T(0);
+        acc = X <= lc.thr2[t] ? acc - second : acc;
+        acc = X < lc.hi[t] ? acc + st.prev[t] : acc;
+        if (X >= lc.lo[t] && X <= lc.hi[t]) {
             st.prev[t] = acc;
-            if constexpr (t == M && kOutQ) out_ptr[(long long)(X + t) * n] = acc;
-            else at<T>(ring, lc.aO[t]) = acc;
+            if constexpr (t < M) {
+                ring[lc.own[t] + ((x & (Geo<M>::depth(t) - 1)) << 5)] = acc;
+            } else if constexpr (kOutQ) {
+                out_ptr[(long long)x * n] = acc;
+            } else {
+                ring[lc.own[t] + ((x & (Geo<M>::OUT_DEPTH - 1)) << 5)] = acc;
+            }
         }
-        lc.aF[t] = R::template down<t - 1>(lc.aF[t]);
-        lc.aS[t] = R::template down<t - 1>(lc.aS[t]);
-        if constexpr (!(t == M && kOutQ)) lc.aO[t] = R::template down<t>(lc.aO[t]);
-        all_levels<T, M, kOutQ, kGuard, t + 1>(ring, lc, n, X, st, out_ptr);
+        all_levels<T, M, kOutQ, t + 1>(ring, lc, n, X, st, out_ptr);
+    }
+}
+
+// The same for base rows where every term of every level exists for every lane of the warp
+// (interior_range): no comparisons, no selects.
+template <typename T, int M, bool kOutQ, int t = 1>
+ADRT_HD void all_levels_interior(T *ring, const LaneConst<M> &lc, int n, int X, LaneState<T, M> &st, T *out_ptr)
+{
+    if constexpr (t <= M) {
+        constexpr int mask = Geo<M>::depth(t - 1) - 1;
+        const int x = X + t;
+        const T first = ring[lc.colF[t] + (((x + lc.dF[t]) & mask) << 5)];
+        const T second = ring[lc.colS[t] + (((x + lc.dS[t]) & mask) << 5)];
+        const T acc = ((T(0) + first) - second) + st.prev[t];
+        st.prev[t] = acc;
+        if constexpr (t < M) {
+            ring[lc.own[t] + ((x & (Geo<M>::depth(t) - 1)) << 5)] = acc;
+        } else if constexpr (kOutQ) {
+            out_ptr[(long long)x * n] = acc;
+        } else {
+            ring[lc.own[t] + ((x & (Geo<M>::OUT_DEPTH - 1)) << 5)] = acc;
+        }
+        all_levels_interior<T, M, kOutQ, t + 1>(ring, lc, n, X, st, out_ptr);
     }
 }
 
@@ -246,16 +236,15 @@ ADRT_HD void interior_range(const LaneConst<M> &lc, bool active, int &lo, int &h
 // X0 - 3 + M - psi: flush the one aligned group of four offsets that became complete in this trip.
 // `row_ptr`: the lane's workspace row (&W[output column][0]); psi = c0 * lambda.
 template <typename T, int M>
-ADRT_HD void flush_outputs(const char *ring, const Team &tm, int psi, int lane, int X0, T *row_ptr)
+ADRT_HD void flush_outputs(const T *ring, const Team &tm, int psi, int lane, int X0, T *row_ptr)
 {
-    using R = Ring<T, M>;
     if (!tm.active) return;
     const int lo = X0 - 3 + M - psi;           // lowest offset computed so far
     const int d0 = (lo + 3) & ~3;              // lowest complete aligned group
     if (d0 < 0 || d0 >= 2 * tm.n) return;
     T w[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) w[e] = at<T>(ring, R::template cell<M>(d0 + e + psi, lane));
+    for (int e = 0; e < 4; ++e) w[e] = ring[Geo<M>::OUT_BASE * kLanes + lane + (((d0 + e + psi) & (Geo<M>::OUT_DEPTH - 1)) << 5)];
     constexpr int L = tile::VecOf<T>::L;
 #pragma unroll
     for (int g = 0; g < 4 / L; ++g) tile::store_cv<T>(row_ptr + d0 + g * L, &w[g * L]);

@@ -292,17 +292,14 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
     const int D = 2 * n - 1;
     const long long in_plane = kInQ ? (long long)D * n : (long long)n * 2 * n;
     const long long out_plane = kOutQ ? (long long)D * n : (long long)n * 2 * n;
-    using R = itile::Ring<T, M>;
-    // ring addresses are byte offsets from a base that is a multiple of the largest region: offset 0 here
-    std::vector<T> ring_store(R::BYTES / sizeof(T));
-    char *ring = reinterpret_cast<char *>(ring_store.data());
+    std::vector<T> ring((size_t)G::ROWS * itile::kLanes);
     for (int64_t plane = 0; plane < planes; ++plane)
         for (int w = 0; w < warps; ++w) {
             const int tp0 = w * G::TEAMS;
             const itile::Team t0 = itile::make_team<M>(n, s0, tp0);
             if (!t0.active) continue;
             const int top = itile::sweep_top(D, t0.c0 * (G::G - 1));
-            std::fill(ring_store.begin(), ring_store.end(), T(NAN));   // reads of never-written cells show up
+            std::fill(ring.begin(), ring.end(), T(NAN));   // reads of never-written cells show up
             itile::Team tm[32];
             itile::LaneState<T, M> st[32];
             itile::LaneConst<M> lc[32];
@@ -311,7 +308,7 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
             for (int lane = 0; lane < 32; ++lane) {
                 const int k = lane % G::G;
                 tm[lane] = itile::make_team<M>(n, s0, tp0 + lane / G::G);
-                itile::setup_levels<T, M>(tm[lane], (lane / G::G) * G::G, k, lane, top, lc[lane]);
+                itile::setup_levels<M>(tm[lane], (lane / G::G) * G::G, k, lane, lc[lane]);
                 ip[lane] = in + plane * in_plane + (kInQ ? tm[lane].in_col + k : (tm[lane].in_col + k) * (long long)(2 * n));
                 op[lane] = out + plane * out_plane + (kOutQ ? tm[lane].out_col + k : (tm[lane].out_col + (long long)k * tm[lane].out_stride) * (long long)(2 * n));
                 for (int t = 0; t <= M; ++t) st[lane].prev[t] = T(0);
@@ -328,18 +325,18 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
             for (int X0 = top; X0 >= -M; X0 -= 4) {
                 for (int i = 0; i < 32; ++i) {
                     const int lane = g_order ? 31 - i : i;
-                    itile::commit_inputs<T, M>(ring, tm[lane], lc[lane], X0, st[lane].v);
+                    itile::commit_inputs<T, M>(ring.data(), tm[lane], lane, X0, st[lane].v);
                     itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], X0 - 4, st[lane].v);
                 }
                 for (int u = 0; u < 4; ++u)
                     for (int i = 0; i < 32; ++i) {
                         const int lane = g_order ? 31 - i : i;
-                        if (X0 - 3 >= ilo && X0 <= ihi) itile::all_levels<T, M, kOutQ, false>(ring, lc[lane], n, X0 - u, st[lane], op[lane]);
-                        else itile::all_levels<T, M, kOutQ, true>(ring, lc[lane], n, X0 - u, st[lane], op[lane]);
+                        if (X0 - 3 >= ilo && X0 <= ihi) itile::all_levels_interior<T, M, kOutQ>(ring.data(), lc[lane], n, X0 - u, st[lane], op[lane]);
+                        else itile::all_levels<T, M, kOutQ>(ring.data(), lc[lane], n, X0 - u, st[lane], op[lane]);
                     }
                 if (!kOutQ)
                     for (int lane = 0; lane < 32; ++lane)
-                        itile::flush_outputs<T, M>(ring, tm[lane], tm[lane].c0 * (lane % G::G), lane, X0, op[lane]);
+                        itile::flush_outputs<T, M>(ring.data(), tm[lane], tm[lane].c0 * (lane % G::G), lane, X0, op[lane]);
             }
         }
 }
