@@ -36,6 +36,12 @@ def _worker(rank, world, port, q):
         local = torch.from_numpy(O.adrt(x[lo:hi]))
         full = gather_batch(local, dist)
         ok = full.numpy().tobytes() == O.adrt(x).tobytes()
+        # the inverses shard the same way (batch replicas, no exchange): exact inverse and
+        # one multigrid pass of this rank's sinograms, gathered, equal the unsharded results
+        y = O.adrt(x)
+        inv = gather_batch(torch.from_numpy(O.iadrt(y[lo:hi])), dist)
+        fmg = gather_batch(torch.from_numpy(O.iadrt_fmg_step(y[lo:hi])), dist)
+        ok = ok and inv.numpy().tobytes() == O.iadrt(y).tobytes() and fmg.numpy().tobytes() == O.iadrt_fmg_step(y).tobytes()
         t = max_over_ranks(10.0 + rank, dist)
         q.put((rank, lo, hi, ok, t))
     finally:

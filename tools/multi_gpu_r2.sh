@@ -23,4 +23,10 @@ for G in 2 4 8; do
   timeout 300 $TR --nproc-per-node $G --master-port $((29700+G)) tools/cg_sharded.py 8192 4 2>&1 | grep -E "^\{|Error" | tee -a $OUT/r02_cg_sharded.jsonl
 done
 ADRT_B200_SHARD_PARTS=2 timeout 300 $TR --nproc-per-node 4 --master-port 29720 tools/cg_sharded.py 8192 4 2>&1 | grep -E "^\{|Error" | tee -a $OUT/r02_cg_sharded.jsonl
+# inverses, batch sharded (16 x 2048^2 fp32 split over the ranks)
+: > $OUT/r02_inverse_sharded.jsonl
+timeout 200 python tools/inverse_sharded.py 16 2048 2>&1 | grep "^{" | tee -a $OUT/r02_inverse_sharded.jsonl
+for G in 2 4 8; do
+  timeout 300 $TR --nproc-per-node $G --master-port $((29800+G)) tools/inverse_sharded.py 16 2048 2>&1 | grep -E "^\{|Error" | tee -a $OUT/r02_inverse_sharded.jsonl
+done
 nvidia-smi topo -m > $OUT/r02_topo.txt 2>&1
