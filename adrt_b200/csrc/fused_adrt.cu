@@ -73,11 +73,13 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
     c.d0 = blockIdx.x * Prog::TD;
     c.next_g = a.next_g;
     c.d_need = a.d_need;
+    c.sup_loge = a.sup_loge;
+    c.sup_gmask = a.sup_gmask;
     c.in_pitch = a.in_pitch;
     c.out_pitch = a.out_pitch;
     c.q = 0;
     const int mode = Prog::classify(c);
-    if (mode == tile::TILE_SKIP) return;
+    if (mode == tile::TILE_SKIP || (mode == tile::TILE_ZERO && a.skip_zero)) return;
 
     for (int plane = blockIdx.z; plane < a.planes; plane += gridDim.z) {
         const T *sp;
@@ -143,6 +145,8 @@ pass_kernel_p(const T *__restrict__ src, T *__restrict__ dst, PassArgs a, SchedA
     c.e = a.e;
     c.next_g = a.next_g;
     c.d_need = a.d_need;
+    c.sup_loge = a.sup_loge;
+    c.sup_gmask = a.sup_gmask;
     c.in_pitch = a.in_pitch;
     c.out_pitch = a.out_pitch;
     c.q = 0;
@@ -155,7 +159,7 @@ pass_kernel_p(const T *__restrict__ src, T *__restrict__ dst, PassArgs a, SchedA
         c.a_g = c.g & (a.e - 1);
         c.d0 = (x + a.x_off) * Prog::TD;
         const int mode = Prog::classify(c);
-        if (mode != tile::TILE_SKIP) {
+        if (mode != tile::TILE_SKIP && !(mode == tile::TILE_ZERO && a.skip_zero)) {
             const T *sp;
             if (LOADK == tile::LOAD_IMAGE) {
                 const int gp = plane + a.plane0;
@@ -384,6 +388,7 @@ int run_plan_cosched(const plan::Plan &pl, const CoCfg &cc, const T *in, T *out,
         const plan::Pass &p = pl.pass[i];
         PassArgs a;
         a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g; a.d_need = p.d_need;
+            a.skip_zero = p.skip_zero; a.sup_loge = p.sup_loge; a.sup_gmask = p.sup_gmask;
         a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
         a.planes = (int)total;
         a.x_off = 0;
@@ -496,6 +501,7 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
             const plan::Pass &p = pl.pass[i];
             PassArgs a;
             a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g; a.d_need = p.d_need;
+            a.skip_zero = p.skip_zero; a.sup_loge = p.sup_loge; a.sup_gmask = p.sup_gmask;
             a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
             a.planes = np;
             a.x_off = 0;
@@ -562,6 +568,7 @@ int run_part(const plan::Plan &pl, const T *in, T *out, T *xbuf, int64_t total, 
         q.grid_y = yr.y_cnt;
         PassArgs a;
         a.n = n; a.D = D; a.e = 1 << p.s; a.loge = p.s; a.next_g = p.next_g; a.d_need = p.d_need;
+            a.skip_zero = p.skip_zero; a.sup_loge = p.sup_loge; a.sup_gmask = p.sup_gmask;
         a.in_pitch = p.in_pitch; a.out_pitch = p.out_pitch;
         a.planes = (int)total;
         a.x_off = 0;

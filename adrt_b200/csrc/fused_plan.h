@@ -30,6 +30,11 @@ struct Pass {
     int next_g;                     // forward: group size of the pass reading this pass's workspace (0: none)
     int d_need;                     // transposed: output offsets >= d_need are not needed (tiles skipped)
     bool stream;                    // run by the streaming kernels (stream_tile.h) instead of fused_tile.h
+    // transposed plans: this pass does not write its all-zero tiles (d0 >= D: only structural zeros of the
+    // sheared output rows) because the next pass synthesises them (TileCtx::sup_*); and the geometry of
+    // the pass that wrote this pass's input rows when that one skipped (sup_gmask < 0: it did not)
+    bool skip_zero;
+    int sup_loge, sup_gmask;
 };
 
 struct Plan {
@@ -174,6 +179,7 @@ inline bool make_forward_plan_split(int64_t n64, size_t elem_size, const std::ve
         const int TD = tile_td(p.M, p.store, p.stream);
         p.next_g = last ? 0 : (1 << ms[i + 1]);
         p.d_need = pl->D;
+        p.skip_zero = false; p.sup_loge = 0; p.sup_gmask = -1;
         const long long extent = (last && !rows_out) ? pl->D : p.out_pitch;  // offsets that must be written
         p.grid_x = (int)((extent + TD - 1) / TD);
         p.grid_y = n / G;
@@ -235,10 +241,24 @@ inline bool make_transposed_plan_split(int64_t n64, size_t elem_size, const std:
         p.stream = use_stream(p.M, elem_size, false, p.load);
         p.next_g = 0;
         p.grid_y = n / G;
+        p.skip_zero = false; p.sup_loge = 0; p.sup_gmask = -1;
         if (!last) {
             const size_t need = (size_t)n * (size_t)round4(pl->D);
             if (need > pl->ws_slot_elems[p.dst_buf]) pl->ws_slot_elems[p.dst_buf] = need;
         }
+    }
+    // A streaming pass reads its workspace rows with per-row bulk copies and fills what a row does not have
+    // from a constant source, so its producer need not write the rows' structural-zero tails: the tiles at
+    // d0 >= D (12 % of the workspace at 2048^2).  ADRT_B200_SKIP_ZERO=0 turns this off.
+    {
+        const char *env = getenv("ADRT_B200_SKIP_ZERO");
+        const bool on = !(env && atoi(env) == 0);
+        for (int i = 1; on && i < pl->npass; ++i)
+            if (pl->pass[i].stream) {
+                pl->pass[i - 1].skip_zero = true;
+                pl->pass[i].sup_loge = pl->pass[i - 1].s;
+                pl->pass[i].sup_gmask = (1 << pl->pass[i - 1].M) - 1;
+            }
     }
     // Offsets each pass must produce: an output at offset d of a pass with block height e
     // and G rows per group reads inputs at offsets < d + (e-1)*(G-1) + G (SURVEY 8a row a5');

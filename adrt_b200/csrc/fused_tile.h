@@ -95,7 +95,22 @@ struct TileCtx {
     long long in_pitch, out_pitch;   // elements per row of the R-layout workspaces (multiples of 4)
     int next_g;        // forward: group size (rows) of the pass that will read the workspace, 0 if none
     int d_need;        // transposed: only output offsets < d_need are wanted (D: all of them)
+    // transposed passes that read workspace rows of a producer which skips its all-zero tiles
+    // (plan::Pass::skip_zero): row r of the workspace is leaf j = (r >> sup_loge) & sup_gmask of the
+    // producer's group with angle a = r & ((1 << sup_loge) - 1), and holds data only at offsets below
+    // D - a*j (everything above is the structural +0.0 that the producer no longer writes);
+    // sup_gmask < 0: rows are complete up to D
+    int sup_loge, sup_gmask;
 };
+
+// first offset at which workspace row r of a transposed plan is structurally zero
+ADRT_HD int bwd_row_support(const TileCtx &c, long long r)
+{
+    if (c.sup_gmask < 0) return c.D;
+    const int a = (int)(r & ((1LL << c.sup_loge) - 1)), j = (int)((r >> c.sup_loge) & c.sup_gmask);
+    const int sup = c.D - a * j;
+    return sup;
+}
 
 // Valid offsets a tile produces.  Passes that store workspace rows give up 4
 // more offsets: a row may be shifted by up to 3 elements against the 16-byte

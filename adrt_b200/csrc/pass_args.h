@@ -17,6 +17,8 @@ struct PassArgs {
     int q_first, q_count;   // image loader: plane -> (image = plane / q_count, quadrant = q_first + plane % q_count)
     int plane0;             // image loader: index of this launch's first plane in the batch (waves, see run_plan)
     int side_idx;           // host only: which helper stream (aux_stream) takes the boundary tiles of this launch
+    int skip_zero;          // transposed: all-zero tiles are not written (plan::Pass::skip_zero)
+    int sup_loge, sup_gmask;   // transposed: geometry of the producer that skipped them (TileCtx::sup_*)
 };
 
 // Persistent, plane-ordered scheduling of one pass (sched.cuh); next == nullptr: ordinary grid launch.

@@ -41,11 +41,13 @@ stream_kernel(const float *__restrict__ src, float *__restrict__ dst, PassArgs a
     c.d0 = (blockIdx.x + a.x_off) * Prog::TD;
     c.next_g = a.next_g;
     c.d_need = a.d_need;
+    c.sup_loge = a.sup_loge;
+    c.sup_gmask = a.sup_gmask;
     c.in_pitch = a.in_pitch;
     c.out_pitch = a.out_pitch;
     c.q = 0;
     const int mode = Prog::classify(c);
-    if (!Prog::runs(mode)) return;
+    if (!Prog::runs(mode) || (mode == tile::TILE_ZERO && a.skip_zero)) return;
     const int tid = threadIdx.x;
     __shared__ unsigned long long bulk_bar;
     typename Prog::State st;
@@ -103,6 +105,8 @@ stream_kernel_p(const float *__restrict__ src, float *__restrict__ dst, PassArgs
     c.e = a.e;
     c.next_g = a.next_g;
     c.d_need = a.d_need;
+    c.sup_loge = a.sup_loge;
+    c.sup_gmask = a.sup_gmask;
     c.in_pitch = a.in_pitch;
     c.out_pitch = a.out_pitch;
     c.q = 0;
@@ -117,7 +121,7 @@ stream_kernel_p(const float *__restrict__ src, float *__restrict__ dst, PassArgs
         c.a_g = c.g & (a.e - 1);
         c.d0 = (x + a.x_off) * Prog::TD;
         const int mode = Prog::classify(c);
-        if (Prog::runs(mode)) {
+        if (Prog::runs(mode) && !(mode == tile::TILE_ZERO && a.skip_zero)) {
             const float *sp;
             if (Prog::kImage) {
                 const int gp = plane + a.plane0;

@@ -1048,9 +1048,10 @@ ADRT_HD void bwd_load_wrows(float *buf, const float *src_plane, const TileCtx &c
     bulk_fence();
     if (tid < G) {
         const int A = tid;
-        const float *row = src_plane + ((long long)c.g * G + A) * c.in_pitch + c.d0;
+        const long long r = (long long)c.g * G + A;
+        const float *row = src_plane + r * c.in_pitch + c.d0;
         float *dst = buf + RowMap<M, kRev, false>::out_row(A) * P;
-        int xv = c.D - c.d0;             // columns that exist
+        int xv = tile::bwd_row_support(c, r) - c.d0;   // columns that exist (the producer may have skipped the row's zero tail)
         if (xv > XW) xv = XW;
         if (xv < 0) xv = 0;
         const int xb = xv & ~3;          // whole chunks

@@ -43,10 +43,11 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
                 c.d0 = bx * Prog::TD;
                 c.next_g = p.next_g;
                 c.d_need = p.d_need;
+                c.sup_loge = p.sup_loge; c.sup_gmask = p.sup_gmask;
                 c.in_pitch = p.in_pitch; c.out_pitch = p.out_pitch;
                 c.q = 0;
                 const int mode = Prog::classify(c);
-                if (mode == tile::TILE_SKIP) continue;
+                if (mode == tile::TILE_SKIP || (mode == tile::TILE_ZERO && p.skip_zero)) continue;
                 const T *sp;
                 if (LOADK == tile::LOAD_IMAGE) { c.q = plane & 3; sp = src + (long long)(plane >> 2) * sps; }
                 else sp = src + (long long)plane * sps;
@@ -88,10 +89,11 @@ void run_stream_pass(const plan::Pass &p, const float *src, float *dst, int n, i
                 c.d0 = bx * Prog::TD;
                 c.next_g = p.next_g;
                 c.d_need = p.d_need;
+                c.sup_loge = p.sup_loge; c.sup_gmask = p.sup_gmask;
                 c.in_pitch = p.in_pitch; c.out_pitch = p.out_pitch;
                 c.q = 0;
                 const int mode = Prog::classify(c);
-                if (mode == tile::TILE_SKIP) continue;
+                if (mode == tile::TILE_SKIP || (mode == tile::TILE_ZERO && p.skip_zero)) continue;
                 if (!Prog::runs(mode)) continue;
                 const float *sp;
                 if (image_loader) { c.q = plane & 3; sp = src + (long long)(plane >> 2) * sps; }
