@@ -226,20 +226,34 @@ int get_interp_table(int device, int64_t n, int dtype, cudaStream_t s, InterpTab
     }
     InterpTable tab;
     const size_t fsz = dtype == ADRT_B200_F64 ? sizeof(double) : sizeof(float);
-    ADRT_CUDA_CHECK(cudaMalloc(&tab.t, n * sizeof(float)));
-    ADRT_CUDA_CHECK(cudaMalloc(&tab.base, W * sizeof(int32_t)));
-    ADRT_CUDA_CHECK(cudaMalloc(&tab.h_base, W * sizeof(float)));
-    ADRT_CUDA_CHECK(cudaMalloc(&tab.cosv, W * sizeof(float)));
-    ADRT_CUDA_CHECK(cudaMalloc(&tab.sgn, W * sizeof(int32_t)));
-    ADRT_CUDA_CHECK(cudaMalloc(&tab.factor, W * fsz));
-    // synchronous copies from pageable memory: the vectors die at scope exit
-    ADRT_CUDA_CHECK(cudaMemcpy(tab.t, t.data(), n * sizeof(float), cudaMemcpyHostToDevice));
-    ADRT_CUDA_CHECK(cudaMemcpy(tab.base, base.data(), W * sizeof(int32_t), cudaMemcpyHostToDevice));
-    ADRT_CUDA_CHECK(cudaMemcpy(tab.h_base, hb.data(), W * sizeof(float), cudaMemcpyHostToDevice));
-    ADRT_CUDA_CHECK(cudaMemcpy(tab.cosv, cv.data(), W * sizeof(float), cudaMemcpyHostToDevice));
-    ADRT_CUDA_CHECK(cudaMemcpy(tab.sgn, sg.data(), W * sizeof(int32_t), cudaMemcpyHostToDevice));
-    ADRT_CUDA_CHECK(cudaMemcpy(tab.factor, dtype == ADRT_B200_F64 ? (void *)f64.data() : (void *)f32.data(),
-                               W * fsz, cudaMemcpyHostToDevice));
+    // One allocation for the six tables (256-byte aligned pieces): nothing to unwind piecewise when
+    // an allocation or a copy fails.  Synchronous copies from pageable memory: the vectors die at
+    // scope exit.  (First use of an (n, dtype) on a device therefore must not happen inside a stream
+    // capture; later calls only launch the gather kernel.)
+    auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t o_t = 0, o_base = o_t + pad(n * sizeof(float)), o_hb = o_base + pad(W * sizeof(int32_t)),
+                 o_cos = o_hb + pad(W * sizeof(float)), o_sgn = o_cos + pad(W * sizeof(float)),
+                 o_fac = o_sgn + pad(W * sizeof(int32_t)), total = o_fac + pad(W * fsz);
+    char *blob = nullptr;
+    ADRT_CUDA_CHECK(cudaMalloc(&blob, total));
+    auto up = [&](size_t off, const void *src, size_t bytes) { return cudaMemcpy(blob + off, src, bytes, cudaMemcpyHostToDevice); };
+    cudaError_t ce = up(o_t, t.data(), n * sizeof(float));
+    if (ce == cudaSuccess) ce = up(o_base, base.data(), W * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = up(o_hb, hb.data(), W * sizeof(float));
+    if (ce == cudaSuccess) ce = up(o_cos, cv.data(), W * sizeof(float));
+    if (ce == cudaSuccess) ce = up(o_sgn, sg.data(), W * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = up(o_fac, dtype == ADRT_B200_F64 ? (const void *)f64.data() : (const void *)f32.data(), W * fsz);
+    if (ce != cudaSuccess) {
+        cudaFree(blob);
+        set_error("interp_to_cart table upload failed: %s", cudaGetErrorString(ce));
+        return ADRT_B200_ECUDA;
+    }
+    tab.t = reinterpret_cast<float *>(blob + o_t);
+    tab.base = reinterpret_cast<int32_t *>(blob + o_base);
+    tab.h_base = reinterpret_cast<float *>(blob + o_hb);
+    tab.cosv = reinterpret_cast<float *>(blob + o_cos);
+    tab.sgn = reinterpret_cast<int32_t *>(blob + o_sgn);
+    tab.factor = blob + o_fac;
     (void)s;
     g_interp_cache[key] = tab;
     *out = tab;
