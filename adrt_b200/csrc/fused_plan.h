@@ -249,10 +249,12 @@ inline bool make_transposed_plan_split(int64_t n64, size_t elem_size, const std:
     }
     // A streaming pass reads its workspace rows with per-row bulk copies and fills what a row does not have
     // from a constant source, so its producer need not write the rows' structural-zero tails: the tiles at
-    // d0 >= D (12 % of the workspace at 2048^2).  ADRT_B200_SKIP_ZERO=0 turns this off.
+    // d0 >= D (12 % of the workspace at 2048^2).  Opt-in (ADRT_B200_SKIP_ZERO=1): bit-identical, but measured
+    // 2-3 % SLOWER (64 x 2048^2 bdrt 6.36 -> 6.55 ms, profiles/r02_skipzero.jsonl) -- a clipped row costs a
+    // second bulk copy from the constant source, which is worth more than the DRAM bytes it saves.
     {
         const char *env = getenv("ADRT_B200_SKIP_ZERO");
-        const bool on = !(env && atoi(env) == 0);
+        const bool on = env && atoi(env) != 0;
         for (int i = 1; on && i < pl->npass; ++i)
             if (pl->pass[i].stream) {
                 pl->pass[i - 1].skip_zero = true;

@@ -296,3 +296,16 @@ def test_fused_iadrt(emu, n, split, dt):
     finally:
         emu.emu_set_order(0)
         os.environ.pop("ADRT_B200_IADRT_SPLIT", None)
+
+
+def test_bdrt_zero_tile_skipping(emu):
+    """ADRT_B200_SKIP_ZERO=1 (opt-in): the producer of a streaming transposed pass does not write its all-zero
+    tiles and the streaming loader clips every workspace row at its support D - a*j; the emulator's
+    workspaces start as NaN, so any read of an unwritten cell would surface."""
+    os.environ["ADRT_B200_SKIP_ZERO"] = "1"
+    try:
+        _check_stream(emu, 512, "3,6", 300)
+        _check_stream(emu, 1024, None, 1024)
+        _check(emu, 256, 1, np.float32)
+    finally:
+        os.environ.pop("ADRT_B200_SKIP_ZERO", None)
