@@ -222,14 +222,106 @@ def _part_backprojection(x, q_first: int, q_count: int, part: int, parts: int, b
     return out.view(B, q_count, D, n)[:, :, :n, cols].contiguous()
 
 
+def _slab_mean(piece, rank: int, world: int, per: int, parts: int, dist):
+    """Quadrant mean of the ranks' shares WITHOUT gathering them everywhere.
+
+    `piece` ``(B, per, n, w)``: this rank's offsets ``d < n`` / columns ``[p*w, (p+1)*w)`` of its
+    group's quadrants.  The result is cut into `world` slabs of ``h = n / world`` image rows; rank k
+    receives exactly the four pieces of the truncated quadrants that cover its slab -- row blocks of
+    the untransposed quadrants 1, 2 from the `parts` ranks of those quadrants, one column block of
+    each transposed quadrant 0, 3 (utils.truncate orientation, utils.py:234-242) -- sums them in
+    NumPy's order ``((t0 + t1) + t2) + t3`` and divides by 4 (the arithmetic of the ``truncate_mean``
+    kernel with divisor 1, hence the same bits), and ONE all-gather of the slabs replicates the
+    result.  Per rank ``4 n^2 / world`` elements arrive instead of ``4 n^2 (world - 1) / world``."""
+    import torch
+
+    B, n, w = int(piece.shape[0]), int(piece.shape[2]), int(piece.shape[3])
+    h = n // world
+    grp_of = lambda q: q // per                 # noqa: E731
+    my_grp, my_p = divmod(rank, parts)
+    my_quads = range(my_grp * per, (my_grp + 1) * per)
+
+    def block(q, k):
+        """What the owner of (quadrant q, column block my_p) holds for slab k, or None."""
+        i = q - my_grp * per
+        if q == 2:
+            return piece[:, i, k * h:(k + 1) * h, :]
+        if q == 1:
+            return piece[:, i, n - (k + 1) * h:n - k * h, :]
+        lo = k * h if q == 0 else n - (k + 1) * h           # the columns of z_q that slab k needs
+        if lo // w != my_p:
+            return None
+        return piece[:, i, :, lo - my_p * w:lo - my_p * w + h]
+
+    def block_shape(q, k, p):
+        if q in (1, 2):
+            return (B, h, w)
+        lo = k * h if q == 0 else n - (k + 1) * h
+        return (B, n, h) if lo // w == p else None
+
+    # messages: one flat tensor per (source, destination) pair, the source's blocks for that slab in quadrant order
+    sends, recvs, ops = {}, {}, []
+    for k in range(world):
+        blocks = [b for b in (block(q, k) for q in my_quads) if b is not None]
+        if blocks:
+            sends[k] = torch.cat([b.reshape(-1) for b in blocks])
+    for src in range(world):
+        g, p = divmod(src, parts)
+        shapes = [(q, sh) for q in range(g * per, (g + 1) * per) for sh in [block_shape(q, rank, p)] if sh is not None]
+        if shapes:
+            recvs[src] = shapes
+    bufs = {}
+    for src, shapes in recvs.items():
+        if src == rank:
+            bufs[src] = sends[rank]
+            continue
+        count = sum(a * b * c for _, (a, b, c) in shapes)
+        bufs[src] = torch.empty(count, dtype=piece.dtype, device=piece.device)
+        ops.append(dist.P2POp(dist.irecv, bufs[src], src))
+    for k, t in sends.items():
+        if k != rank:
+            ops.append(dist.P2POp(dist.isend, t, k))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    # assemble the four oriented slabs (B, h, n)
+    T = [None] * 4
+    for src, shapes in recvs.items():
+        _, p = divmod(src, parts)
+        off = 0
+        for q, sh in shapes:
+            cnt = sh[0] * sh[1] * sh[2]
+            raw = bufs[src][off:off + cnt].view(sh)
+            off += cnt
+            if q in (1, 2):
+                if T[q] is None:
+                    T[q] = torch.empty((B, h, n), dtype=piece.dtype, device=piece.device)
+                T[q][:, :, p * w:(p + 1) * w] = raw.flip(-2) if q == 1 else raw
+            elif q == 0:
+                T[0] = raw.flip(-2).transpose(-1, -2)
+            else:
+                T[3] = raw.flip((-1, -2)).transpose(-1, -2)
+    slab = ((((T[0] + T[1]) + T[2]) + T[3]) / 4).contiguous()
+    out = torch.empty((world, B, h, n), dtype=piece.dtype, device=piece.device)
+    try:
+        dist.all_gather_into_tensor(out, slab)
+    except (RuntimeError, NotImplementedError):
+        lst = [torch.empty_like(slab) for _ in range(world)]
+        dist.all_gather(lst, slab)
+        out = torch.stack(lst, dim=0)
+    return out.permute(1, 0, 2, 3).reshape(B, n, n)
+
+
 def sharded_normal_operator(x, dist=None, *, local_fn=_local_rows, finish_fn=_finish_mean, parts=None):
     """``mean_q(truncate(bdrt(adrt(x))))`` with ONE image (or batch) spread over the ranks
     of the default process group: by quadrant up to 4 ranks, by quadrant x angle block
     beyond (8 ranks = 4 quadrants x 2 angle halves).  `x` ``(n, n)`` or ``(B, n, n)`` must
     be replicated on every rank; the result is replicated too and bit-identical to the
-    single-GPU ``recipes.normal_operator``: every rank back-projects its share, ONE
-    all-gather hands every rank all shares, and the quadrant mean is the same
-    ``truncate_mean`` kernel (same summation order) the single-GPU path runs.
+    single-GPU ``recipes.normal_operator``: every rank back-projects its share, receives
+    the pieces of the four truncated quadrants that cover its slab of the result, sums them in
+    the ``truncate_mean`` kernel's order, and one all-gather of the slabs replicates the result
+    (``_slab_mean``; ``ADRT_B200_SHARD_GATHER=1`` selects the older form: all-gather of all shares
+    + the ``truncate_mean`` kernel over them).
     `local_fn` / `finish_fn` are overridable so that CPU tests can exercise the exchanges
     with the oracle."""
     import torch
@@ -244,6 +336,13 @@ def sharded_normal_operator(x, dist=None, *, local_fn=_local_rows, finish_fn=_fi
     B, n = int(xb.shape[0]), int(xb.shape[-1])
     w = n // parts
     piece = local_fn(xb, q_first, q_count, part, parts, rank - part, dist)       # (B, per, n, w)
+    import os
+
+    if (world > 1 and finish_fn is _finish_mean and n % world == 0 and n // world >= 1
+            and os.environ.get("ADRT_B200_SHARD_GATHER", "0") == "0"):
+        # default: every rank receives only what covers its slab of the result (_slab_mean)
+        res = _slab_mean(piece, rank, world, per, parts, dist)
+        return res[0] if squeeze else res
     if world == 1:
         flat = piece[None]
     else:

@@ -76,10 +76,24 @@ def _worker_quadrants(rank, world, port, q):
         got = sharded_normal_operator(x, dist, local_fn=oracle_fn, finish_fn=oracle_finish).numpy()
         # the same with the two ranks sharing every quadrant as angle halves (columns of the back-projection)
         got2 = sharded_normal_operator(x, dist, local_fn=oracle_fn, finish_fn=oracle_finish, parts=2).numpy()
+        # default finish: slab exchange + ordered local sum + all-gather of the slabs (_slab_mean), both layouts,
+        # single image and batch
+        y = O.bdrt(O.adrt(x.numpy()))
+        t = O.truncate(y)
+        xb3 = torch.from_numpy(np.random.default_rng(4).standard_normal((3, n, n)))
+        yb = O.bdrt(O.adrt(xb3.numpy()))
+        tb = O.truncate(yb)
+        wantb = (((tb[:, 0] + tb[:, 1]) + tb[:, 2]) + tb[:, 3]) / 4
+        ok_slab = True
+        for pp in (1, 2):
+            g1 = sharded_normal_operator(x, dist, local_fn=oracle_fn, parts=pp).numpy()
+            g3 = sharded_normal_operator(xb3, dist, local_fn=oracle_fn, parts=pp).numpy()
+            ok_slab = ok_slab and g1.tobytes() == ((((t[0] + t[1]) + t[2]) + t[3]) / 4).tobytes() and g3.tobytes() == wantb.tobytes()
         y = O.bdrt(O.adrt(x.numpy()))
         t = O.truncate(y)
         want = (((t[0] + t[1]) + t[2]) + t[3]) / 4
-        q.put((rank, quadrant_owner_range(world, rank), got.tobytes() == want.tobytes() and got2.tobytes() == want.tobytes()))
+        q.put((rank, quadrant_owner_range(world, rank),
+               got.tobytes() == want.tobytes() and got2.tobytes() == want.tobytes() and ok_slab))
     finally:
         dist.destroy_process_group()
 
