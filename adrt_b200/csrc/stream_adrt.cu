@@ -229,6 +229,12 @@ int launch_bwd(const plan::Pass &p, const float *src, float *dst, const PassArgs
     if (xm > p.grid_x) xm = p.grid_x;
     const int nmask = p.grid_x - xm;
     cudaStream_t side = (xm > 0 && nmask > 0) ? aux_stream(a.side_idx) : nullptr;
+    // the helper streams are shared per device: while the caller's stream is being captured into a graph the
+    // boundary tiles simply follow on the caller's stream (a fork into a shared stream would pull every other
+    // user of that stream into the capture)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (side && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) side = nullptr;
+    (void)cudaGetLastError();
     cudaEvent_t fork = nullptr, join = nullptr;
     if (side) {
         if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
