@@ -257,7 +257,8 @@ template <typename T, bool kForward>
 int dispatch_pass(const plan::Pass &p, const T *src, T *dst, const PassArgs &a, cudaStream_t s)
 {
     if (p.stream) {
-        if constexpr (std::is_same<T, float>::value) return launch_stream_pass(p, kForward, src, dst, a, s);
+        if constexpr (std::is_same<T, float>::value)
+            return p.staged ? launch_staged_pass(p, kForward, src, dst, a, s) : launch_stream_pass(p, kForward, src, dst, a, s);
         set_error("internal: streaming passes are fp32 only");
         return ADRT_B200_EINVAL;
     }
@@ -352,7 +353,7 @@ CoCfg cosched_config(const plan::Plan &pl, int64_t total_planes)
         if ((double)total_planes * pl.pass[i].grid_x * pl.pass[i].grid_y >= 4.0e9) c.on = false;
     // the masked / per-M kernels instantiated for co-scheduling
     for (int i = 0; i < 2; ++i)
-        if (!pl.pass[i].stream && (pl.pass[i].M < 4 || pl.pass[i].M > 6)) c.on = false;
+        if ((!pl.pass[i].stream && (pl.pass[i].M < 4 || pl.pass[i].M > 6)) || pl.pass[i].staged) c.on = false;
     return c;
 }
 

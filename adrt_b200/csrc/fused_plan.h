@@ -30,6 +30,7 @@ struct Pass {
     int next_g;                     // forward: group size of the pass reading this pass's workspace (0: none)
     int d_need;                     // transposed: output offsets >= d_need are not needed (tiles skipped)
     bool stream;                    // run by the streaming kernels (stream_tile.h) instead of fused_tile.h
+    bool staged;                    // ... by their staged variants (stage_tile.h: TMA-fed, persistent); implies stream
     // transposed plans: this pass does not write its all-zero tiles (d0 >= D: only structural zeros of the
     // sheared output rows) because the next pass synthesises them (TileCtx::sup_*); and the geometry of
     // the pass that wrote this pass's input rows when that one skipped (sup_gmask < 0: it did not)
@@ -126,6 +127,20 @@ inline bool use_stream(int M, size_t elem_size, bool forward, int load)
     return strstr(set, key) != nullptr;
 }
 
+// Which passes the staged kernels (stage_tile.h) take: the fp32 five-stage passes that read the public
+// layout and store workspace rows -- "f5p" (images) and "b5p" (sinograms).  ADRT_B200_STAGE_SET overrides
+// the default set ("" = none).  Default "f5p": 64 x 2048^2 adrt 4.75 -> 4.50 ms, 64 x 1024^2 1.27 -> 1.19 ms;
+// "b5p" is bit-identical too but slower than the fused_tile.h kernel with its fused loader (bdrt 6.37 ->
+// 9.1 ms: its masked boundary tiles cost 7x an interior tile), profiles/s5_*.
+inline bool use_staged(int M, size_t elem_size, bool forward, int load, int store)
+{
+    if (elem_size != 4 || M != 5 || store != tile::STORE_WROWS) return false;
+    if (load != (forward ? tile::LOAD_IMAGE : tile::LOAD_QCOLS)) return false;
+    const char *set = getenv("ADRT_B200_STAGE_SET");
+    if (!set) set = "f5p";
+    return strstr(set, forward ? "f5p" : "b5p") != nullptr;
+}
+
 // `rows_out`: the last pass stores its result as R-layout rows (row = angle, pitch round4(D), logical
 // positions, zeros above each row's support) into the caller's buffer instead of the public (d, column)
 // layout -- the format the first pass of a transposed plan built with `rows_in` loads.  The fused
@@ -175,7 +190,8 @@ inline bool make_forward_plan_split(int64_t n64, size_t elem_size, const std::ve
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        p.stream = use_stream(p.M, elem_size, true, p.load);
+        p.staged = use_staged(p.M, elem_size, true, p.load, p.store);
+        p.stream = p.staged || use_stream(p.M, elem_size, true, p.load);
         const int TD = tile_td(p.M, p.store, p.stream);
         p.next_g = last ? 0 : (1 << ms[i + 1]);
         p.d_need = pl->D;
@@ -238,7 +254,8 @@ inline bool make_transposed_plan_split(int64_t n64, size_t elem_size, const std:
         p.src_buf = first ? -1 : (i - 1) & 1;
         p.dst_buf = last ? -1 : i & 1;
         const int G = 1 << p.M;
-        p.stream = use_stream(p.M, elem_size, false, p.load);
+        p.staged = use_staged(p.M, elem_size, false, p.load, p.store);
+        p.stream = p.staged || use_stream(p.M, elem_size, false, p.load);
         p.next_g = 0;
         p.grid_y = n / G;
         p.skip_zero = false; p.sup_loge = 0; p.sup_gmask = -1;

@@ -14,6 +14,7 @@
 
 #include "../../adrt_b200/csrc/fused_plan.h"
 #include "../../adrt_b200/csrc/iadrt_tile.h"
+#include "../../adrt_b200/csrc/stage_tile.h"
 
 using namespace adrt_b200;
 
@@ -115,6 +116,62 @@ void run_stream_pass(const plan::Pass &p, const float *src, float *dst, int n, i
             }
 }
 
+// Staged passes (stage_tile.h): the tensor-map / bulk copies are played by the host branch of
+// sgtile::tma_load_box / stile::bulk_load / sgtile::bulk_store; every tile runs its five phases in order
+// (the GPU kernel swaps the two buffers from tile to tile and issues phase 0 of a CTA's next tile early
+// -- an ordering the barriers protect, not the arithmetic).
+long long g_staged_tiles = 0;
+template <typename Prog>
+void run_staged_pass(const plan::Pass &p, const float *src, float *dst, int n, int D, int planes, long long sps, long long dps,
+                     bool image_loader)
+{
+    const size_t cells = 2 * (size_t)sgtile::STG_FLOATS + 64;
+    std::vector<tile::Pack<float>> storeA(cells / 4 + 1);
+    float *stg = reinterpret_cast<float *>(storeA.data());
+    float *buf = stg + sgtile::STG_FLOATS;
+    std::vector<typename Prog::State> states(Prog::NT);
+    const int e = 1 << p.s;
+    sgtile::TmaMap tm;
+    tm.base = src;
+    tm.dim0 = n;
+    tm.dim1 = image_loader ? n : D;
+    tm.dim2 = image_loader ? (planes + 3) / 4 : planes;
+    tm.stride1 = n;
+    tm.stride2 = sps;
+    const int y_lo = g_y_cnt < 0 ? 0 : g_y_off, y_hi = g_y_cnt < 0 ? p.grid_y : g_y_off + g_y_cnt;
+    for (int plane = 0; plane < planes; ++plane)
+        for (int by = y_lo; by < y_hi; ++by)
+            for (int bx = 0; bx < p.grid_x; ++bx) {
+                tile::TileCtx c;
+                c.n = n; c.D = D; c.e = e; c.g = by; c.k0 = by / e; c.a_g = by % e;
+                c.d0 = bx * Prog::TD;
+                c.next_g = p.next_g;
+                c.d_need = p.d_need;
+                c.sup_loge = p.sup_loge; c.sup_gmask = p.sup_gmask;
+                c.in_pitch = p.in_pitch; c.out_pitch = p.out_pitch;
+                c.q = 0;
+                const int mode = Prog::classify(c);
+                if (mode == tile::TILE_SKIP || (mode == tile::TILE_ZERO && p.skip_zero)) continue;
+                if (!Prog::runs(mode)) continue;
+                int lplane = plane;
+                if (image_loader) { c.q = plane & 3; lplane = plane >> 2; }
+                float *dp = dst + (long long)plane * dps;
+                for (size_t i = 0; i < cells; ++i) stg[i] = 1e30f;
+                if (mode == tile::TILE_ZERO) {
+                    for (int tid = 0; tid < Prog::NT; ++tid) Prog::zero_tile(buf, dp, c, tid);
+                    continue;
+                }
+                ++g_staged_tiles;
+                unsigned long long fake_bar = 0;
+                for (int tid = 0; tid < Prog::NT; ++tid) stile::bulk_init(states[tid].bar, &fake_bar, Prog::NT, tid);
+                for (int ph = 0; ph < Prog::kPhases; ++ph)
+                    for (int i = 0; i < Prog::NT; ++i) {
+                        const int tid = g_order ? Prog::NT - 1 - i : i;
+                        sgtile::run_phase<Prog>(ph, mode, stg, buf, states[tid], tm, src, dp, c, lplane, tid);
+                    }
+            }
+}
+
 template <int M, bool kForward>
 void run_stream_kinds(const plan::Pass &p, const float *src, float *dst, int n, int D, int planes, long long sps, long long dps)
 {
@@ -136,6 +193,14 @@ template <typename T, bool kForward>
 void run_stream(const plan::Pass &p, const T *src, T *dst, int n, int D, int planes, long long sps, long long dps)
 {
     if constexpr (std::is_same<T, float>::value) {
+        if (p.staged) {
+            if (kForward) run_staged_pass<sgtile::FwdStaged<5>>(p, src, dst, n, D, planes, sps, dps, true);
+            else {
+                run_staged_pass<sgtile::BwdStaged<5, false>>(p, src, dst, n, D, planes, sps, dps, false);
+                run_staged_pass<sgtile::BwdStaged<5, true>>(p, src, dst, n, D, planes, sps, dps, false);
+            }
+            return;
+        }
         if (p.M == 6) run_stream_kinds<6, kForward>(p, src, dst, n, D, planes, sps, dps);
         else run_stream_kinds<5, kForward>(p, src, dst, n, D, planes, sps, dps);
     }
@@ -388,6 +453,7 @@ int emu_iadrt_f32(const float *in, float *out, int64_t B, int64_t n) { return ru
 int emu_iadrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run_iadrt<double>(in, out, B, n); }
 void emu_set_order(int order) { g_order = order; }
 long long emu_stream_tiles(void) { return g_stream_tiles; }
+long long emu_staged_tiles(void) { return g_staged_tiles; }
 int emu_adrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, true>(in, out, B, n); }
 int emu_adrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run<double, true>(in, out, B, n); }
 int emu_bdrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, false>(in, out, B, n); }

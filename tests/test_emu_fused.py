@@ -20,7 +20,7 @@ SO = os.path.join(HERE, "emu", "_build", "libemu.so")
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [SRC] + [os.path.join(HERE, "..", "adrt_b200", "csrc", f) for f in ("fused_tile.h", "fused_plan.h", "stream_tile.h", "iadrt_tile.h")]
+    deps = [SRC] + [os.path.join(HERE, "..", "adrt_b200", "csrc", f) for f in ("fused_tile.h", "fused_plan.h", "stream_tile.h", "stage_tile.h", "iadrt_tile.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
@@ -138,10 +138,11 @@ def test_bdrt_rows(emu, n, rows, split):
 # that depended on the order would mean two threads race on a tile cell inside a phase.
 def _check_stream(emu, n, split, rows=None):
     emu.emu_stream_tiles.restype = ctypes.c_longlong
-    keys = ("ADRT_B200_SPLIT", "ADRT_B200_SPLIT_BDRT", "ADRT_B200_STREAM_SET")
+    keys = ("ADRT_B200_SPLIT", "ADRT_B200_SPLIT_BDRT", "ADRT_B200_STREAM_SET", "ADRT_B200_STAGE_SET")
     for k in keys:
         os.environ.pop(k, None)
     os.environ["ADRT_B200_STREAM_SET"] = "all"
+    os.environ["ADRT_B200_STAGE_SET"] = ""      # the staged variants (stage_tile.h) have their own tests below
     if split:
         os.environ["ADRT_B200_SPLIT"] = split
         os.environ["ADRT_B200_SPLIT_BDRT"] = split
@@ -192,6 +193,62 @@ def test_streaming_two_six_stage_passes(emu):
     # 6 + 5 and 5 + 6 (the 2048^2 plans) are covered through 11-stage splits of n = 2048 on the GPU.
     _check_stream(emu, 512, "6,3")
     _check_stream(emu, 512, "4,5")
+
+
+# ---------------------------------------------------------------------------------------------
+# Staged passes (adrt_b200/csrc/stage_tile.h): the five-stage fp32 passes next to the images / the
+# public-layout sinogram with their input tile delivered by tensor-map or bulk copies into a staging
+# buffer and an out-of-place first butterfly step.  ADRT_B200_STAGE_SET selects them; both thread orders.
+def _check_staged(emu, n, split, rows=None, B=1):
+    emu.emu_staged_tiles.restype = ctypes.c_longlong
+    keys = ("ADRT_B200_SPLIT", "ADRT_B200_SPLIT_BDRT", "ADRT_B200_STAGE_SET")
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ["ADRT_B200_STAGE_SET"] = "f5p,b5p"
+    if split:
+        # forward order in both: the staged pass is the first forward pass and undoes the last one
+        os.environ["ADRT_B200_SPLIT"] = split
+        os.environ["ADRT_B200_SPLIT_BDRT"] = ",".join(reversed(split.split(",")))
+    try:
+        x = make_image(11 + n, (B, n, n), np.float32)
+        want = O.adrt(x)
+        s = make_sino(13 + n, want.shape, np.float32)
+        wz = O.bdrt(s)
+        x0, s0 = np.full_like(x, -0.0), np.full_like(s, -0.0)
+        wy0, wz0 = O.adrt(x0), O.bdrt(s0)
+        for order in (0, 1):
+            emu.emu_set_order(order)
+            t0 = emu.emu_staged_tiles()
+            y = _run(emu, "emu_adrt", x, want.shape)
+            assert emu.emu_staged_tiles() > t0, "no staged tile ran"
+            assert bytes_equal(y, want), f"adrt n={n} split={split} order={order}: {first_diff(y, want)}"
+            assert bytes_equal(_run(emu, "emu_adrt", x0, want.shape), wy0), f"adrt(-0) n={n} split={split} order={order}"
+            t0 = emu.emu_staged_tiles()
+            z = _run(emu, "emu_bdrt", s, s.shape)
+            assert emu.emu_staged_tiles() > t0, "no staged tile ran"
+            assert bytes_equal(z, wz), f"bdrt n={n} split={split} order={order}: {first_diff(z, wz)}"
+            assert bytes_equal(_run(emu, "emu_bdrt", s0, s.shape), wz0), f"bdrt(-0) n={n} split={split} order={order}"
+            if rows:
+                out = np.full(s.shape, np.nan, dtype=s.dtype)
+                rc = emu.emu_bdrt_rows_f32(ctypes.c_void_p(s.ctypes.data), ctypes.c_void_p(out.ctypes.data),
+                                           ctypes.c_int64(B), ctypes.c_int64(n), ctypes.c_int64(rows))
+                assert rc == 0
+                assert bytes_equal(out[:, :, :rows], wz[:, :, :rows]), first_diff(out[:, :, :rows], wz[:, :, :rows])
+    finally:
+        emu.emu_set_order(0)
+        for k in keys:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("n,split,rows,B", [
+    (64, "5,1", None, 2),                  # one group, every tile masked, two images (plane -> image / quadrant)
+    (128, "5,2", 100, 1),                  # the staged pass first in both directions
+    (256, "5,3", None, 1),
+    (512, "5,4", 512, 1),                  # several d-tiles per group: interior and boundary tiles, row-limited
+    (1024, None, None, 1),                 # the 1024^2 plan (5 + 5)
+])
+def test_staged_passes(emu, n, split, rows, B):
+    _check_staged(emu, n, split, rows, B)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -489,11 +489,14 @@ def test_streaming_kinds_agree(n, B):
     try:
         for tag, val in (("none", ""), ("all", "all"), ("default", None)):
             os.environ.pop("ADRT_B200_STREAM_SET", None)
+            os.environ.pop("ADRT_B200_STAGE_SET", None)
             if val is not None:
                 os.environ["ADRT_B200_STREAM_SET"] = val
+                os.environ["ADRT_B200_STAGE_SET"] = ""   # the staged variants: test_staged_passes_equal_default
             got[tag] = (adrt.adrt(x), adrt.bdrt(s), adrt.bdrt(s0))
     finally:
         os.environ.pop("ADRT_B200_STREAM_SET", None)
+        os.environ.pop("ADRT_B200_STAGE_SET", None)
     for tag in ("all", "default"):
         for i, what in enumerate(("adrt", "bdrt", "bdrt(-0)")):
             _eq(got[tag][i], got["none"][i], f"{what} n={n} streaming set {tag} vs fused_tile.h kernels")
