@@ -320,8 +320,9 @@ def sharded_normal_operator(x, dist=None, *, local_fn=_local_rows, finish_fn=_fi
     single-GPU ``recipes.normal_operator``: every rank back-projects its share, receives
     the pieces of the four truncated quadrants that cover its slab of the result, sums them in
     the ``truncate_mean`` kernel's order, and one all-gather of the slabs replicates the result
-    (``_slab_mean``; ``ADRT_B200_SHARD_GATHER=1`` selects the older form: all-gather of all shares
-    + the ``truncate_mean`` kernel over them).
+    (``_slab_mean``, the default from 4 ranks on; with 2 ranks, or with ``ADRT_B200_SHARD_GATHER=1``, the
+    older form: all-gather of all shares + the ``truncate_mean`` kernel over them;
+    ``ADRT_B200_SHARD_GATHER=0`` forces the slab form).
     `local_fn` / `finish_fn` are overridable so that CPU tests can exercise the exchanges
     with the oracle."""
     import torch
@@ -338,9 +339,13 @@ def sharded_normal_operator(x, dist=None, *, local_fn=_local_rows, finish_fn=_fi
     piece = local_fn(xb, q_first, q_count, part, parts, rank - part, dist)       # (B, per, n, w)
     import os
 
-    if (world > 1 and finish_fn is _finish_mean and n % world == 0 and n // world >= 1
-            and os.environ.get("ADRT_B200_SHARD_GATHER", "0") == "0"):
-        # default: every rank receives only what covers its slab of the result (_slab_mean)
+    # measured on one 8192^2 fp32 image (profiles/r03_normal_op_sharded_8192.jsonl, gpurun_out/r2d_*): the slab
+    # exchange wins from 4 ranks on (4: 2.59 vs 2.95 ms, 8: 2.95 vs 3.69 ms); with 2 ranks its assembly passes over
+    # half-image slabs cost more than the smaller transfer saves (4.70 vs 4.03 ms)
+    gather = os.environ.get("ADRT_B200_SHARD_GATHER")
+    use_slab = (world >= 4) if gather is None else gather == "0"
+    if world > 1 and finish_fn is _finish_mean and n % world == 0 and n // world >= 1 and use_slab:
+        # every rank receives only what covers its slab of the result (_slab_mean)
         res = _slab_mean(piece, rank, world, per, parts, dist)
         return res[0] if squeeze else res
     if world == 1:

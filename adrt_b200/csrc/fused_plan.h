@@ -127,6 +127,14 @@ inline bool use_stream(int M, size_t elem_size, bool forward, int load)
     return strstr(set, key) != nullptr;
 }
 
+// ADRT_B200_STREAM_SPLIT2=1: the six-stage forward streaming pass that stores the public layout runs two
+// threads per (butterfly, segment), 128 per tile (stile::FwdStream kSplit = 2)
+inline bool stream_split2()
+{
+    const char *e = getenv("ADRT_B200_STREAM_SPLIT2");
+    return e && atoi(e) != 0;
+}
+
 // Which passes the staged kernels (stage_tile.h) take: the fp32 five-stage passes that read the public
 // layout and store workspace rows -- "f5p" (images) and "b5p" (sinograms).  ADRT_B200_STAGE_SET overrides
 // the default set ("" = none).  Default "f5p": 64 x 2048^2 adrt 4.75 -> 4.50 ms, 64 x 1024^2 1.27 -> 1.19 ms;

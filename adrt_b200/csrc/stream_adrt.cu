@@ -213,7 +213,10 @@ int dispatch_fwd(const plan::Pass &p, const float *src, float *dst, const PassAr
     if (p.load == LOAD_IMAGE && p.store == STORE_WROWS) return launch<stile::FwdStream<M, LOAD_IMAGE, STORE_WROWS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
     if (p.load == LOAD_IMAGE && p.store == STORE_QCOLS) return launch<stile::FwdStream<M, LOAD_IMAGE, STORE_QCOLS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
     if (p.load == LOAD_WROWS && p.store == STORE_WROWS) return launch<stile::FwdStream<M, LOAD_WROWS, STORE_WROWS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
-    if (p.load == LOAD_WROWS && p.store == STORE_QCOLS) return launch<stile::FwdStream<M, LOAD_WROWS, STORE_QCOLS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
+    if (p.load == LOAD_WROWS && p.store == STORE_QCOLS) {
+        if (M == 6 && plan::stream_split2()) return launch<stile::FwdStream<6, LOAD_WROWS, STORE_QCOLS, 2>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
+        return launch<stile::FwdStream<M, LOAD_WROWS, STORE_QCOLS>>(src, dst, a, 0, p.grid_x, p.grid_y, s);
+    }
     set_error("internal: bad streaming pass kinds %d/%d", p.load, p.store);
     return ADRT_B200_EINVAL;
 }

@@ -706,8 +706,12 @@ ADRT_HD void store_qcols(const float *buf, float *dst_plane, const TileCtx &c, i
 // ===========================================================================
 // Phases: 0 load | 1 step-1 prologue | 2 step-1 main | 3 step-2 prologue | 4 step-2 main | 5 store,
 // with a CTA barrier after each.
-template <int M, int LOADK, int STOREK>
+// kSplit = 2: every (butterfly, segment) of a step is shared by TWO threads (lower / upper part of the
+// segment, 5 + 4 or 4 + 3 vectors), 128 threads per tile: a tile occupies its shared memory for the copy
+// latency plus the butterflies, and the butterflies are serial per thread
+template <int M, int LOADK, int STOREK, int kSplit = 1>
 struct FwdStream {
+    static_assert(kSplit == 1 || kSplit == 2, "one or two threads per segment");
     typedef SGeo<M, true> Geo;
     static constexpr int G = Geo::G;
     static constexpr bool kRev = (STOREK == STORE_QCOLS);
@@ -722,12 +726,15 @@ struct FwdStream {
     // copied asynchronously, so those passes only need the 64 threads of the butterfly steps
     // 64 threads: the butterfly steps want ~200 registers, and a scheduler's 16K registers are shared by
     // the warps resident on it (3 CTAs x 2 warps = at most 2 warps per scheduler)
-    static constexpr int NT = 64;
+    static constexpr int NT = 64 * kSplit;
     static constexpr int NWARP = NT / 32;
     static constexpr int MIN_CTAS = (M == 6) ? 3 : 6;
     typedef FwdState<M> State;
     // a direct step 2 writes nothing to the tile: its prologue and main loop need no barrier between them
     ADRT_HD static constexpr bool barrier_after(int ph) { return !(kDirect && ph == 3); }
+    // vectors of a segment that its first thread walks (the second one takes the rest)
+    static constexpr int N1 = Geo::SEG1 / V, N1A = kSplit == 2 ? (N1 + 1) / 2 : N1, N1B = N1 - N1A;
+    static constexpr int N2 = Geo::SEG2 / V, N2A = kSplit == 2 ? (N2 + 1) / 2 : N2, N2B = N2 - N2A;
 
     ADRT_HD static int classify(const TileCtx &c)
     {
@@ -760,21 +767,28 @@ struct FwdStream {
         } else if constexpr (PH == 1 || PH == 2) {
             int base, c0;
             bool warm;
-            if (!fwd_s1_map<M, kRev>(tid, base, c0, warm)) return;
+            const int half = kSplit == 2 ? tid >> 6 : 0;    // warp uniform
+            if (!fwd_s1_map<M, kRev>(tid & 63, base, c0, warm)) return;
+            if (half) { c0 += V * N1A; warm = true; }
             if constexpr (PH == 1) fwd_step_prologue<Geo::LOGR1, false>(buf, base, RM::s1_stride, 0, c0, warm, st.s1);
-            else fwd_step_main<Geo::LOGR1, false, Geo::SEG1 / V>(buf, base, RM::s1_stride, 0, c0, st.s1);
+            else if (kSplit == 1 || !half) fwd_step_main<Geo::LOGR1, false, N1A>(buf, base, RM::s1_stride, 0, c0, st.s1);
+            else if constexpr (kSplit == 2) fwd_step_main<Geo::LOGR1, false, N1B>(buf, base, RM::s1_stride, 0, c0, st.s1);
         } else if constexpr (PH == 3 || PH == 4) {
             int base, p, c0;
-            if (!fwd_s2_map<M, kRev>(tid, base, p, c0)) return;
+            const int half = kSplit == 2 ? tid >> 6 : 0;
+            if (!fwd_s2_map<M, kRev>(tid & 63, base, p, c0)) return;
+            if (half) c0 += V * N2A;
             if constexpr (PH == 3) {
                 fwd_step_prologue<Geo::LOGR2, true>(buf, base, RM::s2_stride, p, c0, true, st.s2);
             } else if constexpr (kDirect) {
                 // tile position c0 is offset d0 + (c0 - LH); the butterfly's columns start at g*G + p*R2
                 const int d = c.d0 + (c0 - LH);
                 float *o = dst + (long long)d * c.n + c.g * G + p * Geo::R2;
-                fwd_step_main_direct<Geo::LOGR2, Geo::SEG2 / V>(buf, base, RM::s2_stride, p, c0, st.s2, o, c.n, c.D - d);
+                if (kSplit == 1 || !half) fwd_step_main_direct<Geo::LOGR2, N2A>(buf, base, RM::s2_stride, p, c0, st.s2, o, c.n, c.D - d);
+                else if constexpr (kSplit == 2) fwd_step_main_direct<Geo::LOGR2, N2B>(buf, base, RM::s2_stride, p, c0, st.s2, o, c.n, c.D - d);
             } else {
-                fwd_step_main<Geo::LOGR2, true, Geo::SEG2 / V>(buf, base, RM::s2_stride, p, c0, st.s2);
+                if (kSplit == 1 || !half) fwd_step_main<Geo::LOGR2, true, N2A>(buf, base, RM::s2_stride, p, c0, st.s2);
+                else if constexpr (kSplit == 2) fwd_step_main<Geo::LOGR2, true, N2B>(buf, base, RM::s2_stride, p, c0, st.s2);
             }
         } else {
             if (STOREK == STORE_QCOLS) store_qcols<M, kRev, TD, NWARP>(buf, dst, c, LH, false, tid);

@@ -180,6 +180,7 @@ void run_stream_kinds(const plan::Pass &p, const float *src, float *dst, int n, 
         if (p.load == LOAD_IMAGE && p.store == STORE_WROWS) run_stream_pass<stile::FwdStream<M, LOAD_IMAGE, STORE_WROWS>>(p, src, dst, n, D, planes, sps, dps, true);
         else if (p.load == LOAD_IMAGE && p.store == STORE_QCOLS) run_stream_pass<stile::FwdStream<M, LOAD_IMAGE, STORE_QCOLS>>(p, src, dst, n, D, planes, sps, dps, true);
         else if (p.load == LOAD_WROWS && p.store == STORE_WROWS) run_stream_pass<stile::FwdStream<M, LOAD_WROWS, STORE_WROWS>>(p, src, dst, n, D, planes, sps, dps, false);
+        else if (M == 6 && plan::stream_split2()) run_stream_pass<stile::FwdStream<6, LOAD_WROWS, STORE_QCOLS, 2>>(p, src, dst, n, D, planes, sps, dps, false);
         else run_stream_pass<stile::FwdStream<M, LOAD_WROWS, STORE_QCOLS>>(p, src, dst, n, D, planes, sps, dps, false);
     } else {
         if (p.load == LOAD_QCOLS && p.store == STORE_WROWS) { run_stream_pass<stile::BwdStream<M, LOAD_QCOLS, STORE_WROWS, false>>(p, src, dst, n, D, planes, sps, dps, false); run_stream_pass<stile::BwdStream<M, LOAD_QCOLS, STORE_WROWS, true>>(p, src, dst, n, D, planes, sps, dps, false); }

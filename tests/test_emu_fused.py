@@ -188,6 +188,14 @@ def test_streaming_passes(emu, n, split, rows):
     _check_stream(emu, n, split, rows)
 
 
+@pytest.mark.parametrize("n,split", [(128, "1,6"), (256, "2,6"), (512, "3,6")])
+def test_streaming_two_threads_per_segment(emu, n, split, monkeypatch):
+    # ADRT_B200_STREAM_SPLIT2: the six-stage forward pass that stores the public layout on 128 threads per tile
+    # (every segment shared by two threads); both thread orders expose a race on the in-place tile
+    monkeypatch.setenv("ADRT_B200_STREAM_SPLIT2", "1")
+    _check_stream(emu, n, split)
+
+
 def test_streaming_two_six_stage_passes(emu):
     # K = 12 = 6 + 6 (the 4096^2 plan) at the smallest size that has it is too slow to emulate;
     # 6 + 5 and 5 + 6 (the 2048^2 plans) are covered through 11-stage splits of n = 2048 on the GPU.

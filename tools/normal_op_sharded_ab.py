@@ -1,5 +1,5 @@
 """Sharded normal operator of ONE n x n image (BASELINE config 5) on the ranks of this torchrun job: the slab
-exchange (default) and the older all-gather form (ADRT_B200_SHARD_GATHER=1) timed back to back in the same
+exchange (ADRT_B200_SHARD_GATHER=0, default from 4 ranks on) and the all-gather form (=1) timed back to back in the same
 processes (CUDA events, max over ranks), each checked bit for bit against the 1-GPU operator; then CG
 iterations with the default.  One JSON line per mode from rank 0.
 usage: torchrun --nproc-per-node N tools/normal_op_sharded_ab.py [n] [iters]"""
@@ -50,7 +50,7 @@ for mode in (("slab", "0"), ("gather", "1")) if world > 1 else (("single", "0"),
     if rank == 0:
         print(json.dumps({"n": n, "world": world, "quadrants_per_group": per, "ranks_per_group": parts, "mode": mode[0],
                           "normal_operator_ms": round(float(ms.item()), 3), "bit_identical_to_1gpu": same}), flush=True)
-os.environ["ADRT_B200_SHARD_GATHER"] = os.environ.get("AB_CG_GATHER", "0")
+os.environ.pop("ADRT_B200_SHARD_GATHER", None)      # the default form for this world size
 b = adrt.adrt(img)
 
 
