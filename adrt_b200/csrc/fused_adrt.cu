@@ -258,7 +258,8 @@ int dispatch_pass(const plan::Pass &p, const T *src, T *dst, const PassArgs &a, 
 {
     if (p.stream) {
         if constexpr (std::is_same<T, float>::value)
-            return p.staged ? launch_staged_pass(p, kForward, src, dst, a, s) : launch_stream_pass(p, kForward, src, dst, a, s);
+            return p.staged && staged_pass_available() ? launch_staged_pass(p, kForward, src, dst, a, s)
+                                                       : launch_stream_pass(p, kForward, src, dst, a, s);
         set_error("internal: streaming passes are fp32 only");
         return ADRT_B200_EINVAL;
     }

@@ -58,6 +58,8 @@ cudaStream_t aux_stream(int idx);
 int launch_stream_pass(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a, cudaStream_t s);
 // staged variants of the streaming passes (plan::Pass::staged); defined in stage_adrt.cu
 int launch_staged_pass(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a, cudaStream_t s);
+// false when the driver has no tensor-map encoder: the plain streaming kernels (same tile geometry) run instead
+bool staged_pass_available();
 // persistent variant: `sc` describes the whole pass (all its d-tiles); the transposed direction splits it
 // into an interior and a boundary launch, the latter on `side` with its own work counter sc.next + 1
 int launch_stream_pass_sched(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a,

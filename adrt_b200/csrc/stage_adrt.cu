@@ -251,6 +251,8 @@ int launch_fwd5(const plan::Pass &p, const float *src, float *dst, const PassArg
 
 }  // namespace
 
+bool staged_pass_available() { return encode_fn() != nullptr; }
+
 int launch_staged_pass(const plan::Pass &p, bool forward, const float *src, float *dst, const PassArgs &a, cudaStream_t s)
 {
     if (p.M == 5 && forward && p.load == tile::LOAD_IMAGE && p.store == tile::STORE_WROWS) return launch_fwd5(p, src, dst, a, s);
