@@ -68,6 +68,10 @@ SIGNATURES = {
     "adrt_b200_truncate_mean_shares": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int, ctypes.c_double, _c_int, _c_vp]),
     "adrt_b200_sub": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "adrt_b200_add": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
+    "adrt_b200_cg_workspace_bytes": (_c_sz, []),
+    "adrt_b200_cg_dot": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_i64, _c_int, _c_vp, _c_sz, _c_vp]),
+    "adrt_b200_cg_update": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_sz, _c_vp]),
+    "adrt_b200_cg_direction": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "adrt_b200_host_adrt": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int]),
     "adrt_b200_host_bdrt": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int]),
     "adrt_b200_host_iadrt": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_int, _c_int]),

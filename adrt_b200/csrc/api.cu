@@ -822,4 +822,35 @@ int adrt_b200_add(const void *a, const void *b, void *out, int64_t count, int dt
                     launch_binary<double>((const double *)a, (const double *)b, (double *)out, count, 1, as_stream(stream)));
 }
 
+size_t adrt_b200_cg_workspace_bytes(void) { return cg_workspace_bytes(); }
+
+int adrt_b200_cg_dot(const void *a, const void *b, void *state, int slot, int64_t count, int dtype, void *ws, size_t ws_bytes,
+                     void *stream)
+{
+    ADRT_REQUIRE(a && b && state && ws && dtype_ok(dtype) && count > 0 && slot >= 0 && slot < 4, "bad argument");
+    ADRT_REQUIRE(ws_bytes >= cg_workspace_bytes(), "cg workspace too small: need %zu bytes, got %zu", cg_workspace_bytes(), ws_bytes);
+    return DISPATCH(dtype,
+                    launch_cg_dot<float>((const float *)a, (const float *)b, (double *)state, slot, count, (double *)ws, as_stream(stream)),
+                    launch_cg_dot<double>((const double *)a, (const double *)b, (double *)state, slot, count, (double *)ws, as_stream(stream)));
+}
+
+int adrt_b200_cg_update(void *x, void *r, const void *p, const void *ap, void *state, int64_t count, int dtype, void *ws,
+                        size_t ws_bytes, void *stream)
+{
+    ADRT_REQUIRE(x && r && p && ap && state && ws && dtype_ok(dtype) && count > 0, "bad argument");
+    ADRT_REQUIRE(x != r && x != p && x != ap && r != p && r != ap, "cg_update: the vectors must be distinct");
+    ADRT_REQUIRE(ws_bytes >= cg_workspace_bytes(), "cg workspace too small: need %zu bytes, got %zu", cg_workspace_bytes(), ws_bytes);
+    return DISPATCH(dtype,
+                    launch_cg_update<float>((float *)x, (float *)r, (const float *)p, (const float *)ap, (double *)state, count, (double *)ws, as_stream(stream)),
+                    launch_cg_update<double>((double *)x, (double *)r, (const double *)p, (const double *)ap, (double *)state, count, (double *)ws, as_stream(stream)));
+}
+
+int adrt_b200_cg_direction(void *p, const void *r, void *state, int64_t count, int dtype, void *stream)
+{
+    ADRT_REQUIRE(p && r && state && p != r && dtype_ok(dtype) && count > 0, "bad argument");
+    return DISPATCH(dtype,
+                    launch_cg_direction<float>((float *)p, (const float *)r, (double *)state, count, as_stream(stream)),
+                    launch_cg_direction<double>((double *)p, (const double *)r, (double *)state, count, as_stream(stream)));
+}
+
 }  // extern "C"

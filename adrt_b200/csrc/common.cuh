@@ -71,6 +71,11 @@ template <typename T> int launch_truncate_mean_shares(const T *in, T *out, int64
 template <typename T> int launch_stitch(const T *in, T *out, int64_t B, int64_t n, bool remove_repeated, cudaStream_t s);
 template <typename T> int launch_unstitch(const T *in, T *out, int64_t B, int64_t n, bool trimmed, cudaStream_t s);
 template <typename T> int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStream_t s);
+// CG vector updates (step_kernels.cu): state = {r.r, p.Ap, new r.r, ...} in double on the device
+size_t cg_workspace_bytes();
+template <typename T> int launch_cg_dot(const T *a, const T *b, double *state, int slot, int64_t count, double *partials, cudaStream_t s);
+template <typename T> int launch_cg_update(T *x, T *r, const T *p, const T *ap, double *state, int64_t count, double *partials, cudaStream_t s);
+template <typename T> int launch_cg_direction(T *p, const T *r, double *state, int64_t count, cudaStream_t s);
 
 // Fused multi-stage paths (fused_adrt.cu).  Return ADRT_B200_OK or an error;
 // `handled` is false when the shape is left to the per-stage path.

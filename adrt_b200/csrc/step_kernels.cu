@@ -769,6 +769,112 @@ int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStr
     return ADRT_B200_OK;
 }
 
+// ---------------------------------------------------------------------------
+// CG vector updates (recipes.iadrt_cg; the reference's recipe hands the normal operator to
+// scipy.sparse.linalg.cg, docs/examples.cginverse.md:40-67).  One iteration = the operator plus
+//   dot:       state[1] = p . Ap
+//   update:    alpha = state[0] / state[1];  x += alpha p;  r -= alpha Ap;  state[2] = r . r
+//   direction: beta = state[2] / state[0];   p = r + beta p;  state[0] = state[2]
+// i.e. three passes over the vectors instead of a dozen elementwise ones.  Dot products: per-thread
+// and per-block partial sums in double in a fixed order, a one-block pass adds the block partials --
+// deterministic, so ranks that hold replicas of the vectors stay bit-identical.
+constexpr int kCgBlocks = 148 * 8;
+
+template <typename T>
+__device__ __forceinline__ double cg_block_sum(double v)
+{
+    __shared__ double warp_sums[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += warp_sums[w];
+    return t;   // valid in thread 0
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cg_dot_kernel(const T *__restrict__ a, const T *__restrict__ b, double *__restrict__ partials, int64_t count)
+{
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads)
+        acc += (double)a[i] * (double)b[i];
+    const double t = cg_block_sum<T>(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cg_update_kernel(T *__restrict__ x, T *__restrict__ r, const T *__restrict__ p, const T *__restrict__ ap,
+                 const double *__restrict__ state, double *__restrict__ partials, int64_t count)
+{
+    const T alpha = (T)(state[0] / state[1]);
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads) {
+        x[i] = x[i] + alpha * p[i];
+        const T rn = r[i] - alpha * ap[i];
+        r[i] = rn;
+        acc += (double)rn * (double)rn;
+    }
+    const double t = cg_block_sum<T>(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kThreads)
+cg_finish_kernel(const double *__restrict__ partials, int n, double *__restrict__ out)
+{
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += kThreads) acc += partials[i];
+    const double t = cg_block_sum<double>(acc);
+    if (threadIdx.x == 0) *out = t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cg_direction_kernel(T *__restrict__ p, const T *__restrict__ r, const double *__restrict__ state, int64_t count)
+{
+    const T beta = (T)(state[2] / state[0]);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kThreads)
+        p[i] = r[i] + beta * p[i];
+}
+
+__global__ void cg_shift_kernel(double *state) { state[0] = state[2]; }
+
+size_t cg_workspace_bytes() { return (size_t)kCgBlocks * sizeof(double); }
+
+template <typename T>
+int launch_cg_dot(const T *a, const T *b, double *state, int slot, int64_t count, double *partials, cudaStream_t s)
+{
+    cg_dot_kernel<T><<<kCgBlocks, kThreads, 0, s>>>(a, b, partials, count);
+    ADRT_LAUNCH_CHECK();
+    cg_finish_kernel<<<1, kThreads, 0, s>>>(partials, kCgBlocks, state + slot);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_cg_update(T *x, T *r, const T *p, const T *ap, double *state, int64_t count, double *partials, cudaStream_t s)
+{
+    cg_update_kernel<T><<<kCgBlocks, kThreads, 0, s>>>(x, r, p, ap, state, partials, count);
+    ADRT_LAUNCH_CHECK();
+    cg_finish_kernel<<<1, kThreads, 0, s>>>(partials, kCgBlocks, state + 2);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
+template <typename T>
+int launch_cg_direction(T *p, const T *r, double *state, int64_t count, cudaStream_t s)
+{
+    cg_direction_kernel<T><<<kCgBlocks, kThreads, 0, s>>>(p, r, state, count);
+    ADRT_LAUNCH_CHECK();
+    cg_shift_kernel<<<1, 1, 0, s>>>(state);
+    ADRT_LAUNCH_CHECK();
+    return ADRT_B200_OK;
+}
+
 #define INSTANTIATE(T)                                                                                  \
     template int launch_adrt_init<T>(const T *, T *, int64_t, int64_t, cudaStream_t);                  \
     template int launch_adrt_step<T>(const T *, T *, int64_t, int64_t, int, cudaStream_t);             \
@@ -783,7 +889,10 @@ int launch_binary(const T *a, const T *b, T *out, int64_t count, int op, cudaStr
     template int launch_truncate_mean_shares<T>(const T *, T *, int64_t, int64_t, int, int, T, cudaStream_t); \
     template int launch_stitch<T>(const T *, T *, int64_t, int64_t, bool, cudaStream_t);               \
     template int launch_unstitch<T>(const T *, T *, int64_t, int64_t, bool, cudaStream_t);             \
-    template int launch_binary<T>(const T *, const T *, T *, int64_t, int, cudaStream_t);
+    template int launch_binary<T>(const T *, const T *, T *, int64_t, int, cudaStream_t);             \
+    template int launch_cg_dot<T>(const T *, const T *, double *, int, int64_t, double *, cudaStream_t); \
+    template int launch_cg_update<T>(T *, T *, const T *, const T *, double *, int64_t, double *, cudaStream_t); \
+    template int launch_cg_direction<T>(T *, const T *, double *, int64_t, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(double)
 

@@ -7,8 +7,8 @@ gradient solve of ``A^T A x = A^T b`` with ``A = adrt`` and
 ``A^T = mean_q(truncate(bdrt(.)))``.  Here every CG iteration stays on the GPU: the
 operator is ONE native call (``adrt_b200_normal_operator``: forward passes, back-projection
 restricted to the offsets ``truncate`` keeps, ``truncate_mean``; the sinogram passes from
-adrt to bdrt as workspace rows and never takes the public layout); the vector updates are
-elementwise torch ops on device tensors.
+adrt to bdrt as workspace rows and never takes the public layout); the vector updates are three
+native passes with their dot products (``adrt_b200_cg_dot`` / ``_cg_update`` / ``_cg_direction``).
 """
 from __future__ import annotations
 
@@ -56,26 +56,39 @@ def iadrt_cg(b, /, *, ridge: float = 0.0, rtol: float = 1e-5, atol: float = 0.0,
     as_numpy = isinstance(b, np.ndarray)
     bt = _to_device(b) if as_numpy else b
     n = bt.shape[-1]
-    rhs = cd.bdrt_truncate_mean(bt, 1.0)
-    x = torch.zeros_like(rhs) if x0 is None else (_to_device(x0) if isinstance(x0, np.ndarray) else x0).clone()
-    r = rhs - normal_operator(x, ridge=ridge, dist=dist) if x0 is not None else rhs.clone()
+    rhs = cd.bdrt_truncate_mean(bt, 1.0).contiguous()
+    x = torch.zeros_like(rhs) if x0 is None else (_to_device(x0) if isinstance(x0, np.ndarray) else x0).clone().contiguous()
+    r = (rhs - normal_operator(x, ridge=ridge, dist=dist)).contiguous() if x0 is not None else rhs.clone()
     p = r.clone()
-    rs = torch.sum(r * r)
     tol = max(rtol * float(torch.linalg.vector_norm(rhs)), atol)
     maxiter = 10 * n * n if maxiter is None else int(maxiter)
-    it, converged = 0, float(rs) ** 0.5 <= tol
-    while not converged and it < maxiter:
-        ap = normal_operator(p, ridge=ridge, dist=dist)
-        alpha = rs / torch.sum(p * ap)
-        x += alpha * p
-        r -= alpha * ap
-        rs_new = torch.sum(r * r)
-        it += 1
-        if float(rs_new) ** 0.5 <= tol:
-            converged = True
-            break
-        p = r + (rs_new / rs) * p
-        rs = rs_new
+    # the vector updates of an iteration are three native passes (adrt_b200_cg_dot / _cg_update / _cg_direction);
+    # the scalars r.r, p.Ap and the new r.r stay on the device, only the stopping test reads one back
+    from . import _lib
+
+    lib = _lib.load()
+    code = _lib.F32 if rhs.dtype == torch.float32 else _lib.F64
+    count = rhs.numel()
+    with torch.cuda.device(rhs.device):
+        state = torch.zeros(4, dtype=torch.float64, device=rhs.device)
+        wsb = int(lib.adrt_b200_cg_workspace_bytes())
+        ws = torch.empty(wsb, dtype=torch.uint8, device=rhs.device)
+
+        def stream():
+            return torch.cuda.current_stream().cuda_stream
+
+        _lib.check(lib.adrt_b200_cg_dot(r.data_ptr(), r.data_ptr(), state.data_ptr(), 0, count, code, ws.data_ptr(), wsb, stream()), "cg_dot")
+        it, converged = 0, float(state[0]) ** 0.5 <= tol
+        while not converged and it < maxiter:
+            ap = normal_operator(p, ridge=ridge, dist=dist).contiguous()
+            _lib.check(lib.adrt_b200_cg_dot(p.data_ptr(), ap.data_ptr(), state.data_ptr(), 1, count, code, ws.data_ptr(), wsb, stream()), "cg_dot")
+            _lib.check(lib.adrt_b200_cg_update(x.data_ptr(), r.data_ptr(), p.data_ptr(), ap.data_ptr(), state.data_ptr(), count, code,
+                                               ws.data_ptr(), wsb, stream()), "cg_update")
+            it += 1
+            if float(state[2]) ** 0.5 <= tol:
+                converged = True
+                break
+            _lib.check(lib.adrt_b200_cg_direction(p.data_ptr(), r.data_ptr(), state.data_ptr(), count, code, stream()), "cg_direction")
     if not converged:
         raise ValueError(f"convergence failed (cg status {it})")
     out = x.cpu().numpy() if as_numpy else x

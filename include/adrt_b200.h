@@ -213,6 +213,20 @@ int    adrt_b200_truncate_mean_shares(const void *in, void *out, int64_t B, int6
                                       double divisor, int dtype, void *stream);
 int    adrt_b200_sub(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream);
 int    adrt_b200_add(const void *a, const void *b, void *out, int64_t count, int dtype, void *stream);
+/* Vector updates of conjugate gradients on the normal equations (the reference's recipe,
+ * docs/examples.cginverse.md:40-67, hands `truncate(bdrt(adrt(x)))` to scipy.sparse.linalg.cg): one
+ * iteration is the operator plus three passes over the vectors.  `state`: 4 doubles on the device,
+ * [0] = r.r, [1] = p.Ap, [2] = the new r.r; `ws`: adrt_b200_cg_workspace_bytes() bytes of device scratch.
+ *   cg_dot:       state[slot] = a . b
+ *   cg_update:    alpha = state[0] / state[1];  x += alpha p;  r -= alpha ap;  state[2] = r . r
+ *   cg_direction: beta = state[2] / state[0];   p = r + beta p;  state[0] = state[2]
+ * Sums are accumulated in double in a fixed order (replicated ranks stay bit-identical). */
+size_t adrt_b200_cg_workspace_bytes(void);
+int    adrt_b200_cg_dot(const void *a, const void *b, void *state, int slot, int64_t count, int dtype,
+                        void *ws, size_t ws_bytes, void *stream);
+int    adrt_b200_cg_update(void *x, void *r, const void *p, const void *ap, void *state, int64_t count, int dtype,
+                           void *ws, size_t ws_bytes, void *stream);
+int    adrt_b200_cg_direction(void *p, const void *r, void *state, int64_t count, int dtype, void *stream);
 
 /* Host-pointer family (NumPy path) ----------------------------------------- *
  * Same semantics as above with host buffers.  `device` is the CUDA ordinal.
