@@ -287,19 +287,36 @@ struct WaveCfg {
     int lanes;   // 1 or 2 concurrent waves
 };
 
-WaveCfg wave_config(int64_t total_planes, int q_count, size_t plane_ws_bytes)
+// `overlap`: no override given, run the batch as two half-batch waves on two lanes (see overlap_default)
+WaveCfg wave_config(int64_t total_planes, int q_count, size_t plane_ws_bytes, bool overlap)
 {
     WaveCfg w;
     w.planes = (int)total_planes;
     w.lanes = 1;
     long long want = 0;
-    if (const char *e = getenv("ADRT_B200_WAVE_PLANES")) want = atoll(e);  // read per call: tunable at run time
-    else if (const char *e2 = getenv("ADRT_B200_WAVE")) want = atoll(e2) * q_count;
+    const char *ep = getenv("ADRT_B200_WAVE_PLANES"), *ei = getenv("ADRT_B200_WAVE"), *el = getenv("ADRT_B200_WAVE_LANES");
+    if (ep) want = atoll(ep);  // read per call: tunable at run time
+    else if (ei) want = atoll(ei) * q_count;
+    else if (overlap && !el && total_planes >= 32) {
+        want = ((total_planes / 2 + q_count - 1) / q_count) * q_count;
+        w.lanes = 2;
+    }
     (void)plane_ws_bytes;
     if (want > 0 && want < total_planes) w.planes = (int)want;
-    if (const char *e = getenv("ADRT_B200_WAVE_LANES")) w.lanes = atoi(e) >= 2 ? 2 : 1;
+    if (el) w.lanes = atoi(el) >= 2 ? 2 : 1;
     if ((long long)w.planes * w.lanes > total_planes) w.lanes = 1;
     return w;
+}
+
+// Forward two-pass fp32 plans whose image pass is the staged kernel run the two halves of a batch on two
+// streams: the image pass (3 persistent CTAs per SM waiting on their copies most of the time, a third of the
+// DRAM bandwidth) of one half overlaps the DRAM-heavy second pass of the other -- 64 x 2048^2 adrt 4.50 ->
+// 4.37 ms (profiles/s6_ab_waves.jsonl).  The transposed passes lose when overlapped (6.36 -> 6.50 ms) and
+// stay on one lane; smaller (L2-sized) waves lose in both directions.
+template <bool kForward>
+bool overlap_default(const plan::Plan &pl)
+{
+    return kForward && pl.npass == 2 && pl.pass[0].staged;
 }
 
 // Experiment: keep the workspace resident in L2 (persisting access-policy window on the
@@ -465,7 +482,7 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
         return run_plan_cosched<T, kForward>(pl, cc, in, out, total, q_first, q_count, ws,
                                              reinterpret_cast<unsigned *>(ws + ctr_off), s);
     }
-    const WaveCfg wc = wave_config(total, q_count, plane_ws * sizeof(T));
+    WaveCfg wc = wave_config(total, q_count, plane_ws * sizeof(T), overlap_default<kForward>(pl));
     const size_t slot0 = pl.ws_slot_elems[0] * (size_t)wc.planes;
     const size_t lane_elems = plane_ws * (size_t)wc.planes;
     if (lane_elems * wc.lanes > ws_elems) {
@@ -476,6 +493,13 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
     cudaStream_t lane_stream[2] = {s, nullptr};
     cudaEvent_t fork = nullptr, join = nullptr;
     int lanes = wc.lanes;
+    if (lanes == 2) {
+        // the helper streams are shared per device: never fork into them while the caller's stream is being
+        // captured into a graph (the waves then simply follow one another on the caller's stream)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) lanes = 1;
+        (void)cudaGetLastError();
+    }
     if (lanes == 2) {
         lane_stream[1] = aux_stream(1);
         if (!lane_stream[1] || cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -593,7 +617,7 @@ template <typename T, bool kForward>
 size_t plan_workspace_elems(const plan::Plan &pl, int64_t B, int q_count)
 {
     const size_t plane_ws = pl.ws_slot_elems[0] + pl.ws_slot_elems[1];
-    const WaveCfg wc = wave_config(B * q_count, q_count, plane_ws * sizeof(T));
+    const WaveCfg wc = wave_config(B * q_count, q_count, plane_ws * sizeof(T), overlap_default<kForward>(pl));
     size_t need = plane_ws * (size_t)wc.planes * wc.lanes;
     // room for the co-scheduled variant too (decided per call; one slot + counters), so that a
     // workspace sized by the query serves either
