@@ -25,9 +25,11 @@ def timeit(fn, reps=7):
 
 
 var, vals = sys.argv[1], sys.argv[2].split(",")
+dt = torch.float64 if os.environ.get("BENCH_DTYPE") == "f64" else torch.float32
+iv = torch.int64 if dt == torch.float64 else torch.int32
 shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[3:]] or [(64, 2048)]
 for (B, n) in shapes:
-    x = torch.rand((B, n, n), device="cuda")
+    x = torch.rand((B, n, n), device="cuda", dtype=dt)
     os.environ.pop(var, None)
     y0 = adrt.adrt(x)
     z0 = adrt.bdrt(y0)
@@ -38,11 +40,11 @@ for (B, n) in shapes:
             os.environ[var] = v
         y = adrt.adrt(x)
         z = adrt.bdrt(y0)
-        ok = bool(torch.equal(y.view(torch.int32), y0.view(torch.int32)) and torch.equal(z.view(torch.int32), z0.view(torch.int32)))
+        ok = bool(torch.equal(y.view(iv), y0.view(iv)) and torch.equal(z.view(iv), z0.view(iv)))
         del y, z
         ta = timeit(lambda: adrt.adrt(x))
         tb = timeit(lambda: adrt.bdrt(y0))
-        print(json.dumps({"B": B, "n": n, var: v, "adrt_ms": round(ta, 3), "bdrt_ms": round(tb, 3),
+        print(json.dumps({"B": B, "n": n, "dtype": str(dt), var: v, "adrt_ms": round(ta, 3), "bdrt_ms": round(tb, 3),
                           "step_ms": round(ta + tb, 3), "bytes_equal_default": ok}), flush=True)
     del x, y0, z0
     torch.cuda.empty_cache()
