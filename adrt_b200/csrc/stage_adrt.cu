@@ -164,6 +164,9 @@ int make_map(TmaMap *m, const float *base, long long cols, long long rows, long 
 
 int resident_ctas(int per_sm)
 {
+    // ADRT_B200_STAGE_CTAS: persistent grid size (tuning)
+    if (const char *e = getenv("ADRT_B200_STAGE_CTAS"))
+        if (atoi(e) > 0) return atoi(e);
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
         (void)cudaGetLastError();
