@@ -8,12 +8,14 @@ namespace adrt_b200 {
 
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
+// Warps per block: ADRT_B200_IADRT_WARPS = 1 / 2 / 4 / 8 (A/B knob; the warps are independent, the block
+// size only sets the granularity at which the SMs fill up)
+constexpr int kDefaultWarps = 4;
 // Launch bound: threads only.  Asking for 5 / 6 / 7 / 8 resident blocks (102 / 80 / 72 / 64 registers)
 // measured 8.0 / 8.9 / 7.8 / 8.8 ms against 7.5 ms at 16 x 2048^2 fp32: the sweep is issue bound, and
 // the spills of the tighter bounds cost more than the extra warps give.
 
-template <typename T, int M, bool kInQ, bool kOutQ>
+template <typename T, int M, bool kInQ, bool kOutQ, int kWarpsPerBlock>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int s0)
 {
@@ -49,19 +51,27 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
         for (int X0 = top; X0 >= -M; X0 -= 4) {
             itile::commit_inputs<T, M>(ring, tm, lane, X0, st.v);
             itile::fetch_inputs<T, kInQ>(ip, tm, X0 - 4, st.v);
+            itile::TripAddr<M> ta;
+            itile::trip_setup<M, kOutQ>(lc, X0, ta);
             __syncwarp();
             if (X0 - 3 >= ilo && X0 <= ihi) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    itile::all_levels_interior<T, M, kOutQ>(ring, lc, n, X0 - u, st, op);
-                    __syncwarp();
-                }
+                itile::all_levels_interior<T, M, kOutQ, 0>(ring, ta, n, X0, st, op);
+                __syncwarp();
+                itile::all_levels_interior<T, M, kOutQ, 1>(ring, ta, n, X0, st, op);
+                __syncwarp();
+                itile::all_levels_interior<T, M, kOutQ, 2>(ring, ta, n, X0, st, op);
+                __syncwarp();
+                itile::all_levels_interior<T, M, kOutQ, 3>(ring, ta, n, X0, st, op);
+                __syncwarp();
             } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    itile::all_levels<T, M, kOutQ>(ring, lc, n, X0 - u, st, op);
-                    __syncwarp();
-                }
+                itile::all_levels<T, M, kOutQ, 0>(ring, lc, ta, n, X0, st, op);
+                __syncwarp();
+                itile::all_levels<T, M, kOutQ, 1>(ring, lc, ta, n, X0, st, op);
+                __syncwarp();
+                itile::all_levels<T, M, kOutQ, 2>(ring, lc, ta, n, X0, st, op);
+                __syncwarp();
+                itile::all_levels<T, M, kOutQ, 3>(ring, lc, ta, n, X0, st, op);
+                __syncwarp();
             }
             if (!kOutQ) itile::flush_outputs<T, M>(ring, tm, psi_out, lane, X0, op);
         }
@@ -69,20 +79,33 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
     }
 }
 
-template <typename T, int M, bool kInQ, bool kOutQ>
-int launch_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0, cudaStream_t s)
+template <typename T, int M, bool kInQ, bool kOutQ, int kWarpsPerBlock>
+int launch_iadrt_pass_w(const T *in, T *out, int64_t planes, int n, int s0, cudaStream_t s)
 {
     using G = itile::Geo<M>;
     const int teams = n >> M;                                       // per plane
     const int warps = (teams + G::TEAMS - 1) / G::TEAMS;
     const int blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const size_t smem = (size_t)kWarpsPerBlock * G::ROWS * itile::kLanes * sizeof(T);
-    auto kern = iadrt_pass_kernel<T, M, kInQ, kOutQ>;
+    auto kern = iadrt_pass_kernel<T, M, kInQ, kOutQ, kWarpsPerBlock>;
     ADRT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)blocks, (unsigned)(planes < 65535 ? planes : 65535));
     kern<<<grid, kWarpsPerBlock * 32, smem, s>>>(in, out, planes, n, s0);
     ADRT_LAUNCH_CHECK();
     return ADRT_B200_OK;
+}
+
+template <typename T, int M, bool kInQ, bool kOutQ>
+int launch_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0, cudaStream_t s)
+{
+    int w = kDefaultWarps;
+    if (const char *e = getenv("ADRT_B200_IADRT_WARPS")) w = atoi(e);
+    switch (w) {
+    case 1: return launch_iadrt_pass_w<T, M, kInQ, kOutQ, 1>(in, out, planes, n, s0, s);
+    case 2: return launch_iadrt_pass_w<T, M, kInQ, kOutQ, 2>(in, out, planes, n, s0, s);
+    case 8: return launch_iadrt_pass_w<T, M, kInQ, kOutQ, 8>(in, out, planes, n, s0, s);
+    default: return launch_iadrt_pass_w<T, M, kInQ, kOutQ, 4>(in, out, planes, n, s0, s);
+    }
 }
 
 template <typename T, bool kInQ, bool kOutQ>

@@ -60,7 +60,13 @@ template <int M> struct Geo {
     // rows of level t (t < M) that are live at once: the reader (level t+1) looks ahead 2^(M-1-t) + 1 rows;
     // level 0 is committed four rows at a time, three rows early
     ADRT_HD static constexpr int depth(int t) { return pow2_ceil((1 << (M - 1 - t)) + 2 + (t == 0 ? 3 : 0)); }
-    ADRT_HD static constexpr int base(int t) { return t == 0 ? 0 : base(t - 1) + depth(t - 1); }
+    // Every level ring t < M has three MIRROR rows in front of it: physical row p = r + 3 holds ring row r,
+    // and ring rows depth-3 .. depth-1 are stored a second time at p = 0 .. 2.  The four rows r0, r0 - 1,
+    // r0 - 2, r0 - 3 (mod depth) a reader needs in one trip are then the contiguous physical rows
+    // r0 + 3 - u, whatever the lane's own look-ahead: one address per operand and trip, the rows as
+    // immediate offsets (the address arithmetic was 10 of the 16 instructions per node and row).
+    static constexpr int MIRROR = 3;
+    ADRT_HD static constexpr int base(int t) { return t == 0 ? 0 : base(t - 1) + depth(t - 1) + MIRROR; }
     static constexpr int OUT_DEPTH = 8;           // level-M ring (workspace stores): one aligned group + skew
     static constexpr int OUT_BASE = base(M);
     static constexpr int ROWS = OUT_BASE + OUT_DEPTH;   // ring rows per warp (x 32 lanes)
@@ -124,6 +130,36 @@ ADRT_HD void setup_levels(const Team &tm, int team_lane0, int k, int lane, LaneC
     }
 }
 
+// Ring positions of one trip (base rows X0 .. X0 - 3, X0 = 3 mod 4), element offsets, one set per level t:
+//   F, S   the lane's two operands at u = 0 in the level-(t-1) ring; row u is at - 32 u (mirror rows)
+//   W0, W1 the lane's own cell of row 0 of the two aligned row groups the trip's rows x = X0 + t - u fall
+//          into: x = c (mod 4) at u = 0 with c = (3 + t) & 3 known at compile time, so u <= c is row c - u
+//          of group W0 and u > c row 4 + c - u of group W1 (the group below, modulo the ring depth)
+//   top    bit 2t / 2t+1: group W0 / W1 is the ring's last one -- its rows 1 .. 3 are mirrored
+template <int M> struct TripAddr {
+    int F[M + 1], S[M + 1], W0[M + 1], W1[M + 1];
+    unsigned top;
+};
+
+template <int M, bool kOutQ, int t = 1>
+ADRT_HD void trip_setup(const LaneConst<M> &lc, int X0, TripAddr<M> &ta)
+{
+    if constexpr (t == 1) ta.top = 0;
+    if constexpr (t <= M) {
+        constexpr int dp = Geo<M>::depth(t - 1), MR = Geo<M>::MIRROR;
+        const int x0 = X0 + t;
+        ta.F[t] = lc.colF[t] + ((((x0 + lc.dF[t]) & (dp - 1)) + MR) << 5);
+        ta.S[t] = lc.colS[t] + ((((x0 + lc.dS[t]) & (dp - 1)) + MR) << 5);
+        constexpr int c = (3 + t) & 3;
+        constexpr int dw = t < M ? Geo<M>::depth(t) : Geo<M>::OUT_DEPTH;
+        const int g0 = (x0 - c) & (dw - 1), g1 = (x0 - c - 4) & (dw - 1);
+        ta.W0[t] = lc.own[t] + ((g0 + (t < M ? MR : 0)) << 5);
+        ta.W1[t] = lc.own[t] + ((g1 + (t < M ? MR : 0)) << 5);
+        if (t < M && dw > 4) ta.top |= (g0 == dw - 4 ? 1u << (2 * t) : 0u) | (g1 == dw - 4 ? 2u << (2 * t) : 0u);
+        trip_setup<M, kOutQ, t + 1>(lc, X0, ta);
+    }
+}
+
 // ---- input side ---------------------------------------------------------------------------------
 // Rows X0-3 .. X0 (X0 = 3 mod 4) of the lane's input column, to be committed at the start of the trip
 // with base rows X0 .. X0-3.  kInQ: public layout in[d][col] (pitch n), else workspace W[col][2n].
@@ -154,63 +190,102 @@ template <typename T, int M>
 ADRT_HD void commit_inputs(T *ring, const Team &tm, int lane, int X0, const T (&v)[4])
 {
     if (!tm.active || X0 < 0 || X0 - 3 >= tm.D) return;
-    constexpr int mask = Geo<M>::depth(0) - 1;
+    constexpr int dp = Geo<M>::depth(0), MR = Geo<M>::MIRROR;
+    const int g = (X0 - 3) & (dp - 1);   // X0 - 3 is a multiple of 4: one aligned row group
+    const bool top = g == dp - 4;        // the ring's last group: rows 1 .. 3 also go to the mirror rows 0 .. 2
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const int x = X0 - 3 + e;
-        if (x < tm.D) ring[((x & mask) << 5) + lane] = v[e];
+        if (X0 - 3 + e < tm.D) {
+            ring[((g + e + MR) << 5) + lane] = v[e];
+            if (e >= 1 && top) ring[((e - 1) << 5) + lane] = v[e];
+        }
     }
 }
 
-// ---- all levels of one base row X for one lane -----------------------------------------------------------
+// ---- all levels of one base row X = X0 - U for one lane ------------------------------------------------
+// A level reads rows of the level below that were written in EARLIER row steps only (the levels run one
+// row apart), so a row step is: all operands of all levels -> registers, all sums, all stores.  Written
+// that way the compiler sees the independence (it cannot prove that the ring cells do not alias) and the
+// 2 M shared-memory loads of a row step are in flight together instead of one level after the other.
 // kOutQ: the last level is stored straight to the public layout (`out_ptr` = &out[0][lane's column]; the
 // last pass has psi = 0, so every lane is at the same offset d = X + M: one coalesced row piece).
-template <typename T, int M, bool kOutQ, int t = 1>
-ADRT_HD void all_levels(T *ring, const LaneConst<M> &lc, int n, int X, LaneState<T, M> &st, T *out_ptr)
+template <typename T, int M, int U, int t = 1>
+ADRT_HD void load_levels(const T *ring, const TripAddr<M> &ta, T (&first)[M + 1], T (&second)[M + 1])
 {
     if constexpr (t <= M) {
-        constexpr int mask = Geo<M>::depth(t - 1) - 1;
-        const int x = X + t;
-        const T first = ring[lc.colF[t] + (((x + lc.dF[t]) & mask) << 5)];
-        const T second = ring[lc.colS[t] + (((x + lc.dS[t]) & mask) << 5)];
-        T acc = X <= lc.thr1[t] ? T(0) + first : T(0);
-        acc = X <= lc.thr2[t] ? acc - second : acc;
+        first[t] = ring[ta.F[t] - (U << 5)];
+        second[t] = ring[ta.S[t] - (U << 5)];
+        load_levels<T, M, U, t + 1>(ring, ta, first, second);
+    }
+}
+
+template <typename T, int M, bool kOutQ, int U, int t>
+ADRT_HD void put_node(T *ring, const TripAddr<M> &ta, int n, int x, T acc, T *out_ptr)
+{
+    constexpr int c = (3 + t) & 3;
+    constexpr int i = U <= c ? c - U : 4 + c - U;          // row of its aligned group
+    const int w = (U <= c ? ta.W0[t] : ta.W1[t]) + (i << 5);
+    if constexpr (t < M) {
+        constexpr int dw = Geo<M>::depth(t);
+        ring[w] = acc;
+        if constexpr (i >= 1) {
+            const int mirror = Geo<M>::base(t) * kLanes + ((i - 1) << 5);
+            const int lane_col = (U <= c ? ta.W0[t] : ta.W1[t]) & (kLanes - 1);
+            if (dw == 4 || (ta.top >> (2 * t + (U <= c ? 0 : 1))) & 1u) ring[mirror + lane_col] = acc;
+        }
+    } else if constexpr (kOutQ) {
+        out_ptr[(long long)x * n] = acc;
+    } else {
+        ring[w] = acc;
+    }
+}
+
+template <typename T, int M, bool kOutQ, int U, int t = 1>
+ADRT_HD void guarded_levels(T *ring, const LaneConst<M> &lc, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st,
+                            T *out_ptr, const T (&first)[M + 1], const T (&second)[M + 1])
+{
+    if constexpr (t <= M) {
+        const int X = X0 - U;
+        T acc = X <= lc.thr1[t] ? T(0) + first[t] : T(0);
+        acc = X <= lc.thr2[t] ? acc - second[t] : acc;
         acc = X < lc.hi[t] ? acc + st.prev[t] : acc;
         if (X >= lc.lo[t] && X <= lc.hi[t]) {
             st.prev[t] = acc;
-            if constexpr (t < M) {
-                ring[lc.own[t] + ((x & (Geo<M>::depth(t) - 1)) << 5)] = acc;
-            } else if constexpr (kOutQ) {
-                out_ptr[(long long)x * n] = acc;
-            } else {
-                ring[lc.own[t] + ((x & (Geo<M>::OUT_DEPTH - 1)) << 5)] = acc;
-            }
+            put_node<T, M, kOutQ, U, t>(ring, ta, n, X + t, acc, out_ptr);
         }
-        all_levels<T, M, kOutQ, t + 1>(ring, lc, n, X, st, out_ptr);
+        guarded_levels<T, M, kOutQ, U, t + 1>(ring, lc, ta, n, X0, st, out_ptr, first, second);
     }
+}
+
+template <typename T, int M, bool kOutQ, int U>
+ADRT_HD void all_levels(T *ring, const LaneConst<M> &lc, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st,
+                        T *out_ptr)
+{
+    T first[M + 1], second[M + 1];
+    load_levels<T, M, U>(ring, ta, first, second);
+    guarded_levels<T, M, kOutQ, U>(ring, lc, ta, n, X0, st, out_ptr, first, second);
 }
 
 // The same for base rows where every term of every level exists for every lane of the warp
 // (interior_range): no comparisons, no selects.
-template <typename T, int M, bool kOutQ, int t = 1>
-ADRT_HD void all_levels_interior(T *ring, const LaneConst<M> &lc, int n, int X, LaneState<T, M> &st, T *out_ptr)
+template <typename T, int M, bool kOutQ, int U, int t = 1>
+ADRT_HD void interior_levels(T *ring, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st, T *out_ptr,
+                             const T (&first)[M + 1], const T (&second)[M + 1])
 {
     if constexpr (t <= M) {
-        constexpr int mask = Geo<M>::depth(t - 1) - 1;
-        const int x = X + t;
-        const T first = ring[lc.colF[t] + (((x + lc.dF[t]) & mask) << 5)];
-        const T second = ring[lc.colS[t] + (((x + lc.dS[t]) & mask) << 5)];
-        const T acc = ((T(0) + first) - second) + st.prev[t];
+        const T acc = ((T(0) + first[t]) - second[t]) + st.prev[t];
         st.prev[t] = acc;
-        if constexpr (t < M) {
-            ring[lc.own[t] + ((x & (Geo<M>::depth(t) - 1)) << 5)] = acc;
-        } else if constexpr (kOutQ) {
-            out_ptr[(long long)x * n] = acc;
-        } else {
-            ring[lc.own[t] + ((x & (Geo<M>::OUT_DEPTH - 1)) << 5)] = acc;
-        }
-        all_levels_interior<T, M, kOutQ, t + 1>(ring, lc, n, X, st, out_ptr);
+        put_node<T, M, kOutQ, U, t>(ring, ta, n, X0 - U + t, acc, out_ptr);
+        interior_levels<T, M, kOutQ, U, t + 1>(ring, ta, n, X0, st, out_ptr, first, second);
     }
+}
+
+template <typename T, int M, bool kOutQ, int U>
+ADRT_HD void all_levels_interior(T *ring, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st, T *out_ptr)
+{
+    T first[M + 1], second[M + 1];
+    load_levels<T, M, U>(ring, ta, first, second);
+    interior_levels<T, M, kOutQ, U>(ring, ta, n, X0, st, out_ptr, first, second);
 }
 
 // Base rows X for which this lane needs no guard at any level: [lo, hi] (empty for padding teams).

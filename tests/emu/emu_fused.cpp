@@ -352,6 +352,18 @@ int run_normal(const T *in, T *mid, T *out, int64_t B, int64_t n, int64_t rows)
     return run<T, false>(mid, out, B, n, rows, true);
 }
 // ---- fused iadrt passes (iadrt_tile.h): the 32 lanes of every warp played phase by phase ------------
+// one base row X0 - U for the 32 lanes of a warp, in the configured lane order
+template <typename T, int M, bool kOutQ, int U>
+void iadrt_row(bool interior, T *ring, const itile::LaneConst<M> *lc, const itile::TripAddr<M> *ta, int n, int X0,
+               itile::LaneState<T, M> *st, T **op)
+{
+    for (int i = 0; i < 32; ++i) {
+        const int lane = g_order ? 31 - i : i;
+        if (interior) itile::all_levels_interior<T, M, kOutQ, U>(ring, ta[lane], n, X0, st[lane], op[lane]);
+        else itile::all_levels<T, M, kOutQ, U>(ring, lc[lane], ta[lane], n, X0, st[lane], op[lane]);
+    }
+}
+
 template <typename T, int M, bool kInQ, bool kOutQ>
 void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
 {
@@ -396,12 +408,13 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
                     itile::commit_inputs<T, M>(ring.data(), tm[lane], lane, X0, st[lane].v);
                     itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], X0 - 4, st[lane].v);
                 }
-                for (int u = 0; u < 4; ++u)
-                    for (int i = 0; i < 32; ++i) {
-                        const int lane = g_order ? 31 - i : i;
-                        if (X0 - 3 >= ilo && X0 <= ihi) itile::all_levels_interior<T, M, kOutQ>(ring.data(), lc[lane], n, X0 - u, st[lane], op[lane]);
-                        else itile::all_levels<T, M, kOutQ>(ring.data(), lc[lane], n, X0 - u, st[lane], op[lane]);
-                    }
+                itile::TripAddr<M> ta[32];
+                for (int lane = 0; lane < 32; ++lane) itile::trip_setup<M, kOutQ>(lc[lane], X0, ta[lane]);
+                const bool interior = X0 - 3 >= ilo && X0 <= ihi;
+                iadrt_row<T, M, kOutQ, 0>(interior, ring.data(), lc, ta, n, X0, st, op);
+                iadrt_row<T, M, kOutQ, 1>(interior, ring.data(), lc, ta, n, X0, st, op);
+                iadrt_row<T, M, kOutQ, 2>(interior, ring.data(), lc, ta, n, X0, st, op);
+                iadrt_row<T, M, kOutQ, 3>(interior, ring.data(), lc, ta, n, X0, st, op);
                 if (!kOutQ)
                     for (int lane = 0; lane < 32; ++lane)
                         itile::flush_outputs<T, M>(ring.data(), tm[lane], tm[lane].c0 * (lane % G::G), lane, X0, op[lane]);
