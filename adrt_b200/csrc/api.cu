@@ -691,9 +691,9 @@ int adrt_b200_iadrt(const void *in, void *out, int64_t B, int64_t n, int dtype, 
         set_error("iadrt workspace too small: need %zu bytes, got %zu", need, ws_bytes);
         return ADRT_B200_EWORKSPACE;
     }
-    // fused multi-stage passes (iadrt_fused.cu) need 16-byte aligned workspace rows; mode 1 and
+    // fused multi-stage passes (iadrt_fused.cu) need 32-byte aligned workspace rows (256-bit accesses); mode 1 and
     // misaligned workspaces take the one-kernel-per-stage path
-    if (g_mode.load() == 0 && num_iters(n) >= 1 && reinterpret_cast<uintptr_t>(ws) % 16 == 0)
+    if (g_mode.load() == 0 && num_iters(n) >= 1 && reinterpret_cast<uintptr_t>(ws) % 32 == 0)
         return DISPATCH(dtype,
                         fused_iadrt<float>((const float *)in, (float *)out, B, n, (float *)ws, ws_bytes / 4, as_stream(stream)),
                         fused_iadrt<double>((const double *)in, (double *)out, B, n, (double *)ws, ws_bytes / 8, as_stream(stream)));

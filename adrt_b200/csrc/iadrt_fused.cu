@@ -48,30 +48,34 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
 #pragma unroll
         for (int t = 0; t <= M; ++t) st.prev[t] = T(0);
         itile::fetch_inputs<T, kInQ>(ip, tm, top, st.v);
-        for (int X0 = top; X0 >= -M; X0 -= 4) {
+        for (int X0 = top; X0 >= -M; X0 -= 8) {
             itile::commit_inputs<T, M>(ring, tm, lane, X0, st.v);
-            itile::fetch_inputs<T, kInQ>(ip, tm, X0 - 4, st.v);
-            itile::TripAddr<M> ta;
-            itile::trip_setup<M, kOutQ>(lc, X0, ta);
-            __syncwarp();
-            if (X0 - 3 >= ilo && X0 <= ihi) {
-                itile::all_levels_interior<T, M, kOutQ, 0>(ring, ta, n, X0, st, op);
+            itile::fetch_inputs<T, kInQ>(ip, tm, X0 - 8, st.v);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int X4 = X0 - 4 * h;      // the two trips of the pair
+                itile::TripAddr<M> ta;
+                itile::trip_setup<M, kOutQ>(lc, X4, ta);
                 __syncwarp();
-                itile::all_levels_interior<T, M, kOutQ, 1>(ring, ta, n, X0, st, op);
-                __syncwarp();
-                itile::all_levels_interior<T, M, kOutQ, 2>(ring, ta, n, X0, st, op);
-                __syncwarp();
-                itile::all_levels_interior<T, M, kOutQ, 3>(ring, ta, n, X0, st, op);
-                __syncwarp();
-            } else {
-                itile::all_levels<T, M, kOutQ, 0>(ring, lc, ta, n, X0, st, op);
-                __syncwarp();
-                itile::all_levels<T, M, kOutQ, 1>(ring, lc, ta, n, X0, st, op);
-                __syncwarp();
-                itile::all_levels<T, M, kOutQ, 2>(ring, lc, ta, n, X0, st, op);
-                __syncwarp();
-                itile::all_levels<T, M, kOutQ, 3>(ring, lc, ta, n, X0, st, op);
-                __syncwarp();
+                if (X4 - 3 >= ilo && X4 <= ihi) {
+                    itile::all_levels_interior<T, M, kOutQ, 0>(ring, ta, n, X4, st, op);
+                    __syncwarp();
+                    itile::all_levels_interior<T, M, kOutQ, 1>(ring, ta, n, X4, st, op);
+                    __syncwarp();
+                    itile::all_levels_interior<T, M, kOutQ, 2>(ring, ta, n, X4, st, op);
+                    __syncwarp();
+                    itile::all_levels_interior<T, M, kOutQ, 3>(ring, ta, n, X4, st, op);
+                    __syncwarp();
+                } else {
+                    itile::all_levels<T, M, kOutQ, 0>(ring, lc, ta, n, X4, st, op);
+                    __syncwarp();
+                    itile::all_levels<T, M, kOutQ, 1>(ring, lc, ta, n, X4, st, op);
+                    __syncwarp();
+                    itile::all_levels<T, M, kOutQ, 2>(ring, lc, ta, n, X4, st, op);
+                    __syncwarp();
+                    itile::all_levels<T, M, kOutQ, 3>(ring, lc, ta, n, X4, st, op);
+                    __syncwarp();
+                }
             }
             if (!kOutQ) itile::flush_outputs<T, M>(ring, tm, psi_out, lane, X0, op);
         }
@@ -131,7 +135,7 @@ size_t fused_iadrt_workspace_elems(int64_t B, int64_t n)
     const int K = num_iters(n);
     if (K < 1 || n > kMaxN) return 0;
     int ms[8];
-    const int np = itile::iadrt_split(K, ms);
+    const int np = itile::iadrt_split(K, ms, (int)sizeof(T));
     const size_t w = (size_t)(B * 4) * (size_t)n * (size_t)(2 * n);
     return np <= 1 ? 0 : (np == 2 ? w : 2 * w);
 }
@@ -141,7 +145,7 @@ int fused_iadrt(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_elem
 {
     const int K = num_iters(n);
     int ms[8];
-    const int np = itile::iadrt_split(K, ms);
+    const int np = itile::iadrt_split(K, ms, (int)sizeof(T));
     const size_t need = fused_iadrt_workspace_elems<T>(B, n);
     if (need > 0 && (!ws || ws_elems < need)) {
         set_error("iadrt workspace too small: need %zu elements, got %zu", need, ws_elems);

@@ -58,8 +58,8 @@ template <int M> struct Geo {
     static constexpr int G = 1 << M;              // lanes per team
     static constexpr int TEAMS = kLanes / G;      // teams per warp
     // rows of level t (t < M) that are live at once: the reader (level t+1) looks ahead 2^(M-1-t) + 1 rows;
-    // level 0 is committed four rows at a time, three rows early
-    ADRT_HD static constexpr int depth(int t) { return pow2_ceil((1 << (M - 1 - t)) + 2 + (t == 0 ? 3 : 0)); }
+    // level 0 is committed eight rows at a time (two trips), seven rows early
+    ADRT_HD static constexpr int depth(int t) { return pow2_ceil((1 << (M - 1 - t)) + 2 + (t == 0 ? 7 : 0)); }
     // Every level ring t < M has three MIRROR rows in front of it: physical row p = r + 3 holds ring row r,
     // and ring rows depth-3 .. depth-1 are stored a second time at p = 0 .. 2.  The four rows r0, r0 - 1,
     // r0 - 2, r0 - 3 (mod depth) a reader needs in one trip are then the contiguous physical rows
@@ -67,7 +67,7 @@ template <int M> struct Geo {
     // immediate offsets (the address arithmetic was 10 of the 16 instructions per node and row).
     static constexpr int MIRROR = 3;
     ADRT_HD static constexpr int base(int t) { return t == 0 ? 0 : base(t - 1) + depth(t - 1) + MIRROR; }
-    static constexpr int OUT_DEPTH = 8;           // level-M ring (workspace stores): one aligned group + skew
+    static constexpr int OUT_DEPTH = 16;          // level-M ring (workspace stores): one aligned group of 8 + skew
     static constexpr int OUT_BASE = base(M);
     static constexpr int ROWS = OUT_BASE + OUT_DEPTH;   // ring rows per warp (x 32 lanes)
 };
@@ -85,7 +85,7 @@ struct Team {
 // per-lane registers that live across iterations
 template <typename T, int M> struct LaneState {
     T prev[M + 1];     // running scan value of the lane's node at level t (index t, 1..M)
-    T v[4];            // four input rows fetched for the next trip
+    T v[8];            // eight input rows fetched for the next pair of trips
 };
 
 // Per-lane constants of the sweep, one set per level t = 1..M (index t): where the two operands of the
@@ -161,43 +161,84 @@ ADRT_HD void trip_setup(const LaneConst<M> &lc, int X0, TripAddr<M> &ta)
 }
 
 // ---- input side ---------------------------------------------------------------------------------
-// Rows X0-3 .. X0 (X0 = 3 mod 4) of the lane's input column, to be committed at the start of the trip
-// with base rows X0 .. X0-3.  kInQ: public layout in[d][col] (pitch n), else workspace W[col][2n].
-// `col_ptr`: the lane's column (public layout: &in[0][col]; workspace: &W[col][0]).
-template <typename T, bool kInQ>
-ADRT_HD void fetch_inputs(const T *col_ptr, const Team &tm, int X0, T (&v)[4])
+// One 32-byte sector of a lane's workspace row (8 floats / 4 doubles), 32-byte aligned: the lanes of a warp
+// stream 32 different rows, so every global access of a pass costs 32 L1 wavefronts whatever its width --
+// the widest access per lane halves that cost per element against 16-byte vectors.
+ADRT_HD void load_sector(const float *p, float *dst)
 {
-    if (!tm.active || X0 < 0 || X0 - 3 >= tm.D) return;
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=f"(dst[0]), "=f"(dst[1]), "=f"(dst[2]), "=f"(dst[3]), "=f"(dst[4]), "=f"(dst[5]), "=f"(dst[6]), "=f"(dst[7])
+                 : "l"(p));
+#else
+    for (int i = 0; i < 8; ++i) dst[i] = p[i];
+#endif
+}
+ADRT_HD void load_sector(const double *p, double *dst)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];\n" : "=d"(dst[0]), "=d"(dst[1]), "=d"(dst[2]), "=d"(dst[3]) : "l"(p));
+#else
+    for (int i = 0; i < 4; ++i) dst[i] = p[i];
+#endif
+}
+ADRT_HD void store_sector(float *p, const float *v)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+#else
+    for (int i = 0; i < 8; ++i) p[i] = v[i];
+#endif
+}
+ADRT_HD void store_sector(double *p, const double *v)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+#else
+    for (int i = 0; i < 4; ++i) p[i] = v[i];
+#endif
+}
+template <typename T> struct Sector { static constexpr int L = 32 / (int)sizeof(T); };
+
+// Rows X0-7 .. X0 (X0 = 7 mod 8) of the lane's input column, to be committed at the start of the pair of
+// trips with base rows X0 .. X0-3 and X0-4 .. X0-7.  kInQ: public layout in[d][col] (pitch n), else
+// workspace W[col][2n].  `col_ptr`: the lane's column (public layout: &in[0][col]; workspace: &W[col][0]).
+template <typename T, bool kInQ>
+ADRT_HD void fetch_inputs(const T *col_ptr, const Team &tm, int X0, T (&v)[8])
+{
+    if (!tm.active || X0 < 0 || X0 - 7 >= tm.D) return;
     if (kInQ) {
-        const T *p = col_ptr + (long long)(X0 - 3) * tm.n;
+        const T *p = col_ptr + (long long)(X0 - 7) * tm.n;
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (X0 - 3 + e < tm.D) v[e] = p[(long long)e * tm.n];
+        for (int e = 0; e < 8; ++e)
+            if (X0 - 7 + e < tm.D) v[e] = p[(long long)e * tm.n];
     } else {
-        // aligned 16-byte group(s) of the padded row; the pad cell (offset 2n - 1) is loaded and never used
-        const T *p = col_ptr + (X0 - 3);
-        constexpr int L = tile::VecOf<T>::L;
+        // aligned 32-byte sector(s) of the padded row; the pad cell (offset 2n - 1) is loaded and never used
+        const T *p = col_ptr + (X0 - 7);
+        constexpr int L = Sector<T>::L;
 #pragma unroll
-        for (int g = 0; g < 4 / L; ++g) {
-            const tile::Pack<T> w = *reinterpret_cast<const tile::Pack<T> *>(p + g * L);
-#pragma unroll
-            for (int i = 0; i < L; ++i) v[g * L + i] = w.v[i];
-        }
+        for (int g = 0; g < 8 / L; ++g) load_sector(p + g * L, &v[g * L]);
     }
 }
 
+// rows X0-7 .. X0 into the level-0 ring: two aligned groups of four
 template <typename T, int M>
-ADRT_HD void commit_inputs(T *ring, const Team &tm, int lane, int X0, const T (&v)[4])
+ADRT_HD void commit_inputs(T *ring, const Team &tm, int lane, int X0, const T (&v)[8])
 {
-    if (!tm.active || X0 < 0 || X0 - 3 >= tm.D) return;
+    if (!tm.active || X0 < 0 || X0 - 7 >= tm.D) return;
     constexpr int dp = Geo<M>::depth(0), MR = Geo<M>::MIRROR;
-    const int g = (X0 - 3) & (dp - 1);   // X0 - 3 is a multiple of 4: one aligned row group
-    const bool top = g == dp - 4;        // the ring's last group: rows 1 .. 3 also go to the mirror rows 0 .. 2
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        if (X0 - 3 + e < tm.D) {
-            ring[((g + e + MR) << 5) + lane] = v[e];
-            if (e >= 1 && top) ring[((e - 1) << 5) + lane] = v[e];
+    for (int h = 0; h < 2; ++h) {
+        const int x4 = X0 - 7 + 4 * h;       // a multiple of 4: one aligned row group
+        const int g = x4 & (dp - 1);
+        const bool top = g == dp - 4;        // the ring's last group: rows 1 .. 3 also go to the mirror rows 0 .. 2
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (x4 + e < tm.D) {
+                ring[((g + e + MR) << 5) + lane] = v[4 * h + e];
+                if (e >= 1 && top) ring[((e - 1) << 5) + lane] = v[4 * h + e];
+            }
         }
     }
 }
@@ -307,28 +348,28 @@ ADRT_HD void interior_range(const LaneConst<M> &lc, bool active, int &lo, int &h
 }
 
 // ---- workspace stores -------------------------------------------------------------------------------
-// After the trip with base rows X0 .. X0-3 the lane's output column is complete down to offset
-// X0 - 3 + M - psi: flush the one aligned group of four offsets that became complete in this trip.
+// After the pair of trips with base rows X0 .. X0-7 the lane's output column is complete down to offset
+// X0 - 7 + M - psi: flush the one aligned group of eight offsets that became complete in this pair.
 // `row_ptr`: the lane's workspace row (&W[output column][0]); psi = c0 * lambda.
 template <typename T, int M>
 ADRT_HD void flush_outputs(const T *ring, const Team &tm, int psi, int lane, int X0, T *row_ptr)
 {
     if (!tm.active) return;
-    const int lo = X0 - 3 + M - psi;           // lowest offset computed so far
-    const int d0 = (lo + 3) & ~3;              // lowest complete aligned group
+    const int lo = X0 - 7 + M - psi;           // lowest offset computed so far
+    const int d0 = (lo + 7) & ~7;              // lowest complete aligned group
     if (d0 < 0 || d0 >= 2 * tm.n) return;
-    T w[4];
+    T w[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) w[e] = ring[Geo<M>::OUT_BASE * kLanes + lane + (((d0 + e + psi) & (Geo<M>::OUT_DEPTH - 1)) << 5)];
-    constexpr int L = tile::VecOf<T>::L;
+    for (int e = 0; e < 8; ++e) w[e] = ring[Geo<M>::OUT_BASE * kLanes + lane + (((d0 + e + psi) & (Geo<M>::OUT_DEPTH - 1)) << 5)];
+    constexpr int L = Sector<T>::L;
 #pragma unroll
-    for (int g = 0; g < 4 / L; ++g) tile::store_cv<T>(row_ptr + d0 + g * L, &w[g * L]);
+    for (int g = 0; g < 8 / L; ++g) store_sector(row_ptr + d0 + g * L, &w[g * L]);
 }
 
-// Sweep bounds of a warp: base rows from x_top (= 3 mod 4) down to x_end (inclusive, multiple of 4 trips).
+// Sweep bounds of a warp: base rows from x_top (= 7 mod 8) downwards, two trips of four rows per iteration.
 ADRT_HD int sweep_top(int D, int psi_max)
 {
-    return ((D - 1 + psi_max) | 3);
+    return ((D - 1 + psi_max) | 7);
 }
 
 }  // namespace itile
@@ -338,9 +379,13 @@ ADRT_HD int sweep_top(int D, int psi_max)
 namespace adrt_b200 {
 namespace itile {
 
-// stages per pass: as even as possible with at most 5 per pass (a team is at most one warp);
-// ADRT_B200_IADRT_SPLIT="4,4,3" overrides
-inline int iadrt_split(int K, int *ms /* [8] */)
+// stages per pass: at most 5 per pass (a team is at most one warp), the FIRST pass the shortest -- its
+// groups span the whole block (c0 up to n / G), so its lanes' frames are up to n rows apart and every lane
+// idles through the other lanes' ramps; later passes have short ramps and amortise the per-row overhead
+// over more levels.  Measured at 2048^2 (profiles/r05_iadrt.jsonl): fp32 2,4,5 4.61 ms / 3,4,4 4.93 /
+// 4,4,3 5.13 / 1,5,5 5.09; fp64 (five-level rings are 2 x the shared memory) 3,4,4 4.82 / 2,4,5 4.96 /
+// 4,4,3 5.26.  ADRT_B200_IADRT_SPLIT="4,4,3" overrides.
+inline int iadrt_split(int K, int *ms /* [8] */, int elem_size = 4)
 {
     if (const char *e = getenv("ADRT_B200_IADRT_SPLIT")) {
         int cnt = 0, sum = 0;
@@ -355,9 +400,16 @@ inline int iadrt_split(int K, int *ms /* [8] */)
         if (ok && sum == K && cnt <= 3) return cnt;
     }
     const int np = (K + 4) / 5;
+    if (np == 3 && elem_size == 4 && K >= 10) {
+        ms[0] = K - 9;
+        ms[1] = 4;
+        ms[2] = 5;
+        return np;
+    }
+    // as even as possible, ascending
     int left = K;
     for (int i = 0; i < np; ++i) {
-        const int m = (left + (np - i) - 1) / (np - i);
+        const int m = left / (np - i);
         ms[i] = m;
         left -= m;
     }

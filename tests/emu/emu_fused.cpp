@@ -392,7 +392,7 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
                 ip[lane] = in + plane * in_plane + (kInQ ? tm[lane].in_col + k : (tm[lane].in_col + k) * (long long)(2 * n));
                 op[lane] = out + plane * out_plane + (kOutQ ? tm[lane].out_col + k : (tm[lane].out_col + (long long)k * tm[lane].out_stride) * (long long)(2 * n));
                 for (int t = 0; t <= M; ++t) st[lane].prev[t] = T(0);
-                for (int e = 0; e < 4; ++e) st[lane].v[e] = T(NAN);
+                for (int e = 0; e < 8; ++e) st[lane].v[e] = T(NAN);
                 itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], top, st[lane].v);
             }
             int ilo = -0x40000000, ihi = 0x40000000;   // the warp-wide reduction of the lanes' interior ranges
@@ -402,19 +402,22 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
                 ilo = std::max(ilo, lo);
                 ihi = std::min(ihi, hi);
             }
-            for (int X0 = top; X0 >= -M; X0 -= 4) {
+            for (int X0 = top; X0 >= -M; X0 -= 8) {
                 for (int i = 0; i < 32; ++i) {
                     const int lane = g_order ? 31 - i : i;
                     itile::commit_inputs<T, M>(ring.data(), tm[lane], lane, X0, st[lane].v);
-                    itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], X0 - 4, st[lane].v);
+                    itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], X0 - 8, st[lane].v);
                 }
-                itile::TripAddr<M> ta[32];
-                for (int lane = 0; lane < 32; ++lane) itile::trip_setup<M, kOutQ>(lc[lane], X0, ta[lane]);
-                const bool interior = X0 - 3 >= ilo && X0 <= ihi;
-                iadrt_row<T, M, kOutQ, 0>(interior, ring.data(), lc, ta, n, X0, st, op);
-                iadrt_row<T, M, kOutQ, 1>(interior, ring.data(), lc, ta, n, X0, st, op);
-                iadrt_row<T, M, kOutQ, 2>(interior, ring.data(), lc, ta, n, X0, st, op);
-                iadrt_row<T, M, kOutQ, 3>(interior, ring.data(), lc, ta, n, X0, st, op);
+                for (int h = 0; h < 2; ++h) {
+                    const int X4 = X0 - 4 * h;
+                    itile::TripAddr<M> ta[32];
+                    for (int lane = 0; lane < 32; ++lane) itile::trip_setup<M, kOutQ>(lc[lane], X4, ta[lane]);
+                    const bool interior = X4 - 3 >= ilo && X4 <= ihi;
+                    iadrt_row<T, M, kOutQ, 0>(interior, ring.data(), lc, ta, n, X4, st, op);
+                    iadrt_row<T, M, kOutQ, 1>(interior, ring.data(), lc, ta, n, X4, st, op);
+                    iadrt_row<T, M, kOutQ, 2>(interior, ring.data(), lc, ta, n, X4, st, op);
+                    iadrt_row<T, M, kOutQ, 3>(interior, ring.data(), lc, ta, n, X4, st, op);
+                }
                 if (!kOutQ)
                     for (int lane = 0; lane < 32; ++lane)
                         itile::flush_outputs<T, M>(ring.data(), tm[lane], tm[lane].c0 * (lane % G::G), lane, X0, op[lane]);
@@ -440,7 +443,7 @@ int run_iadrt(const T *in, T *out, int64_t B, int64_t n64)
     const int n = (int)n64, K = plan::ilog2(n64);
     if (K < 1) return 1;
     int ms[8];
-    const int np = itile::iadrt_split(K, ms);
+    const int np = itile::iadrt_split(K, ms, (int)sizeof(T));
     const int64_t planes = B * 4;
     const size_t w = (size_t)planes * n * 2 * n;
     std::vector<T> w0(np > 1 ? w : 0, T(NAN)), w1(np > 2 ? w : 0, T(NAN));

@@ -26,10 +26,10 @@ def timeit(fn, reps=5):
 
 lib = _lib.load()
 QUICK = os.environ.get("QUICK") == "1"   # default split only, two shapes
-for (B, n, dt, splits) in ((16, 2048, torch.float32, [None]), (8, 2048, torch.float64, [None])) if QUICK else ((16, 2048, torch.float32, [None, "4,4,3", "5,5,1", "5,3,3", "3,4,4", "3,3,5"]),
-                           (8, 2048, torch.float64, [None, "5,5,1", "3,4,4"]),
-                           (4, 4096, torch.float32, [None, "5,5,2", "4,4,4"]),
-                           (64, 1024, torch.float32, [None, "5,5"]),
+for (B, n, dt, splits) in ((16, 2048, torch.float32, [None]), (8, 2048, torch.float64, [None])) if QUICK else ((16, 2048, torch.float32, [None, "4,4,3", "5,5,1", "1,5,5", "2,4,5", "3,4,4", "2,5,4"]),
+                           (8, 2048, torch.float64, [None, "4,4,3", "3,4,4", "2,4,5"]),
+                           (4, 4096, torch.float32, [None, "5,5,2", "4,4,4", "2,5,5"]),
+                           (64, 1024, torch.float32, [None, "5,5", "3,4,3", "2,4,4"]),
                            (1, 8192, torch.float32, [None])):
     y = torch.rand((B, 4, 2 * n - 1, n), device="cuda", dtype=dt)
     out = torch.empty_like(y)
