@@ -26,15 +26,18 @@ def timeit(fn, reps=5):
 
 lib = _lib.load()
 QUICK = os.environ.get("QUICK") == "1"   # default split only, two shapes
+DEFAULTS = os.environ.get("DEFAULTS") == "1"   # every shape, default split only
 for (B, n, dt, splits) in ((16, 2048, torch.float32, [None]), (8, 2048, torch.float64, [None])) if QUICK else ((16, 2048, torch.float32, [None, "4,4,3", "5,5,1", "1,5,5", "2,4,5", "3,4,4", "2,5,4"]),
                            (8, 2048, torch.float64, [None, "4,4,3", "3,4,4", "2,4,5"]),
                            (4, 4096, torch.float32, [None, "5,5,2", "4,4,4", "2,5,5"]),
                            (64, 1024, torch.float32, [None, "5,5", "3,4,3", "2,4,4"]),
                            (1, 8192, torch.float32, [None])):
+    if DEFAULTS:
+        splits = [None]
     y = torch.rand((B, 4, 2 * n - 1, n), device="cuda", dtype=dt)
     out = torch.empty_like(y)
     S = y.numel() * y.element_size()
-    if not QUICK:
+    if not QUICK and not DEFAULTS:
         lib.adrt_b200_set_mode(1)
         t = timeit(lambda: adrt.iadrt(y, out=out))
         lib.adrt_b200_set_mode(0)
