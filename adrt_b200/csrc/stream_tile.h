@@ -205,7 +205,11 @@ ADRT_HD const float *fill_src(bool neg)
 // one 32-byte sector (8 consecutive columns of the public layout)
 ADRT_HD void store8(float *p, const float (&v)[8])
 {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(ADRT_STORE8_SPLIT)
+    // A/B: two 16-byte stores (the L1 data pipe spends one wavefront per LANE on a 256-bit store)
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+#elif defined(__CUDA_ARCH__)
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                  "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 #else
