@@ -286,7 +286,8 @@ int adrt_quadrants_impl(const T *in, T *out, int64_t B, int64_t n, int q_first, 
 }
 
 template <typename T>
-int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, int64_t rows, T *ws, size_t ws_bytes, cudaStream_t s)
+int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, int64_t rows, T *ws, size_t ws_bytes, cudaStream_t s,
+                     const T *sub = nullptr)
 {
     if (n == 1) {
         ADRT_CUDA_CHECK(cudaMemcpyAsync(out, in, sizeof(T) * planes, cudaMemcpyDeviceToDevice, s));
@@ -298,7 +299,7 @@ int bdrt_planes_impl(const T *in, T *out, int64_t planes, int64_t n, int64_t row
         return ADRT_B200_EWORKSPACE;
     }
     bool handled = false;
-    return fused_bdrt<T>(in, out, planes, n, 1, rows, ws, ws_bytes / sizeof(T), s, &handled);
+    return fused_bdrt<T>(in, out, planes, n, 1, rows, ws, ws_bytes / sizeof(T), s, &handled, false, sub);
 }
 
 // ---- fused normal operator ---------------------------------------
@@ -435,8 +436,13 @@ int fmg_step_impl(const T *in, T *out, int64_t B, int64_t n, T *ws, size_t ws_by
         T *pro = img[which ^ 1];
         if ((rc = launch_fmg_prolongation<T>(cur, pro, B, m / 2, m / 2, s))) return rc;
         if ((rc = adrt_impl<T>(pro, sino_a, B, m, tws, tws_bytes, s))) return rc;
-        if ((rc = launch_binary<T>(sino_a, level[k], sino_a, sino_elems(B, m), 0, s))) return rc;
-        if (g_mode.load() == 0) rc = bdrt_planes_impl<T>(sino_a, sino_b, B * 4, m, m, tws, tws_bytes, s);
+        // adrt(ret) - a_level: subtracted by the loader of bdrt's first pass where that pass is one of the
+        // public-layout kernels with a fused first step (large levels: three sinogram sweeps less), by a
+        // kernel of its own otherwise; element-wise either way, so the result does not depend on which
+        const bool sub_on_load = g_mode.load() == 0 && m >= 2 && getenv("ADRT_B200_FMG_SUB_SEPARATE") == nullptr &&
+                                 fused_bdrt_sub_ok<T>(m, m);
+        if (!sub_on_load && (rc = launch_binary<T>(sino_a, level[k], sino_a, sino_elems(B, m), 0, s))) return rc;
+        if (g_mode.load() == 0) rc = bdrt_planes_impl<T>(sino_a, sino_b, B * 4, m, m, tws, tws_bytes, s, sub_on_load ? level[k] : (const T *)nullptr);
         else rc = bdrt_impl<T>(sino_a, sino_b, B, m, tws, tws_bytes, s);
         if (rc) return rc;
         if ((rc = launch_truncate_mean<T>(sino_b, grad, B, m, (T)(m - 1), s))) return rc;

@@ -85,7 +85,10 @@ template <typename T> size_t fused_bdrt_workspace_elems(int64_t B, int64_t n, in
 // rows_out / rows_in: the caller-side array is in R-layout rows (planes x n x round4(2n-1)) instead of the
 // public (d, column) layout: how the fused normal operator hands adrt's result to bdrt
 template <typename T> int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_count, T *ws, size_t ws_elems, cudaStream_t s, bool *handled, bool rows_out = false);
-template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems, cudaStream_t s, bool *handled, bool rows_in = false);
+// `sub` (same shape as `in`, public layout): the transform of in - sub, the subtraction done by the first
+// pass's loader (element-wise, so bit-identical to a separate subtraction); only where fused_bdrt_sub_ok
+template <typename T> int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems, cudaStream_t s, bool *handled, bool rows_in = false, const T *sub = nullptr);
+template <typename T> bool fused_bdrt_sub_ok(int64_t n, int64_t rows);
 
 // adrt.iadrt as fused multi-stage passes (iadrt_fused.cu); workspace in elements
 template <typename T> size_t fused_iadrt_workspace_elems(int64_t B, int64_t n);

@@ -53,12 +53,12 @@ constexpr int min_ctas()
     return tile::Geo<M>::MIN_CTAS;
 }
 
-template <typename T, int M, int LOADK, int STOREK, bool kForward>
+template <typename T, int M, int LOADK, int STOREK, bool kForward, bool kSub = false>
 __global__ void __launch_bounds__(tile::Geo<M>::NT, min_ctas<T, M, LOADK, kForward>())
 pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
 {
     using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
-                                           tile::BwdProgram<T, M, LOADK, STOREK>>::type;
+                                           tile::BwdProgram<T, M, LOADK, STOREK, kSub>>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *buf = reinterpret_cast<T *>(smem_raw);
     T regs[tile::NREG];
@@ -78,6 +78,7 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
     c.in_pitch = a.in_pitch;
     c.out_pitch = a.out_pitch;
     c.q = 0;
+    if (kSub) c.sub_delta = a.sub_delta;
     const int mode = Prog::classify(c);
     if (mode == tile::TILE_SKIP || (mode == tile::TILE_ZERO && a.skip_zero)) return;
 
@@ -99,10 +100,10 @@ pass_kernel(const T *__restrict__ src, T *__restrict__ dst, PassArgs a)
     }
 }
 
-template <typename T, int M, int LOADK, int STOREK, bool kForward>
+template <typename T, int M, int LOADK, int STOREK, bool kForward, bool kSub = false>
 int launch_pass(const T *src, T *dst, const PassArgs &a, int grid_x, int grid_y, cudaStream_t s)
 {
-    auto kern = pass_kernel<T, M, LOADK, STOREK, kForward>;
+    auto kern = pass_kernel<T, M, LOADK, STOREK, kForward, kSub>;
     size_t smem = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value * sizeof(T);
     if (const char *e = getenv("ADRT_B200_SMEM_PAD_KB")) smem += (size_t)atoi(e) * 1024;  // occupancy experiments
     // per device, so not cached in a static: a process may drive several GPUs
@@ -209,6 +210,14 @@ int dispatch_kinds(int load, int store, const T *src, T *dst, const PassArgs &a,
         if (load == LOAD_WROWS && store == STORE_WROWS) return launch_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);
         if (load == LOAD_WROWS && store == STORE_QCOLS) return launch_pass<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(src, dst, a, gx, gy, s);
     } else {
+        if (a.sub_delta != 0) {
+            // subtract-on-load: the first pass of a multi-pass transposed plan (see sub_on_load_ok)
+            if constexpr (M >= 4) {
+                if (load == LOAD_QCOLS && store == STORE_WROWS) return launch_pass<T, M, LOAD_QCOLS, STORE_WROWS, kForward, true>(src, dst, a, gx, gy, s);
+            }
+            set_error("internal: no subtract-on-load kernel for pass kinds %d/%d, %d stages", load, store, M);
+            return ADRT_B200_EINVAL;
+        }
         if (load == LOAD_QCOLS && store == STORE_WROWS) return launch_pass<T, M, LOAD_QCOLS, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);
         if (load == LOAD_QCOLS && store == STORE_QCOLS) return launch_pass<T, M, LOAD_QCOLS, STORE_QCOLS, kForward>(src, dst, a, gx, gy, s);
         if (load == LOAD_WROWS && store == STORE_WROWS) return launch_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(src, dst, a, gx, gy, s);
@@ -462,14 +471,15 @@ int run_plan_cosched(const plan::Plan &pl, const CoCfg &cc, const T *in, T *out,
 
 template <typename T, bool kForward>
 int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, int q_count, T *ws, size_t ws_elems,
-             cudaStream_t s)
+             cudaStream_t s, long long sub_delta = 0)
 {
     // B images of q_count planes each (forward: quadrants q_first .. q_first+q_count-1 of
     // every image; transposed: any plane count, the quadrant identity does not matter)
     const int n = pl.n, D = pl.D;
     const int64_t total = B * q_count;
     const size_t plane_ws = pl.ws_slot_elems[0] + pl.ws_slot_elems[1];
-    const CoCfg cc = cosched_config<T>(pl, total);
+    CoCfg cc = cosched_config<T>(pl, total);
+    if (sub_delta != 0) cc.on = false;
     if (cc.on) {
         // whole batch, one workspace slot (pass 1 -> pass 2), counters behind it
         const size_t ws_need = pl.ws_slot_elems[0] * (size_t)total;
@@ -541,7 +551,7 @@ int run_plan(const plan::Plan &pl, const T *in, T *out, int64_t B, int q_first, 
                 // caller's input: images, a public-layout sinogram, or R-layout rows (plan built with rows_in)
                 const long long in_plane = p.in_pitch ? (long long)n * p.in_pitch : sino_plane;
                 if (kForward) { src = in; a.plane0 = (int)p0; a.src_plane_stride = img_elems; }
-                else { src = in + p0 * in_plane; a.src_plane_stride = in_plane; }
+                else { src = in + p0 * in_plane; a.src_plane_stride = in_plane; a.sub_delta = sub_delta; }
             } else {
                 src = slot[p.src_buf];
                 a.src_plane_stride = (long long)n * p.in_pitch;
@@ -660,9 +670,26 @@ int fused_adrt(const T *in, T *out, int64_t B, int64_t n, int q_first, int q_cou
     return run_plan<T, true>(pl, in, out, B, q_first, q_count, ws, ws_elems, s);
 }
 
+// Can the first pass of the transposed plan subtract a second sinogram while it loads (fused_bdrt's `sub`)?
+// Only the fused_tile.h kernels whose loader runs the first radix-4 step on the public layout do.
+inline bool sub_on_load_ok(const plan::Plan &pl)
+{
+    const plan::Pass &p = pl.pass[0];
+    return pl.npass >= 2 && !p.stream && !p.staged && p.src_buf < 0 && p.in_pitch == 0 && p.load == tile::LOAD_QCOLS &&
+           p.store == tile::STORE_WROWS && p.M >= 4 && p.M <= 6;
+}
+
+template <typename T>
+bool fused_bdrt_sub_ok(int64_t n, int64_t rows)
+{
+    plan::Plan pl;
+    if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl, rows, false)) return false;
+    return sub_on_load_ok(pl);
+}
+
 template <typename T>
 int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t rows, T *ws, size_t ws_elems,
-               cudaStream_t s, bool *handled, bool rows_in)
+               cudaStream_t s, bool *handled, bool rows_in, const T *sub)
 {
     // rows < 2n-1: only offsets d < rows of every output plane are computed, the rest of
     // `out` is left as it was
@@ -671,7 +698,15 @@ int fused_bdrt(const T *in, T *out, int64_t B, int64_t n, int q_count, int64_t r
     // rows_in: `in` holds R-layout rows as written by fused_adrt(..., rows_out = true)
     if (n > kMaxN || !plan::make_transposed_plan(n, sizeof(T), &pl, rows, rows_in)) return ADRT_B200_OK;
     *handled = true;
-    return run_plan<T, false>(pl, in, out, B, 0, q_count, ws, ws_elems, s);
+    long long sub_delta = 0;
+    if (sub) {
+        if (rows_in || !sub_on_load_ok(pl)) {
+            set_error("internal: this transposed plan has no subtract-on-load first pass (n = %lld)", (long long)n);
+            return ADRT_B200_EINVAL;
+        }
+        sub_delta = (long long)(reinterpret_cast<const char *>(sub) - reinterpret_cast<const char *>(in));
+    }
+    return run_plan<T, false>(pl, in, out, B, 0, q_count, ws, ws_elems, s, sub_delta);
 }
 
 template <typename T>
@@ -746,7 +781,8 @@ int fused_bdrt_part(const T *sino, T *xbuf, T *out, int64_t planes, int64_t n, i
     template size_t fused_adrt_workspace_elems<T>(int64_t, int64_t, int);   \
     template size_t fused_bdrt_workspace_elems<T>(int64_t, int64_t, int);   \
     template int fused_adrt<T>(const T *, T *, int64_t, int64_t, int, int, T *, size_t, cudaStream_t, bool *, bool); \
-    template int fused_bdrt<T>(const T *, T *, int64_t, int64_t, int, int64_t, T *, size_t, cudaStream_t, bool *, bool);
+    template int fused_bdrt<T>(const T *, T *, int64_t, int64_t, int, int64_t, T *, size_t, cudaStream_t, bool *, bool, const T *); \
+    template bool fused_bdrt_sub_ok<T>(int64_t, int64_t);
 INSTANTIATE(float)
 INSTANTIATE(double)
 

@@ -101,6 +101,10 @@ struct TileCtx {
     // D - a*j (everything above is the structural +0.0 that the producer no longer writes);
     // sup_gmask < 0: rows are complete up to D
     int sup_loge, sup_gmask;
+    // transposed passes that read the public layout, kSub instantiations only: byte distance from the
+    // sinogram to a second one of the same shape that is subtracted on load (the residual
+    // adrt(x) - b of iadrt_fmg_step, core.py:329, without a pass of its own); 0: none
+    long long sub_delta = 0;
 };
 
 // first offset at which workspace row r of a transposed plan is structurally zero
@@ -965,7 +969,7 @@ ADRT_HD void bwd_radix4_compute_global(const T *src_plane, const TileCtx &c, int
 // as loaded, which saves one tile write and the step's over-wide window reads (1.9 tile reads)
 // of shared-memory traffic.  Lanes walk the butterflies first (NB * 16 contiguous bytes per
 // offset row), then the chunks.  Children are stored exactly where bwd_radix4_store puts them.
-template <typename T, int M, bool kMask, int t>
+template <typename T, int M, bool kMask, int t, bool kSub = false>
 ADRT_HD void bwd_radix4_from_qcols(T *buf, const T *src_plane, const TileCtx &c, int tid)
 {
     constexpr int W = VecOf<T>::L, G = Geo<M>::G, NT = Geo<M>::NT, P = Pitch<T>::value;
@@ -988,7 +992,16 @@ ADRT_HD void bwd_radix4_from_qcols(T *buf, const T *src_plane, const TileCtx &c,
             Pack<T> v[4 / W];
             if (!kMask || x + i < dt) {
 #pragma unroll
-                for (int k = 0; k < 4 / W; ++k) v[k] = *reinterpret_cast<const Pack<T> *>(col + (long long)(x + i) * n1 + k * W);
+                for (int k = 0; k < 4 / W; ++k) {
+                    const T *pv = col + (long long)(x + i) * n1 + k * W;
+                    v[k] = *reinterpret_cast<const Pack<T> *>(pv);
+                    if constexpr (kSub) {
+                        // element-wise "a - b" exactly as the separate subtraction kernel computes it
+                        const Pack<T> w = *reinterpret_cast<const Pack<T> *>(reinterpret_cast<const char *>(pv) + c.sub_delta);
+#pragma unroll
+                        for (int q = 0; q < W; ++q) v[k].v[q] = v[k].v[q] - w.v[q];
+                    }
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < 4 / W; ++k)
@@ -1273,7 +1286,7 @@ struct FwdProgram {
     }
 };
 
-template <typename T, int M, int LOADK, int STOREK>
+template <typename T, int M, int LOADK, int STOREK, bool kSub = false>
 struct BwdProgram {
     static constexpr int G = Geo<M>::G;
     // odd M writing workspace rows: the transposed stage 0 is done by the store
@@ -1291,6 +1304,7 @@ struct BwdProgram {
     // loader (bwd_radix4_from_qcols); phases 1 and 2 are then empty
     static constexpr bool kFusedLoad = LOADK == LOAD_QCOLS && NS > 0 && (step_t(0) + 2 <= M) && M >= 4 &&
                                        (4 << step_t(0)) == G;
+    static_assert(!kSub || kFusedLoad, "subtract-on-load exists for the fused public-layout loader only");
 
     ADRT_HD static int classify(const TileCtx &c)
     {
@@ -1312,8 +1326,8 @@ struct BwdProgram {
     ADRT_HD static void phase_ct(int mode, T *buf, T (&regs)[NREG], const T *src, T *dst, const TileCtx &c, int tid)
     {
         if constexpr (PH == 0 && kFusedLoad) {
-            if (mode == TILE_FULL_MASKED) bwd_radix4_from_qcols<T, M, true, step_t(0)>(buf, src, c, tid);
-            else bwd_radix4_from_qcols<T, M, false, step_t(0)>(buf, src, c, tid);
+            if (mode == TILE_FULL_MASKED) bwd_radix4_from_qcols<T, M, true, step_t(0), kSub>(buf, src, c, tid);
+            else bwd_radix4_from_qcols<T, M, false, step_t(0), kSub>(buf, src, c, tid);
         } else if constexpr (kFusedLoad && (PH == 1 || PH == 2)) {
             // done in phase 0
         } else if constexpr (PH == 0) {

@@ -19,6 +19,7 @@ struct PassArgs {
     int side_idx;           // host only: which helper stream (aux_stream) takes the boundary tiles of this launch
     int skip_zero;          // transposed: all-zero tiles are not written (plan::Pass::skip_zero)
     int sup_loge, sup_gmask;   // transposed: geometry of the producer that skipped them (TileCtx::sup_*)
+    long long sub_delta = 0;   // transposed public-layout loader: subtract the sinogram this many bytes away (TileCtx::sub_delta)
 };
 
 // Persistent, plane-ordered scheduling of one pass (sched.cuh); next == nullptr: ordinary grid launch.
