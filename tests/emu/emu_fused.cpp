@@ -23,11 +23,14 @@ namespace {
 // groups (blockIdx.y range) the next pass runs: angle-block sharding runs a rank's share only
 int g_y_off = 0, g_y_cnt = -1;
 
-template <typename T, int M, int LOADK, int STOREK, bool kForward>
+// subtract-on-load (BwdProgram<..., kSub>): byte distance from the sinogram to the one subtracted, 0 = off
+long long g_sub_delta = 0;
+
+template <typename T, int M, int LOADK, int STOREK, bool kForward, bool kSub = false>
 void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int planes, long long sps, long long dps)
 {
     using Prog = typename std::conditional<kForward, tile::FwdProgram<T, M, LOADK, STOREK>,
-                                           tile::BwdProgram<T, M, LOADK, STOREK>>::type;
+                                           tile::BwdProgram<T, M, LOADK, STOREK, kSub>>::type;
     // Pack<T> accesses need 16-byte alignment: allocate as Pack vectors
     const size_t cells = (size_t)tile::Geo<M>::G * tile::Pitch<T>::value;
     std::vector<tile::Pack<T>> storeA(cells / tile::VecOf<T>::L + 1);
@@ -47,6 +50,7 @@ void run_pass(const plan::Pass &p, const T *src, T *dst, int n, int D, int plane
                 c.sup_loge = p.sup_loge; c.sup_gmask = p.sup_gmask;
                 c.in_pitch = p.in_pitch; c.out_pitch = p.out_pitch;
                 c.q = 0;
+                c.sub_delta = kSub ? g_sub_delta : 0;
                 const int mode = Prog::classify(c);
                 if (mode == tile::TILE_SKIP || (mode == tile::TILE_ZERO && p.skip_zero)) continue;
                 const T *sp;
@@ -217,6 +221,12 @@ void run_kinds(const plan::Pass &p, const T *src, T *dst, int n, int D, int plan
         else if (p.load == LOAD_WROWS && p.store == STORE_WROWS) run_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(p, src, dst, n, D, planes, sps, dps);
         else run_pass<T, M, LOAD_WROWS, STORE_QCOLS, kForward>(p, src, dst, n, D, planes, sps, dps);
     } else {
+        if constexpr (M >= 4) {
+            if (g_sub_delta != 0 && p.src_buf < 0 && p.load == LOAD_QCOLS && p.store == STORE_WROWS) {
+                run_pass<T, M, LOAD_QCOLS, STORE_WROWS, kForward, true>(p, src, dst, n, D, planes, sps, dps);
+                return;
+            }
+        }
         if (p.load == LOAD_QCOLS && p.store == STORE_WROWS) run_pass<T, M, LOAD_QCOLS, STORE_WROWS, kForward>(p, src, dst, n, D, planes, sps, dps);
         else if (p.load == LOAD_QCOLS && p.store == STORE_QCOLS) run_pass<T, M, LOAD_QCOLS, STORE_QCOLS, kForward>(p, src, dst, n, D, planes, sps, dps);
         else if (p.load == LOAD_WROWS && p.store == STORE_WROWS) run_pass<T, M, LOAD_WROWS, STORE_WROWS, kForward>(p, src, dst, n, D, planes, sps, dps);
@@ -340,6 +350,23 @@ int run_parts(const T *in, T *out, int64_t B, int64_t n64, int parts, int m_last
         if (run_range(xi + 1, np - 1, part, xbuf[part].data(), out)) return 3;
     }
     return 0;
+}
+
+// bdrt(a - b) with the subtraction done by the loader of the first pass (iadrt_fmg_step's residual);
+// returns 4 when the plan of this size has no such first pass (the engine then subtracts separately)
+template <typename T>
+int run_bdrt_sub(const T *a, const T *b, T *out, int64_t B, int64_t n, int64_t rows)
+{
+    plan::Plan pl;
+    if (!plan::make_transposed_plan(n, sizeof(T), &pl, rows, false)) return 1;
+    const plan::Pass &p = pl.pass[0];
+    if (!(pl.npass >= 2 && !p.stream && !p.staged && p.src_buf < 0 && p.in_pitch == 0 && p.load == tile::LOAD_QCOLS &&
+          p.store == tile::STORE_WROWS && p.M >= 4 && p.M <= 6))
+        return 4;
+    g_sub_delta = (long long)(reinterpret_cast<const char *>(b) - reinterpret_cast<const char *>(a));
+    const int rc = run<T, false>(a, out, B, n, rows, false);
+    g_sub_delta = 0;
+    return rc;
 }
 
 // fused normal operator data flow: adrt with R-layout rows out (`mid`: B * 4 * n * round4(2n-1) elements),
@@ -469,6 +496,8 @@ extern "C" {
 int emu_iadrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run_iadrt<float>(in, out, B, n); }
 int emu_iadrt_f64(const double *in, double *out, int64_t B, int64_t n) { return run_iadrt<double>(in, out, B, n); }
 void emu_set_order(int order) { g_order = order; }
+int emu_bdrt_sub_f32(const float *a, const float *b, float *out, int64_t B, int64_t n, int64_t rows) { return run_bdrt_sub<float>(a, b, out, B, n, rows); }
+int emu_bdrt_sub_f64(const double *a, const double *b, double *out, int64_t B, int64_t n, int64_t rows) { return run_bdrt_sub<double>(a, b, out, B, n, rows); }
 long long emu_stream_tiles(void) { return g_stream_tiles; }
 long long emu_staged_tiles(void) { return g_staged_tiles; }
 int emu_adrt_f32(const float *in, float *out, int64_t B, int64_t n) { return run<float, true>(in, out, B, n); }

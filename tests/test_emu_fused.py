@@ -131,6 +131,34 @@ def test_bdrt_rows(emu, n, rows, split):
         os.environ.pop("ADRT_B200_SPLIT_BDRT", None)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,rows,split", [(128, 128, None), (256, 256, None), (256, 511, "4,4"), (512, 512, None), (1024, 1024, None)])
+def test_bdrt_subtract_on_load(emu, n, rows, split, dt):
+    # iadrt_fmg_step's residual (core.py:329): bdrt(a - b) with the subtraction done by the loader of the
+    # first pass (BwdProgram<..., kSub>) == bdrt of the separately subtracted sinogram, bit for bit,
+    # masked boundary tiles and signed zeros included (a == b gives +0.0 where a copy would keep -0.0)
+    os.environ.pop("ADRT_B200_SPLIT_BDRT", None)
+    if split:
+        os.environ["ADRT_B200_SPLIT_BDRT"] = split
+    try:
+        suffix = "f32" if dt == np.float32 else "f64"
+        a = make_sino(41 + n, (1, 4, 2 * n - 1, n), dt)
+        b = make_sino(43 + n, (1, 4, 2 * n - 1, n), dt)
+        b.reshape(-1)[::7] = a.reshape(-1)[::7]
+        a.reshape(-1)[::11] = -0.0
+        out = np.full(a.shape, np.nan, dtype=dt)
+        rc = getattr(emu, f"emu_bdrt_sub_{suffix}")(ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(b.ctypes.data),
+                                                    ctypes.c_void_p(out.ctypes.data), ctypes.c_int64(1), ctypes.c_int64(n),
+                                                    ctypes.c_int64(rows))
+        if rc == 4:
+            pytest.skip("the plan of this size has no public-layout first pass with a fused step")
+        assert rc == 0
+        want = O.bdrt(a - b)
+        assert bytes_equal(out[:, :, :rows], want[:, :, :rows]), first_diff(out[:, :, :rows], want[:, :, :rows])
+    finally:
+        os.environ.pop("ADRT_B200_SPLIT_BDRT", None)
+
+
 # ---------------------------------------------------------------------------------------------
 # Streaming passes (adrt_b200/csrc/stream_tile.h: fp32, 5 or 6 stages, butterflies with register
 # history, in-place tiles).  ADRT_B200_STREAM_SET=all forces every pass kind through them; each case
