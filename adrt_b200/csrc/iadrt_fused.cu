@@ -15,8 +15,21 @@ constexpr int kDefaultWarps = 4;
 // measured 8.0 / 8.9 / 7.8 / 8.8 ms against 7.5 ms at 16 x 2048^2 fp32: the sweep is issue bound, and
 // the spills of the tighter bounds cost more than the extra warps give.
 
+// A/B knobs (tools/build_variant.sh): resident blocks the register allocation aims at for the five- / four-level
+// passes (0: threads only)
+#ifndef ADRT_IADRT_MINB5
+#define ADRT_IADRT_MINB5 0
+#endif
+#ifndef ADRT_IADRT_MINB4
+#define ADRT_IADRT_MINB4 0
+#endif
+template <int M, int W> constexpr int iadrt_min_blocks()
+{
+    return W != 4 ? 0 : (M == 5 ? ADRT_IADRT_MINB5 : (M == 4 ? ADRT_IADRT_MINB4 : 0));
+}
+
 template <typename T, int M, bool kInQ, bool kOutQ, int kWarpsPerBlock>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, iadrt_min_blocks<M, kWarpsPerBlock>())
 iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes, int n, int s0)
 {
     using G = itile::Geo<M>;
