@@ -60,6 +60,12 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
         itile::LaneState<T, M> st;
 #pragma unroll
         for (int t = 0; t <= M; ++t) st.prev[t] = T(0);
+        st.h1 = st.h2 = T(0);
+        // the other lane of the pair's h2 (last level from registers, iadrt_tile.h Geo::kRegLast)
+        auto partner = [](T h2) -> T {
+            if constexpr (G::kRegLast) return __shfl_xor_sync(0xffffffffu, h2, 1);
+            else return h2;
+        };
         itile::fetch_inputs<T, kInQ>(ip, tm, top, st.v);
         for (int X0 = top; X0 >= -M; X0 -= 8) {
             itile::commit_inputs<T, M>(ring, tm, lane, X0, st.v);
@@ -71,22 +77,22 @@ iadrt_pass_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t planes,
                 itile::trip_setup<M, kOutQ>(lc, X4, ta);
                 __syncwarp();
                 if (X4 - 3 >= ilo && X4 <= ihi) {
-                    itile::all_levels_interior<T, M, kOutQ, 0>(ring, ta, n, X4, st, op);
+                    itile::all_levels_interior<T, M, kOutQ, 0>(ring, lc, ta, n, X4, st, op, partner(st.h2));
                     __syncwarp();
-                    itile::all_levels_interior<T, M, kOutQ, 1>(ring, ta, n, X4, st, op);
+                    itile::all_levels_interior<T, M, kOutQ, 1>(ring, lc, ta, n, X4, st, op, partner(st.h2));
                     __syncwarp();
-                    itile::all_levels_interior<T, M, kOutQ, 2>(ring, ta, n, X4, st, op);
+                    itile::all_levels_interior<T, M, kOutQ, 2>(ring, lc, ta, n, X4, st, op, partner(st.h2));
                     __syncwarp();
-                    itile::all_levels_interior<T, M, kOutQ, 3>(ring, ta, n, X4, st, op);
+                    itile::all_levels_interior<T, M, kOutQ, 3>(ring, lc, ta, n, X4, st, op, partner(st.h2));
                     __syncwarp();
                 } else {
-                    itile::all_levels<T, M, kOutQ, 0>(ring, lc, ta, n, X4, st, op);
+                    itile::all_levels<T, M, kOutQ, 0>(ring, lc, ta, n, X4, st, op, partner(st.h2));
                     __syncwarp();
-                    itile::all_levels<T, M, kOutQ, 1>(ring, lc, ta, n, X4, st, op);
+                    itile::all_levels<T, M, kOutQ, 1>(ring, lc, ta, n, X4, st, op, partner(st.h2));
                     __syncwarp();
-                    itile::all_levels<T, M, kOutQ, 2>(ring, lc, ta, n, X4, st, op);
+                    itile::all_levels<T, M, kOutQ, 2>(ring, lc, ta, n, X4, st, op, partner(st.h2));
                     __syncwarp();
-                    itile::all_levels<T, M, kOutQ, 3>(ring, lc, ta, n, X4, st, op);
+                    itile::all_levels<T, M, kOutQ, 3>(ring, lc, ta, n, X4, st, op, partner(st.h2));
                     __syncwarp();
                 }
             }

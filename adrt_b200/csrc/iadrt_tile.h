@@ -66,7 +66,13 @@ template <int M> struct Geo {
     // r0 + 3 - u, whatever the lane's own look-ahead: one address per operand and trip, the rows as
     // immediate offsets (the address arithmetic was 10 of the 16 instructions per node and row).
     static constexpr int MIRROR = 3;
-    ADRT_HD static constexpr int base(int t) { return t == 0 ? 0 : base(t - 1) + depth(t - 1) + MIRROR; }
+    // The LAST level reads its two parents from registers: node (M, lambda) has j = 0, so its parents are the
+    // level-(M-1) nodes of its own lane pair (lanes lambda & ~1 and lambda | 1) one row and two rows back --
+    // a lane keeps its last two level-(M-1) values (LaneState::h1 / h2) and one warp shuffle per row step
+    // brings the partner's; level M-1 has no ring (M >= 2; level 0 is the input ring).
+    static constexpr bool kRegLast = M >= 2;
+    ADRT_HD static constexpr int rows_of(int t) { return (kRegLast && t == M - 1) ? 0 : depth(t) + MIRROR; }
+    ADRT_HD static constexpr int base(int t) { return t == 0 ? 0 : base(t - 1) + rows_of(t - 1); }
     static constexpr int OUT_DEPTH = 16;          // level-M ring (workspace stores): one aligned group of 8 + skew
     static constexpr int OUT_BASE = base(M);
     static constexpr int ROWS = OUT_BASE + OUT_DEPTH;   // ring rows per warp (x 32 lanes)
@@ -86,6 +92,7 @@ struct Team {
 template <typename T, int M> struct LaneState {
     T prev[M + 1];     // running scan value of the lane's node at level t (index t, 1..M)
     T v[8];            // eight input rows fetched for the next pair of trips
+    T h1, h2;          // Geo::kRegLast: the lane's level-(M-1) values at the last level's row x and at x + 1
 };
 
 // Per-lane constants of the sweep, one set per level t = 1..M (index t): where the two operands of the
@@ -101,6 +108,7 @@ template <int M> struct LaneConst {
     int lo[M + 1], hi[M + 1];       // node exists for lo <= X <= hi
     int thr1[M + 1], thr2[M + 1];   // first / second term exists for X <= thr
     int own[M + 1];                 // ring element offset (row 0) of the lane's own column at level t
+    bool odd_last;                  // parity of the lane's last-level node (Geo::kRegLast)
 };
 
 template <int M, int t = 1>
@@ -126,6 +134,7 @@ ADRT_HD void setup_levels(const Team &tm, int team_lane0, int k, int lane, LaneC
         lc.thr2[t] = odd ? t_odd : tm.D - 2 + psi - t;  // even: d + 1 < D
         if (!tm.active) { lc.lo[t] = 1; lc.hi[t] = 0; } // padding team: no node ever exists
         lc.own[t] = (t < M ? Geo<M>::base(t) : Geo<M>::OUT_BASE) * kLanes + lane;
+        if (t == M) lc.odd_last = odd;
         setup_levels<M, t + 1>(tm, team_lane0, k, lane, lc);
     }
 }
@@ -253,20 +262,33 @@ ADRT_HD void commit_inputs(T *ring, const Team &tm, int lane, int X0, const T (&
 template <typename T, int M, int U, int t = 1>
 ADRT_HD void load_levels(const T *ring, const TripAddr<M> &ta, T (&first)[M + 1], T (&second)[M + 1])
 {
-    if constexpr (t <= M) {
+    if constexpr (t <= (Geo<M>::kRegLast ? M - 1 : M)) {
         first[t] = ring[ta.F[t] - (U << 5)];
         second[t] = ring[ta.S[t] - (U << 5)];
         load_levels<T, M, U, t + 1>(ring, ta, first, second);
     }
 }
 
+// operands of the last level from the lane pair's registers (`partner_h2`: the other lane's h2, by shuffle)
+template <typename T, int M>
+ADRT_HD void last_level_operands(const LaneConst<M> &lc, const LaneState<T, M> &st, T partner_h2, T (&first)[M + 1],
+                                 T (&second)[M + 1])
+{
+    if constexpr (Geo<M>::kRegLast) {
+        first[M] = lc.odd_last ? st.h2 : st.h1;    // even: A[x] (own, one row back); odd: A1[x + 1] (own, two back)
+        second[M] = partner_h2;                     // even: A1[x + 1]; odd: A[x + 1]
+    }
+}
+
 template <typename T, int M, bool kOutQ, int U, int t>
-ADRT_HD void put_node(T *ring, const TripAddr<M> &ta, int n, int x, T acc, T *out_ptr)
+ADRT_HD void put_node(T *ring, const TripAddr<M> &ta, int n, int x, T acc, T *out_ptr, T &hnew)
 {
     constexpr int c = (3 + t) & 3;
     constexpr int i = U <= c ? c - U : 4 + c - U;          // row of its aligned group
-    const int w = (U <= c ? ta.W0[t] : ta.W1[t]) + (i << 5);
-    if constexpr (t < M) {
+    if constexpr (Geo<M>::kRegLast && t == M - 1) {
+        hnew = acc;
+    } else if constexpr (t < M) {
+        const int w = (U <= c ? ta.W0[t] : ta.W1[t]) + (i << 5);
         constexpr int dw = Geo<M>::depth(t);
         ring[w] = acc;
         if constexpr (i >= 1) {
@@ -277,13 +299,13 @@ ADRT_HD void put_node(T *ring, const TripAddr<M> &ta, int n, int x, T acc, T *ou
     } else if constexpr (kOutQ) {
         out_ptr[(long long)x * n] = acc;
     } else {
-        ring[w] = acc;
+        ring[(U <= c ? ta.W0[t] : ta.W1[t]) + (i << 5)] = acc;
     }
 }
 
 template <typename T, int M, bool kOutQ, int U, int t = 1>
 ADRT_HD void guarded_levels(T *ring, const LaneConst<M> &lc, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st,
-                            T *out_ptr, const T (&first)[M + 1], const T (&second)[M + 1])
+                            T *out_ptr, const T (&first)[M + 1], const T (&second)[M + 1], T &hnew)
 {
     if constexpr (t <= M) {
         const int X = X0 - U;
@@ -292,41 +314,50 @@ ADRT_HD void guarded_levels(T *ring, const LaneConst<M> &lc, const TripAddr<M> &
         acc = X < lc.hi[t] ? acc + st.prev[t] : acc;
         if (X >= lc.lo[t] && X <= lc.hi[t]) {
             st.prev[t] = acc;
-            put_node<T, M, kOutQ, U, t>(ring, ta, n, X + t, acc, out_ptr);
+            put_node<T, M, kOutQ, U, t>(ring, ta, n, X + t, acc, out_ptr, hnew);
         }
-        guarded_levels<T, M, kOutQ, U, t + 1>(ring, lc, ta, n, X0, st, out_ptr, first, second);
+        guarded_levels<T, M, kOutQ, U, t + 1>(ring, lc, ta, n, X0, st, out_ptr, first, second, hnew);
     }
 }
 
 template <typename T, int M, bool kOutQ, int U>
 ADRT_HD void all_levels(T *ring, const LaneConst<M> &lc, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st,
-                        T *out_ptr)
+                        T *out_ptr, T partner_h2)
 {
     T first[M + 1], second[M + 1];
     load_levels<T, M, U>(ring, ta, first, second);
-    guarded_levels<T, M, kOutQ, U>(ring, lc, ta, n, X0, st, out_ptr, first, second);
+    last_level_operands<T, M>(lc, st, partner_h2, first, second);
+    T hnew = st.h1;     // where the level-(M-1) node does not exist the value is never used
+    guarded_levels<T, M, kOutQ, U>(ring, lc, ta, n, X0, st, out_ptr, first, second, hnew);
+    st.h2 = st.h1;
+    st.h1 = hnew;
 }
 
 // The same for base rows where every term of every level exists for every lane of the warp
 // (interior_range): no comparisons, no selects.
 template <typename T, int M, bool kOutQ, int U, int t = 1>
 ADRT_HD void interior_levels(T *ring, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st, T *out_ptr,
-                             const T (&first)[M + 1], const T (&second)[M + 1])
+                             const T (&first)[M + 1], const T (&second)[M + 1], T &hnew)
 {
     if constexpr (t <= M) {
         const T acc = ((T(0) + first[t]) - second[t]) + st.prev[t];
         st.prev[t] = acc;
-        put_node<T, M, kOutQ, U, t>(ring, ta, n, X0 - U + t, acc, out_ptr);
-        interior_levels<T, M, kOutQ, U, t + 1>(ring, ta, n, X0, st, out_ptr, first, second);
+        put_node<T, M, kOutQ, U, t>(ring, ta, n, X0 - U + t, acc, out_ptr, hnew);
+        interior_levels<T, M, kOutQ, U, t + 1>(ring, ta, n, X0, st, out_ptr, first, second, hnew);
     }
 }
 
 template <typename T, int M, bool kOutQ, int U>
-ADRT_HD void all_levels_interior(T *ring, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st, T *out_ptr)
+ADRT_HD void all_levels_interior(T *ring, const LaneConst<M> &lc, const TripAddr<M> &ta, int n, int X0, LaneState<T, M> &st,
+                                 T *out_ptr, T partner_h2)
 {
     T first[M + 1], second[M + 1];
     load_levels<T, M, U>(ring, ta, first, second);
-    interior_levels<T, M, kOutQ, U>(ring, ta, n, X0, st, out_ptr, first, second);
+    last_level_operands<T, M>(lc, st, partner_h2, first, second);
+    T hnew = st.h1;
+    interior_levels<T, M, kOutQ, U>(ring, ta, n, X0, st, out_ptr, first, second, hnew);
+    st.h2 = st.h1;
+    st.h1 = hnew;
 }
 
 // Base rows X for which this lane needs no guard at any level: [lo, hi] (empty for padding teams).

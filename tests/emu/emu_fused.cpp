@@ -379,15 +379,18 @@ int run_normal(const T *in, T *mid, T *out, int64_t B, int64_t n, int64_t rows)
     return run<T, false>(mid, out, B, n, rows, true);
 }
 // ---- fused iadrt passes (iadrt_tile.h): the 32 lanes of every warp played phase by phase ------------
-// one base row X0 - U for the 32 lanes of a warp, in the configured lane order
+// one base row X0 - U for the 32 lanes of a warp, in the configured lane order; the shuffle that brings the
+// partner lane's h2 reads all lanes' registers before any lane computes
 template <typename T, int M, bool kOutQ, int U>
 void iadrt_row(bool interior, T *ring, const itile::LaneConst<M> *lc, const itile::TripAddr<M> *ta, int n, int X0,
                itile::LaneState<T, M> *st, T **op)
 {
+    T ph2[32];
+    for (int lane = 0; lane < 32; ++lane) ph2[lane] = st[lane ^ 1].h2;
     for (int i = 0; i < 32; ++i) {
         const int lane = g_order ? 31 - i : i;
-        if (interior) itile::all_levels_interior<T, M, kOutQ, U>(ring, ta[lane], n, X0, st[lane], op[lane]);
-        else itile::all_levels<T, M, kOutQ, U>(ring, lc[lane], ta[lane], n, X0, st[lane], op[lane]);
+        if (interior) itile::all_levels_interior<T, M, kOutQ, U>(ring, lc[lane], ta[lane], n, X0, st[lane], op[lane], ph2[lane]);
+        else itile::all_levels<T, M, kOutQ, U>(ring, lc[lane], ta[lane], n, X0, st[lane], op[lane], ph2[lane]);
     }
 }
 
@@ -419,6 +422,7 @@ void run_iadrt_pass(const T *in, T *out, int64_t planes, int n, int s0)
                 ip[lane] = in + plane * in_plane + (kInQ ? tm[lane].in_col + k : (tm[lane].in_col + k) * (long long)(2 * n));
                 op[lane] = out + plane * out_plane + (kOutQ ? tm[lane].out_col + k : (tm[lane].out_col + (long long)k * tm[lane].out_stride) * (long long)(2 * n));
                 for (int t = 0; t <= M; ++t) st[lane].prev[t] = T(0);
+                st[lane].h1 = st[lane].h2 = T(NAN);
                 for (int e = 0; e < 8; ++e) st[lane].v[e] = T(NAN);
                 itile::fetch_inputs<T, kInQ>(ip[lane], tm[lane], top, st[lane].v);
             }
