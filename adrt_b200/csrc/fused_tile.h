@@ -655,23 +655,27 @@ ADRT_HD void fwd_load_wrows_stage0(T *buf, const T *src_plane, const TileCtx &c,
 template <typename T, int M, int LH, int TD, int S>
 ADRT_HD void fwd_store_row(const T *b, T *row, const TileCtx &c, int lim, bool zero, int lane)
 {
-    constexpr int Q = (4 - S) & 3;
+    // a lane moves ONE 16-byte vector per trip (4 floats / 2 doubles), so consecutive lanes touch consecutive
+    // 16-byte slots of the tile row and of the global row: with 4 doubles per lane (32-byte lane stride) the
+    // window loads paid 2.2 x their ideal shared-memory wavefronts (profiles/r06_pass_phases_f64.txt, F1)
+    constexpr int CW = VecOf<T>::L;
+    constexpr int Q = ((CW - S) % CW + CW) % CW;
 #pragma unroll
-    for (int k = 0; k < (TD / V + 31) / 32; ++k) {
-        const int xc = (k * 32 + lane) * V;      // gp - d0
+    for (int k = 0; k < (TD / CW + 31) / 32; ++k) {
+        const int xc = (k * 32 + lane) * CW;     // gp - d0
         const int gp = c.d0 + xc;
         if (xc < TD && gp < c.out_pitch) {
-            T v[V];
+            T v[CW];
             if (zero) {
 #pragma unroll
-                for (int i = 0; i < V; ++i) v[i] = T(0.0);
+                for (int i = 0; i < CW; ++i) v[i] = T(0.0);
             } else {
-                load_window<T, V, Q>(b + (LH + xc - S - Q), v);
+                load_window<T, CW, Q>(b + (LH + xc - S - Q), v);
 #pragma unroll
-                for (int i = 0; i < V; ++i)
+                for (int i = 0; i < CW; ++i)
                     if (gp - S + i >= lim) v[i] = T(0.0);
             }
-            store_chunk<T>(row + gp, v);
+            store_cv<T>(row + gp, v);
         }
     }
 }
