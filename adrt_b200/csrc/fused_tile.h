@@ -491,6 +491,95 @@ ADRT_HD void fwd_radix2_store(T *buf, int tid, const T (&o)[NREG])
 // >= n are +0.0 (same rule as fwd_load_image).  Needs ~64 registers for its 4 x 7 operands: used
 // by the fp64 passes (128 registers anyway) and the fp32 six-stage pass (64); fp32 five-stage passes
 // are faster with the plain loader at 48 registers / 5 CTAs per SM (measured 292 vs 315 us).
+// Interior tiles of the fp64 instantiations (every window of every job inside the image -- a CTA-uniform test):
+// the jobs of TWO rounds are loaded before either is used.  A six-stage fp64 tile is alone on its SM (140 KB,
+// 512 threads at 128 registers), and four dependent rounds of 8-10 16-byte loads per thread left only 64 KB per SM
+// in flight: 38 % of the kernel's stall samples sat on the first use of each round
+// (profiles/r06_pass_phases_f64.txt).  Same loads, same adds in the same order.
+template <typename T, int M, bool kCols>
+ADRT_HD void fwd_radix4_from_image_interior(T *buf, const T *img, const TileCtx &c, int tid, int dbase)
+{
+    constexpr int W = VecOf<T>::L, G = Geo<M>::G, NT = Geo<M>::NT, P = Pitch<T>::value;
+    constexpr int NB = G / 4, NCH = XW / W, JOBS = NB * NCH, ROUNDS = JOBS / NT;
+    constexpr int NP = (2 * W + 2) / W;
+    constexpr int NRAW = kCols ? (W + 3) * (4 / W) : 4 * NP;
+    static_assert(JOBS % NT == 0 && ROUNDS % 2 == 0, "rounds are paired");
+    const int n = c.n;
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; rd += 2) {
+        Pack<T> raw[2][NRAW];
+        int k0s[2], xs[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int job = tid + (rd + u) * NT;
+            int k0, chunk;
+            if (kCols) {
+                const int rest = job >> 3;
+                k0 = 2 * (rest % (NB / 2)) + (job & 1);
+                chunk = 4 * (rest / (NB / 2)) + ((job >> 1) & 3);
+            } else {
+                k0 = job / NCH;
+                chunk = job % NCH;
+            }
+            k0s[u] = k0;
+            xs[u] = chunk * W;
+            // jobs below the step's lo_out store nothing; they fetch the window of x = 4 so that no address leaves the image
+            const int x = xs[u] < 4 ? 4 : xs[u];
+            const int r0 = c.g * G + 4 * k0;
+            if (kCols) {
+                const int dlo = dbase + x - 3;
+#pragma unroll
+                for (int i = 0; i < W + 3; ++i) {
+                    const int d = dlo + i;
+                    const T *rp = img + (long long)(c.q == 1 ? n - 1 - d : d) * n + r0;
+#pragma unroll
+                    for (int k = 0; k < 4 / W; ++k) raw[u][i * (4 / W) + k] = *reinterpret_cast<const Pack<T> *>(rp + k * W);
+                }
+            } else {
+                const int col_lo = n - dbase - x - W;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const T *rp = img + (long long)(c.q == 0 ? r0 + j : n - 1 - (r0 + j)) * n + col_lo;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) raw[u][j * NP + k] = *reinterpret_cast<const Pack<T> *>(rp + k * W);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (xs[u] < 4) continue;
+            T w[4][W + 3];                       // w[j][i] = parent j at offset dlo + i
+            if (kCols) {
+#pragma unroll
+                for (int i = 0; i < W + 3; ++i)
+#pragma unroll
+                    for (int k = 0; k < 4 / W; ++k)
+#pragma unroll
+                        for (int q = 0; q < W; ++q) w[k * W + q][i] = raw[u][i * (4 / W) + k].v[q];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < W + 3; ++i) w[j][i] = raw[u][j * NP + (W + 2 - i) / W].v[(W + 2 - i) % W];
+            }
+            T y0[W], y1[W + 1], y2[W + 2], y3[W + 3];
+#pragma unroll
+            for (int i = 0; i < W; ++i) y0[i] = w[0][i + 3];
+#pragma unroll
+            for (int i = 0; i < W + 1; ++i) y1[i] = w[1][i + 2];
+#pragma unroll
+            for (int i = 0; i < W + 2; ++i) y2[i] = w[2][i + 1];
+#pragma unroll
+            for (int i = 0; i < W + 3; ++i) y3[i] = w[3][i];
+            T o[4 * W];
+            fwd_radix4_math<T>(y0, y1, y2, y3, o);
+            T *orow = buf + (4 * k0s[u]) * P + xs[u];
+#pragma unroll
+            for (int p4 = 0; p4 < 4; ++p4) store_cv<T>(orow + p4 * P, &o[p4 * W]);
+        }
+    }
+}
+
 template <typename T, int M, int LH>
 ADRT_HD void fwd_radix4_from_image(T *buf, const T *img, const TileCtx &c, int tid)
 {
@@ -500,6 +589,13 @@ ADRT_HD void fwd_radix4_from_image(T *buf, const T *img, const TileCtx &c, int t
     const int n = c.n;
     const int dbase = c.d0 - LH;
     const bool cols = (c.q == 1 || c.q == 2);
+    if constexpr (sizeof(T) == 8 && JOBS % NT == 0 && ROUNDS % 2 == 0) {
+        if (dbase >= 0 && dbase + XW <= n) {
+            if (cols) fwd_radix4_from_image_interior<T, M, true>(buf, img, c, tid, dbase);
+            else fwd_radix4_from_image_interior<T, M, false>(buf, img, c, tid, dbase);
+            return;
+        }
+    }
 #pragma unroll
     for (int rd = 0; rd < ROUNDS; ++rd) {
         const int job = tid + rd * NT;
@@ -962,7 +1058,10 @@ ADRT_HD void bwd_radix4_compute_global(const T *src_plane, const TileCtx &c, int
 #pragma unroll
     for (int cc = 0; cc < CHUNKS; ++cc) {
         const int x = (lane + 32 * cc) * V;
-        if (bwd_chunk_ok<T>(x, 0, a)) bwd_radix4_chunk<T, false, 0>(ip, c.in_pitch, a, x, 0, 0, 0, &o[cc * 4 * V]);
+        // doubles: x + V + 6 <= pitch for every chunk, and without the test the chunks form one basic block whose
+        // global loads the compiler may issue ahead of the previous chunk's adds
+        if (XW + 6 <= Pitch<T>::value || bwd_chunk_ok<T>(x, 0, a))
+            bwd_radix4_chunk<T, false, 0>(ip, c.in_pitch, a, x, 0, 0, 0, &o[cc * 4 * V]);
     }
 }
 
@@ -986,6 +1085,42 @@ ADRT_HD void bwd_radix4_from_qcols(T *buf, const T *src_plane, const TileCtx &c,
     const int lim_p = dt, lim_1 = dt + c.a_g * 2 * e;
     const T *col = src_plane + (long long)c.d0 * n1 + c.g * G + 4 * a;
     T *orow = buf + a * P;
+    // fp64 interior tiles: the pieces of TWO chunks are fetched before either is used (2 x 10 16-byte loads in
+    // flight per thread instead of 10, two dependent rounds per tile instead of four: 53 % of the five-stage fp64
+    // kernel's stall samples sat in this loader with 2 x 256 threads per SM, profiles/r06_pass_phases_f64.txt);
+    // every chunk of a double tile is live (NCH = SLOTS * CPT, XW + 6 <= pitch), so the pairs need no tests
+    if constexpr (sizeof(T) == 8 && !kMask && !kSub && NCH % SLOTS == 0 && CPT % 2 == 0 && XW + 6 <= P) {
+#pragma unroll
+        for (int cc = 0; cc < CPT; cc += 2) {
+            Pack<T> raw[2][W + 3][4 / W];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int x = (slot + (cc + u) * SLOTS) * W;
+#pragma unroll
+                for (int i = 0; i < W + 3; ++i)
+#pragma unroll
+                    for (int k = 0; k < 4 / W; ++k)
+                        raw[u][i][k] = *reinterpret_cast<const Pack<T> *>(col + (long long)(x + i) * n1 + k * W);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int x = (slot + (cc + u) * SLOTS) * W;
+                T g0[W], g1[W + 1], g2[W + 2], g3[W + 3];
+#pragma unroll
+                for (int i = 0; i < W + 3; ++i) {
+                    if (i < W) g0[i] = raw[u][i][0].v[0];
+                    if (i < W + 1) g1[i] = raw[u][i][1 / W].v[1 % W];
+                    if (i < W + 2) g2[i] = raw[u][i][2 / W].v[2 % W];
+                    g3[i] = raw[u][i][3 / W].v[3 % W];
+                }
+                T o[4 * W];
+                bwd_radix4_math<T, false>(g0, g1, g2, g3, a, x, lim_p, lim_1, o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) store_cv<T>(orow + j * e * P + x, &o[j * W]);   // skew j*a
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int cc = 0; cc < CPT; ++cc) {
         const int x = (slot + cc * SLOTS) * W;

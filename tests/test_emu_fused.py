@@ -107,6 +107,14 @@ def test_medium_default(emu):
     _check(emu, 512, 1, np.float32)
 
 
+def test_medium_default_f64(emu):
+    # fp64 at a size whose image pass has INTERIOR tiles (every window inside the image): the loader
+    # that fetches the jobs of two rounds before using either (fwd_radix4_from_image_interior), the
+    # paired chunks of the sinogram loader and the unbranched direct first step
+    _check(emu, 512, 1, np.float64)
+    _check(emu, 512, 1, np.float64, "3,6")
+
+
 @pytest.mark.parametrize("n,rows,split", [
     (64, 64, None), (128, 128, None), (256, 256, None), (256, 256, "3,5"), (256, 100, "5,3"),
     (512, 512, None), (512, 512, "3,3,3"), (512, 1, None), (1024, 1024, None),
