@@ -195,6 +195,15 @@ ADRT_HD void fwd_load_wrows(T *buf, const T *src_plane, const TileCtx &c, int ti
             for (int k = 0; k < XW / (32 * L); ++k) v[k] = *reinterpret_cast<const Pack<T> *>(row + gbase + (k * 32 + lane) * L);
 #pragma unroll
             for (int k = 0; k < XW / (32 * L); ++k) *reinterpret_cast<Pack<T> *>(dst + (k * 32 + lane) * L) = v[k];
+        } else if (dbase >= sup || dbase + XW <= 0) {
+            // the whole window lies above the row's support (+0.0) or below offset 0 (the -0.0 sentinels): rows
+            // are shifted by up to a_g * (G - 1) against the tile, so this is a quarter of the rows of a pass with
+            // large block height (26 % of the row pairs of the second forward pass at 2048^2)
+            Pack<T> z;
+#pragma unroll
+            for (int i = 0; i < L; ++i) z.v[i] = dbase >= sup ? T(0.0) : T(-0.0);
+#pragma unroll
+            for (int k = 0; k < XW / (32 * L); ++k) *reinterpret_cast<Pack<T> *>(dst + (k * 32 + lane) * L) = z;
         } else {
 #pragma unroll 4
             for (int k = 0; k < XW / 32; ++k) {
@@ -727,6 +736,18 @@ ADRT_HD void fwd_load_wrows_stage0(T *buf, const T *src_plane, const TileCtx &c,
                 }
                 store_chunk<T>(oe + x, ve);
                 store_chunk<T>(oo + x, vo);
+            }
+        } else if (dB - 1 >= sup || dA + XW <= 0) {
+            // every operand of the pair is a structural +0.0 (above the support; 0 + 0 = +0.0) or a -0.0 sentinel
+            // (below offset 0; -0 + -0 = -0.0): constant rows, no loads (see fwd_load_wrows)
+            constexpr int L = VecOf<T>::L;
+            Pack<T> z;
+#pragma unroll
+            for (int i = 0; i < L; ++i) z.v[i] = dB - 1 >= sup ? T(0.0) : T(-0.0);
+#pragma unroll
+            for (int cc = 0; cc < XW / (32 * L); ++cc) {
+                *reinterpret_cast<Pack<T> *>(oe + (cc * 32 + lane) * L) = z;
+                *reinterpret_cast<Pack<T> *>(oo + (cc * 32 + lane) * L) = z;
             }
         } else {
 #pragma unroll 2
