@@ -10,11 +10,15 @@ rep = sys.argv[1]
 flt = sys.argv[2] if len(sys.argv) > 2 else ""
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 blocks = out.split('"Kernel Name",')
+seen = set()
 for b in blocks[1:]:
     lines = b.split("\n")
     name = lines[0]
     if flt and flt not in name:
         continue
+    if b in seen:   # the source page repeats a kernel's table once per view
+        continue
+    seen.add(b)
     rows = list(csv.reader(io.StringIO("\n".join(lines[1:]))))
     hdr = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}
