@@ -113,6 +113,9 @@ def test_medium_default_f64(emu):
     # paired chunks of the sinogram loader and the unbranched direct first step
     _check(emu, 512, 1, np.float64)
     _check(emu, 512, 1, np.float64, "3,6")
+    # the interior loader at the other two group sizes (default plans reach them from 4096^2 up only)
+    _check(emu, 512, 1, np.float64, "4,5")
+    _check(emu, 512, 1, np.float64, "6,3")
 
 
 @pytest.mark.parametrize("n,rows,split", [
