@@ -55,6 +55,10 @@
 namespace adrt_b200 {
 namespace tile {
 
+#ifndef ADRT_QCOLS_PAIR_F32
+#define ADRT_QCOLS_PAIR_F32 0
+#endif
+
 constexpr int V = 4;                 // consecutive offsets per thread
 constexpr int XW = 256;              // offsets per tile row
 constexpr int NCHUNK = XW / V;       // 64 chunks per row
@@ -1109,8 +1113,9 @@ ADRT_HD void bwd_radix4_from_qcols(T *buf, const T *src_plane, const TileCtx &c,
     // fp64 interior tiles: the pieces of TWO chunks are fetched before either is used (2 x 10 16-byte loads in
     // flight per thread instead of 10, two dependent rounds per tile instead of four: 53 % of the five-stage fp64
     // kernel's stall samples sat in this loader with 2 x 256 threads per SM, profiles/r06_pass_phases_f64.txt);
-    // every chunk of a double tile is live (NCH = SLOTS * CPT, XW + 6 <= pitch), so the pairs need no tests
-    if constexpr (sizeof(T) == 8 && !kMask && !kSub && NCH % SLOTS == 0 && CPT % 2 == 0 && XW + 6 <= P) {
+    // every chunk of a double tile is live (NCH = SLOTS * CPT, XW + 6 <= pitch), so the pairs need no tests.
+    // -DADRT_QCOLS_PAIR_F32=1 (A/B builds, tools/build_variant.sh) pairs the two chunks of the fp32 pass as well.
+    if constexpr ((sizeof(T) == 8 || ADRT_QCOLS_PAIR_F32) && !kMask && !kSub && NCH % SLOTS == 0 && CPT % 2 == 0) {
 #pragma unroll
         for (int cc = 0; cc < CPT; cc += 2) {
             Pack<T> raw[2][W + 3][4 / W];
@@ -1126,6 +1131,9 @@ ADRT_HD void bwd_radix4_from_qcols(T *buf, const T *src_plane, const TileCtx &c,
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int x = (slot + (cc + u) * SLOTS) * W;
+                // floats: the last chunk of a row fails bwd_chunk_ok (its outputs lie beyond the valid region); its
+                // loads above are harmless (an unmasked tile ends 8 offsets before D)
+                if (XW + 6 > P && !bwd_chunk_ok<T>(x, 0, a)) continue;
                 T g0[W], g1[W + 1], g2[W + 2], g3[W + 3];
 #pragma unroll
                 for (int i = 0; i < W + 3; ++i) {

@@ -21,11 +21,14 @@ SO = os.path.join(HERE, "emu", "_build", "libemu.so")
 @pytest.fixture(scope="module")
 def emu():
     deps = [SRC] + [os.path.join(HERE, "..", "adrt_b200", "csrc", f) for f in ("fused_tile.h", "fused_plan.h", "stream_tile.h", "stage_tile.h", "iadrt_tile.h")]
-    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        os.makedirs(os.path.dirname(SO), exist_ok=True)
+    # ADRT_EMU_CXXFLAGS="-DMACRO=1 ...": emulate an A/B build of the tile code (tools/build_variant.sh) instead
+    extra = os.environ.get("ADRT_EMU_CXXFLAGS", "").split()
+    so = SO.replace("libemu.so", "libemu_variant.so") if extra else SO
+    if extra or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
-                        "-Wno-unknown-pragmas", "-o", SO, SRC], check=True)
-    return ctypes.CDLL(SO)
+                        "-Wno-unknown-pragmas"] + extra + ["-o", so, SRC], check=True)
+    return ctypes.CDLL(so)
 
 
 def _run(emu, name, a, out_shape):
